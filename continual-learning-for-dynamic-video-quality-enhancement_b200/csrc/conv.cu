@@ -1,0 +1,50 @@
+// ABI entry points for dense convolution: argument validation + engine dispatch.
+#include "common.cuh"
+#include "conv_internal.cuh"
+
+using namespace nv;
+
+NV_API int nervecl_has_tcgen05(void) { return 1; }
+
+static int validate(const nervecl_conv_params* p) {
+  if (!p || !p->x || !p->w || !p->out) return NERVECL_EINVAL;
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0) return NERVECL_EINVAL;
+  if (p->K != 1 && p->K != 3 && p->K != 7) return NERVECL_EUNSUPPORTED;
+  if (p->ldx < p->Cin || p->ldo < p->Cout || p->w_ld < p->Cin || p->w_rows < p->Cout) return NERVECL_EINVAL;
+  if (p->res && p->ldres < (p->res_channels < p->Cout ? p->res_channels : p->Cout)) return NERVECL_EINVAL;
+  if (p->dtype != NERVECL_F32 && p->dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (p->out_dtype != NERVECL_F32 && p->out_dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (p->dtype == NERVECL_F32 && p->out_dtype == NERVECL_BF16) return NERVECL_EDTYPE;
+  return NERVECL_OK;
+}
+
+NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  int engine = p->engine;
+  if (engine == NERVECL_CONV_AUTO) engine = conv_tc_fwd_supported(*p) ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
+  if (engine == NERVECL_CONV_TC) {
+    if (!conv_tc_fwd_supported(*p)) return NERVECL_EUNSUPPORTED;
+    return conv_tc_fwd(*p, s);
+  }
+  if (engine == NERVECL_CONV_SIMT) return conv_simt_fwd(*p, s);
+  return NERVECL_EINVAL;
+}
+
+NV_API int nervecl_conv2d_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, float* dw,
+                                float* db, int N, int H, int W, int Cin, int Cout, int K, float scale,
+                                int engine, nervecl_stream_t stream) {
+  if (!x || !dy || !dw) return NERVECL_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || ldx < Cin || ldy < Cout) return NERVECL_EINVAL;
+  if (K != 1 && K != 3 && K != 7) return NERVECL_EUNSUPPORTED;
+  cudaStream_t s = as_stream(stream);
+  bool tc_ok = conv_tc_wgrad_supported(x, ldx, dy, ldy, dtype, N, H, W, Cin, Cout, K);
+  if (engine == NERVECL_CONV_AUTO) engine = tc_ok ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
+  if (engine == NERVECL_CONV_TC) {
+    if (!tc_ok) return NERVECL_EUNSUPPORTED;
+    return conv_tc_wgrad(x, ldx, dy, ldy, dw, db, N, H, W, Cin, Cout, K, scale, s);
+  }
+  if (engine == NERVECL_CONV_SIMT) return conv_simt_wgrad(x, ldx, dy, ldy, dtype, dw, db, N, H, W, Cin, Cout, K, scale, s);
+  return NERVECL_EINVAL;
+}

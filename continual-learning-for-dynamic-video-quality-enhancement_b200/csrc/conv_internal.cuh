@@ -1,0 +1,19 @@
+// Internal interface between the conv ABI entry points (conv.cu) and the two engines.
+#pragma once
+#include "common.cuh"
+
+namespace nv {
+
+int conv_simt_fwd(const nervecl_conv_params& a, cudaStream_t s);
+int conv_simt_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, float* dw, float* db,
+                    int N, int H, int W, int Cin, int Cout, int K, float scale, cudaStream_t s);
+
+// tcgen05 / TMEM / TMA implicit GEMM (conv_tc.cu)
+bool conv_tc_fwd_supported(const nervecl_conv_params& a);
+int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s);
+bool conv_tc_wgrad_supported(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H,
+                             int W, int Cin, int Cout, int K);
+int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float* dw, float* db, int N, int H,
+                  int W, int Cin, int Cout, int K, float scale, cudaStream_t s);
+
+}  // namespace nv

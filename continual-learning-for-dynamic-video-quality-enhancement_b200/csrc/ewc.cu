@@ -1,0 +1,269 @@
+// EWC Fisher accumulation / consolidation / quadratic penalty (+ its gradient), and a fused AdamW
+// step, over flat fp32 state.  All kernels are pure streaming (12-20 B per parameter): float4
+// accesses, grid sized to the SM count, one launch per <=32 model tensors (pointers travel in the
+// kernel parameter block, so nothing is copied or retained).
+#include "common.cuh"
+
+using namespace nv;
+
+namespace {
+
+constexpr int MT = 32;  // tensors per launch
+
+struct TensorTable {
+  const float* src[MT];   // per-tensor device pointer (theta_i or grad_i)
+  float* dst[MT];         // per-tensor output pointer (penalty_bwd only)
+  int64_t off[MT];        // offset of tensor i in the flat state
+  int64_t n[MT];
+};
+
+__device__ __forceinline__ bool vec_ok(const void* a, const void* b, const void* c) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
+// fisher[off+k] += scale * g[k]^2
+__global__ void __launch_bounds__(256) fisher_accum_kernel(TensorTable tb, float* __restrict__ fisher, float scale) {
+  const int ti = blockIdx.y;
+  const float* __restrict__ g = tb.src[ti];
+  float* __restrict__ f = fisher + tb.off[ti];
+  const int64_t n = tb.n[ti];
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok(g, f, nullptr)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 fv = reinterpret_cast<float4*>(f)[i];
+      fv.x = fmaf(scale * gv.x, gv.x, fv.x);
+      fv.y = fmaf(scale * gv.y, gv.y, fv.y);
+      fv.z = fmaf(scale * gv.z, gv.z, fv.z);
+      fv.w = fmaf(scale * gv.w, gv.w, fv.w);
+      reinterpret_cast<float4*>(f)[i] = fv;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) f[i] = fmaf(scale * g[i], g[i], f[i]);
+  } else {
+    for (int64_t i = tid; i < n; i += stride) f[i] = fmaf(scale * g[i], g[i], f[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) axpby_kernel(float* __restrict__ v, const float* __restrict__ w, int64_t n,
+                                                    float a, float b) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok(v, w, nullptr)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 x = reinterpret_cast<float4*>(v)[i];
+      if (w) {
+        float4 y = reinterpret_cast<const float4*>(w)[i];
+        x = make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w);
+      } else {
+        x = make_float4(a * x.x, a * x.y, a * x.z, a * x.w);
+      }
+      reinterpret_cast<float4*>(v)[i] = x;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) v[i] = w ? a * v[i] + b * w[i] : a * v[i];
+  } else {
+    for (int64_t i = tid; i < n; i += stride) v[i] = w ? a * v[i] + b * w[i] : a * v[i];
+  }
+}
+
+// *out += coef * sum F*(theta-star)^2
+__global__ void __launch_bounds__(256) penalty_fwd_kernel(TensorTable tb, const float* __restrict__ fisher,
+                                                          const float* __restrict__ star, float coef,
+                                                          float* __restrict__ out) {
+  const int ti = blockIdx.y;
+  const float* __restrict__ th = tb.src[ti];
+  const float* __restrict__ f = fisher + tb.off[ti];
+  const float* __restrict__ st = star + tb.off[ti];
+  const int64_t n = tb.n[ti];
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  if (vec_ok(th, f, st)) {
+    const int64_t n4 = n >> 2;
+    float part = 0.f;
+    int cnt = 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 t = reinterpret_cast<const float4*>(th)[i];
+      float4 fv = reinterpret_cast<const float4*>(f)[i];
+      float4 s = reinterpret_cast<const float4*>(st)[i];
+      float dx = t.x - s.x, dy = t.y - s.y, dz = t.z - s.z, dw = t.w - s.w;
+      part += fv.x * dx * dx + fv.y * dy * dy + fv.z * dz * dz + fv.w * dw * dw;
+      if (++cnt == 16) { acc += part; part = 0.f; cnt = 0; }
+    }
+    acc += part;
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
+      float d = th[i] - st[i];
+      acc += (double)(f[i] * d * d);
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += stride) {
+      float d = th[i] - st[i];
+      acc += (double)(f[i] * d * d);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double part_s[8];
+  if ((threadIdx.x & 31) == 0) part_s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part_s[i];
+    if (t != 0.0) atomicAdd(out, (float)(t * (double)coef));
+  }
+}
+
+// grad[k] += gscale * coef2 * F*(theta-star)
+__global__ void __launch_bounds__(256) penalty_bwd_kernel(TensorTable tb, const float* __restrict__ fisher,
+                                                          const float* __restrict__ star, float coef2,
+                                                          const float* __restrict__ gscale) {
+  const int ti = blockIdx.y;
+  const float* __restrict__ th = tb.src[ti];
+  float* __restrict__ gr = tb.dst[ti];
+  const float* __restrict__ f = fisher + tb.off[ti];
+  const float* __restrict__ st = star + tb.off[ti];
+  const int64_t n = tb.n[ti];
+  const float k = coef2 * (gscale ? __ldg(gscale) : 1.f);
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok(th, f, st) && vec_ok(gr, nullptr, nullptr)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 t = reinterpret_cast<const float4*>(th)[i];
+      float4 fv = reinterpret_cast<const float4*>(f)[i];
+      float4 s = reinterpret_cast<const float4*>(st)[i];
+      float4 g = reinterpret_cast<float4*>(gr)[i];
+      g.x = fmaf(k * fv.x, t.x - s.x, g.x);
+      g.y = fmaf(k * fv.y, t.y - s.y, g.y);
+      g.z = fmaf(k * fv.z, t.z - s.z, g.z);
+      g.w = fmaf(k * fv.w, t.w - s.w, g.w);
+      reinterpret_cast<float4*>(gr)[i] = g;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) gr[i] = fmaf(k * f[i], th[i] - st[i], gr[i]);
+  } else {
+    for (int64_t i = tid; i < n; i += stride) gr[i] = fmaf(k * f[i], th[i] - st[i], gr[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                    float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                    float bc2_sqrt, float gscale) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n; i += stride) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    pi *= (1.f - lr * wd);                      // decoupled weight decay
+    float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+inline dim3 table_grid(const TensorTable& tb, int cnt) {
+  int64_t maxn = 1;
+  for (int i = 0; i < cnt; ++i) maxn = imax(maxn, tb.n[i]);
+  int gx = (int)imax(1, imin(cdiv(maxn, 256 * 4 * 4), (kSMs * 8) / cnt + 1));
+  return dim3(gx, cnt);
+}
+
+}  // namespace
+
+NV_API int nervecl_ewc_fisher_accum(float* fisher, const float* const* grads_host, const int64_t* numel_host,
+                                    int ntensors, float scale, nervecl_stream_t stream) {
+  if (!fisher || !grads_host || !numel_host || ntensors <= 0) return NERVECL_EINVAL;
+  int64_t off = 0;
+  for (int base = 0; base < ntensors; base += MT) {
+    TensorTable tb;
+    int cnt = 0;
+    for (int i = base; i < ntensors && cnt < MT; ++i) {
+      if (numel_host[i] < 0) return NERVECL_EINVAL;
+      if (grads_host[i] && numel_host[i] > 0) {  // a NULL grad (param.grad is None, ewc.py:140) is skipped
+        tb.src[cnt] = grads_host[i];
+        tb.dst[cnt] = nullptr;
+        tb.off[cnt] = off;
+        tb.n[cnt] = numel_host[i];
+        ++cnt;
+      }
+      off += numel_host[i];
+    }
+    if (cnt == 0) continue;
+    fisher_accum_kernel<<<table_grid(tb, cnt), 256, 0, as_stream(stream)>>>(tb, fisher, scale);
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return NERVECL_OK;
+}
+
+NV_API int nervecl_ewc_axpby(float* v, const float* w, int64_t n, float a, float b, nervecl_stream_t stream) {
+  if (!v || n <= 0) return NERVECL_EINVAL;
+  int blocks = (int)imax(1, imin(cdiv(n, 256 * 16), kSMs * 8));
+  axpby_kernel<<<blocks, 256, 0, as_stream(stream)>>>(v, w, n, a, b);
+  return launch_status();
+}
+
+NV_API int nervecl_ewc_penalty_fwd(const float* const* theta_host, const int64_t* numel_host, int ntensors,
+                                   const float* fisher, const float* star, float coef, float* out,
+                                   nervecl_stream_t stream) {
+  if (!theta_host || !numel_host || !fisher || !star || !out || ntensors <= 0) return NERVECL_EINVAL;
+  int64_t off = 0;
+  for (int base = 0; base < ntensors; base += MT) {
+    TensorTable tb;
+    int cnt = 0;
+    for (int i = base; i < ntensors && cnt < MT; ++i) {
+      if (!theta_host[i] || numel_host[i] < 0) return NERVECL_EINVAL;
+      if (numel_host[i] > 0) {
+        tb.src[cnt] = theta_host[i];
+        tb.dst[cnt] = nullptr;
+        tb.off[cnt] = off;
+        tb.n[cnt] = numel_host[i];
+        ++cnt;
+      }
+      off += numel_host[i];
+    }
+    if (cnt == 0) continue;
+    penalty_fwd_kernel<<<table_grid(tb, cnt), 256, 0, as_stream(stream)>>>(tb, fisher, star, coef, out);
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return NERVECL_OK;
+}
+
+NV_API int nervecl_ewc_penalty_bwd(const float* const* theta_host, float* const* grad_host,
+                                   const int64_t* numel_host, int ntensors, const float* fisher, const float* star,
+                                   float coef2, const float* gscale, nervecl_stream_t stream) {
+  if (!theta_host || !grad_host || !numel_host || !fisher || !star || ntensors <= 0) return NERVECL_EINVAL;
+  int64_t off = 0;
+  for (int base = 0; base < ntensors; base += MT) {
+    TensorTable tb;
+    int cnt = 0;
+    for (int i = base; i < ntensors && cnt < MT; ++i) {
+      if (!theta_host[i] || !grad_host[i] || numel_host[i] < 0) return NERVECL_EINVAL;
+      if (numel_host[i] > 0) {
+        tb.src[cnt] = theta_host[i];
+        tb.dst[cnt] = grad_host[i];
+        tb.off[cnt] = off;
+        tb.n[cnt] = numel_host[i];
+        ++cnt;
+      }
+      off += numel_host[i];
+    }
+    if (cnt == 0) continue;
+    penalty_bwd_kernel<<<table_grid(tb, cnt), 256, 0, as_stream(stream)>>>(tb, fisher, star, coef2, gscale);
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return NERVECL_OK;
+}
+
+NV_API int nervecl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              float grad_scale, nervecl_stream_t stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return NERVECL_EINVAL;
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  int blocks = (int)imax(1, imin(cdiv(n, 256 * 4), kSMs * 8));
+  adamw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                      weight_decay, bc1, bc2_sqrt, grad_scale);
+  return launch_status();
+}

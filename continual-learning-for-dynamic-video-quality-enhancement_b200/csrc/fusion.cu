@@ -1,0 +1,634 @@
+// Temporal fusion (softmax over T + weighted sum), CBAM, and the output stage
+// (PixelShuffle + bicubic skip + clamp).  Bandwidth-bound; fp32 math; channel-vector accesses.
+#include "common.cuh"
+
+using namespace nv;
+
+namespace {
+
+constexpr int TMAX = 8;
+
+__device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
+
+__device__ __forceinline__ float group_sum(float v, int cg) {
+  for (int o = cg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float group_max(float v, int cg) {
+  for (int o = cg >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int group_min_i(int v, int cg) {
+  for (int o = cg >> 1; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// thread = (pixel, 8 channels); the cg = C/8 threads of a pixel are adjacent lanes.
+template <typename T>
+__global__ void __launch_bounds__(256)
+tfuse_fwd_kernel(const T* __restrict__ feats, int64_t ldf_, const float* __restrict__ logits,
+                 float* __restrict__ attn, T* __restrict__ out, int64_t ldo, int64_t npix, int Tn, int C) {
+  const int cg = C >> 3;
+  const int64_t total = npix * cg;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(t % cg) << 3;
+    int64_t p = t / cg;
+    float a[TMAX];
+    float m = -INFINITY;
+    for (int i = 0; i < Tn; ++i) { a[i] = __ldg(logits + p * Tn + i); m = fmaxf(m, a[i]); }
+    float s = 0.f;
+    for (int i = 0; i < Tn; ++i) { a[i] = expf(a[i] - m); s += a[i]; }
+    float inv = 1.f / s;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int i = 0; i < Tn; ++i) {
+      a[i] *= inv;
+      f8 v = ld8(feats + p * ldf_ + (int64_t)i * C + c0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(a[i], v.v[k], acc[k]);
+    }
+    if (c0 == 0) for (int i = 0; i < Tn; ++i) attn[p * Tn + i] = a[i];
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+    st8(out + p * ldo + c0, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tfuse_bwd_kernel(const T* __restrict__ feats, int64_t ldf_, const float* __restrict__ attn,
+                 const T* __restrict__ dout, int64_t lddo, const float* __restrict__ nc_bias, int64_t pix_per_image,
+                 T* __restrict__ dfeats, int64_t lddf, float* __restrict__ dlogits, int64_t npix, int Tn, int C) {
+  const int cg = C >> 3;
+  const int64_t total = npix * cg;
+  const int64_t total_pad = cdiv(total, 32) * 32;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = t < total;
+    int c0 = (int)(t % cg) << 3;
+    int64_t p = t / cg;
+    float da[TMAX], a[TMAX];
+    for (int i = 0; i < TMAX; ++i) da[i] = a[i] = 0.f;
+    if (active) {
+      f8 d = ld8(dout + p * lddo + c0);
+      if (nc_bias) {
+        const float* b = nc_bias + (p / pix_per_image) * C + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d.v[k] += __ldg(b + k);
+      }
+      for (int i = 0; i < Tn; ++i) {
+        a[i] = __ldg(attn + p * Tn + i);
+        f8 v = ld8(feats + p * ldf_ + (int64_t)i * C + c0);
+        f8 o;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          o.v[k] = a[i] * d.v[k];
+          s = fmaf(d.v[k], v.v[k], s);
+        }
+        da[i] = s;
+        st8(dfeats + p * lddf + (int64_t)i * C + c0, o);
+      }
+    }
+    for (int i = 0; i < Tn; ++i) da[i] = group_sum(da[i], cg);
+    if (active && c0 == 0) {
+      float dot = 0.f;
+      for (int i = 0; i < Tn; ++i) dot = fmaf(a[i], da[i], dot);
+      for (int i = 0; i < Tn; ++i) dlogits[p * Tn + i] = a[i] * (da[i] - dot);
+    }
+  }
+}
+
+// out[n][c] += scale * sum_p x[n,p,c];  grid = (chunks, N), block = (C/4) x lanes
+template <typename T>
+__global__ void __launch_bounds__(256)
+chan_sum_kernel(const T* __restrict__ x, int64_t ldx, int64_t pix, int C, float scale, float* __restrict__ out) {
+  const int cg = C >> 2;
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const int n = blockIdx.y;
+  const T* xb = x + (int64_t)n * pix * ldx;
+  double s[4] = {0, 0, 0, 0};
+  if (lane < lanes) {
+    float fs[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < pix; p += (int64_t)gridDim.x * lanes) {
+      f4 v = ld4(xb + p * ldx + (g << 2));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fs[k] += v.v[k];
+      if (++cnt == 64) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s[k] += fs[k]; fs[k] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] += fs[k];
+  }
+  extern __shared__ double dred[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) dred[i] = 0.0;
+  __syncthreads();
+  if (lane < lanes) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(&dred[(g << 2) + k], s[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + (int64_t)n * C + i, (float)(dred[i] * (double)scale));
+}
+
+// one block per image
+__global__ void ca_gate_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
+                                   const float* __restrict__ w2, float* __restrict__ hidden,
+                                   float* __restrict__ gate, int C, int R) {
+  extern __shared__ float sh[];  // [R]
+  const int n = blockIdx.x;
+  const float* pl = pool + (int64_t)n * C;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(pl[c], w1[(int64_t)r * C + c], s);
+    s = warp_sum(s);
+    if (lane == 0) { s = fmaxf(s, 0.f); sh[r] = s; hidden[(int64_t)n * R + r] = s; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s = fmaf(sh[r], w2[(int64_t)c * R + r], s);
+    gate[(int64_t)n * C + c] = sigmoidf(s);
+  }
+}
+
+__global__ void ca_gate_bwd_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
+                                   const float* __restrict__ w2, const float* __restrict__ hidden,
+                                   const float* __restrict__ gate, const float* __restrict__ dgate,
+                                   float* __restrict__ dpool, float* __restrict__ dw1, float* __restrict__ dw2,
+                                   int C, int R) {
+  extern __shared__ float sh[];  // ds[C], dh[R]
+  float* ds = sh;
+  float* dh = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float gt = gate[(int64_t)n * C + c];
+    ds[c] = dgate[(int64_t)n * C + c] * gt * (1.f - gt);
+  }
+  __syncthreads();
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    float h = hidden[(int64_t)n * R + r];
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      s = fmaf(ds[c], w2[(int64_t)c * R + r], s);
+      atomicAdd(dw2 + (int64_t)c * R + r, ds[c] * h);
+    }
+    s = warp_sum(s);
+    if (lane == 0) dh[r] = h > 0.f ? s : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float pc = pool[(int64_t)n * C + c];
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) {
+      s = fmaf(dh[r], w1[(int64_t)r * C + c], s);
+      atomicAdd(dw1 + (int64_t)r * C + c, dh[r] * pc);
+    }
+    dpool[(int64_t)n * C + c] = s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_stats_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate, float* __restrict__ stats,
+                  int64_t pix, int64_t npix, int C) {
+  const int cg = C >> 3;
+  const int64_t total = npix * cg;
+  const int64_t total_pad = cdiv(total, 32) * 32;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = t < total;
+    int c0 = (int)(t % cg) << 3;
+    int64_t p = t / cg;
+    float s = 0.f, m = -INFINITY;
+    if (active) {
+      f8 v = ld8(x + p * ldx + c0);
+      const float* g = gate + (p / pix) * C + c0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float xs = v.v[k] * __ldg(g + k);
+        s += xs;
+        m = fmaxf(m, xs);
+      }
+    }
+    s = group_sum(s, cg);
+    m = group_max(m, cg);
+    if (active && c0 == 0) reinterpret_cast<float2*>(stats)[p] = make_float2(s / (float)C, m);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_apply_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+                  const float* __restrict__ stats, const float* __restrict__ w7, float* __restrict__ sgate,
+                  T* __restrict__ out, int64_t ldo, int N, int H, int W, int C) {
+  __shared__ float ws[98];
+  for (int i = threadIdx.x; i < 98; i += blockDim.x) ws[i] = w7[i];
+  __syncthreads();
+  const int cg = C >> 3;
+  const int64_t npix = (int64_t)N * H * W;
+  const int64_t total = npix * cg;
+  const int64_t total_pad = cdiv(total, 32) * 32;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = t < total;
+    int gl = (int)(t % cg);
+    int c0 = gl << 3;
+    int64_t p = t / cg;
+    float z = 0.f;
+    int xx = 0, yy = 0;
+    if (active) {
+      xx = (int)(p % W);
+      yy = (int)((p / W) % H);
+      for (int tap = gl; tap < 49; tap += cg) {
+        int ky = tap / 7, kx = tap % 7;
+        int sy = yy + ky - 3, sx = xx + kx - 3;
+        if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+        float2 st = __ldg(reinterpret_cast<const float2*>(stats) + p + (int64_t)(ky - 3) * W + (kx - 3));
+        z = fmaf(ws[tap], st.x, z);
+        z = fmaf(ws[49 + tap], st.y, z);
+      }
+    }
+    z = group_sum(z, cg);
+    if (active) {
+      float sg = sigmoidf(z);
+      if (c0 == 0) sgate[p] = sg;
+      f8 v = ld8(x + p * ldx + c0);
+      const float* g = gate + (p / ((int64_t)H * W)) * C + c0;
+      f8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = v.v[k] * __ldg(g + k) * sg;
+      st8(out + p * ldo + c0, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_bwd_dz_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+                   const float* __restrict__ sgate, const T* __restrict__ dy, int64_t lddy, float* __restrict__ dz,
+                   int64_t pix, int64_t npix, int C) {
+  const int cg = C >> 3;
+  const int64_t total = npix * cg;
+  const int64_t total_pad = cdiv(total, 32) * 32;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = t < total;
+    int c0 = (int)(t % cg) << 3;
+    int64_t p = t / cg;
+    float s = 0.f;
+    if (active) {
+      f8 v = ld8(x + p * ldx + c0);
+      f8 d = ld8(dy + p * lddy + c0);
+      const float* g = gate + (p / pix) * C + c0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s = fmaf(d.v[k], v.v[k] * __ldg(g + k), s);
+    }
+    s = group_sum(s, cg);
+    if (active && c0 == 0) {
+      float sg = sgate[p];
+      dz[p] = s * sg * (1.f - sg);
+    }
+  }
+}
+
+// 16x16 pixel tile per block.  dstats = transposed 7x7 conv of dz;  dw7 += sum dz * shifted stats.
+__global__ void __launch_bounds__(256)
+cbam_bwd_spatial_kernel(const float* __restrict__ dz, const float* __restrict__ stats, const float* __restrict__ w7,
+                        float* __restrict__ dstats, float* __restrict__ dw7, int H, int W) {
+  constexpr int TS = 16, HS = TS + 6;
+  __shared__ float dz_s[HS][HS];
+  __shared__ float st_s[2][HS][HS];
+  __shared__ float ws[98];
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * TS, x0 = blockIdx.x * TS;
+  const int64_t img = (int64_t)n * H * W;
+  for (int i = threadIdx.x; i < 98; i += blockDim.x) ws[i] = w7[i];
+  for (int e = threadIdx.x; e < HS * HS; e += blockDim.x) {
+    int hy = e / HS, hx = e % HS;
+    int gy = y0 + hy - 3, gx = x0 + hx - 3;
+    float d = 0.f, s0 = 0.f, s1 = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      int64_t q = img + (int64_t)gy * W + gx;
+      d = dz[q];
+      float2 st = reinterpret_cast<const float2*>(stats)[q];
+      s0 = st.x;
+      s1 = st.y;
+    }
+    dz_s[hy][hx] = d;
+    st_s[0][hy][hx] = s0;
+    st_s[1][hy][hx] = s1;
+  }
+  __syncthreads();
+  {
+    int ty = threadIdx.x / TS, tx = threadIdx.x % TS;
+    int gy = y0 + ty, gx = x0 + tx;
+    if (gy < H && gx < W) {
+      // dstats[q][ch] = sum_k w[ch][k] * dz[q - (k - 3)]
+      float a0 = 0.f, a1 = 0.f;
+      for (int ky = 0; ky < 7; ++ky)
+        for (int kx = 0; kx < 7; ++kx) {
+          float d = dz_s[ty + 3 - (ky - 3)][tx + 3 - (kx - 3)];
+          a0 = fmaf(ws[ky * 7 + kx], d, a0);
+          a1 = fmaf(ws[49 + ky * 7 + kx], d, a1);
+        }
+      reinterpret_cast<float2*>(dstats)[img + (int64_t)gy * W + gx] = make_float2(a0, a1);
+    }
+  }
+  if (threadIdx.x < 98) {
+    int ch = threadIdx.x / 49, k = threadIdx.x % 49;
+    int ky = k / 7, kx = k % 7;
+    float a = 0.f;
+    for (int ty = 0; ty < TS; ++ty)
+      for (int tx = 0; tx < TS; ++tx) a = fmaf(dz_s[ty + 3][tx + 3], st_s[ch][ty + ky][tx + kx], a);
+    atomicAdd(dw7 + threadIdx.x, a);
+  }
+}
+
+// grid = (chunks, N)
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_bwd_dx_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+                   const float* __restrict__ sgate, const float* __restrict__ stats,
+                   const float* __restrict__ dstats, const T* __restrict__ dy, int64_t lddy, T* __restrict__ dx,
+                   int64_t lddx, float* __restrict__ dgate, int64_t pix, int C) {
+  const int cg = C >> 3;
+  const int n = blockIdx.y;
+  const int64_t total = pix * cg;
+  const int64_t total_pad = cdiv(total, 32) * 32;
+  const float inv_c = 1.f / (float)C;
+  float gacc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gacc[k] = 0.f;
+  const int c0 = (int)(threadIdx.x % cg) << 3;  // fixed per thread: blockDim and stride are multiples of cg
+  float gt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gt[k] = gate[(int64_t)n * C + c0 + k];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = t < total;
+    int64_t p = (int64_t)n * pix + t / cg;
+    int first = 1 << 30;
+    f8 v, d;
+    float2 st = make_float2(0.f, 0.f), dst = make_float2(0.f, 0.f);
+    float sg = 0.f;
+    if (active) {
+      v = ld8(x + p * ldx + c0);
+      d = ld8(dy + p * lddy + c0);
+      st = reinterpret_cast<const float2*>(stats)[p];
+      dst = reinterpret_cast<const float2*>(dstats)[p];
+      sg = sgate[p];
+#pragma unroll
+      for (int k = 7; k >= 0; --k)
+        if (v.v[k] * gt[k] == st.y) first = c0 + k;
+    }
+    first = group_min_i(first, cg);
+    if (active) {
+      f8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dxs = d.v[k] * sg + dst.x * inv_c + ((c0 + k) == first ? dst.y : 0.f);
+        o.v[k] = dxs * gt[k];
+        gacc[k] = fmaf(dxs, v.v[k], gacc[k]);
+      }
+      st8(dx + p * lddx + c0, o);
+    }
+  }
+  extern __shared__ float red[];  // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(&red[c0 + k], gacc[k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dgate + (int64_t)n * C + i, red[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// output stage
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic1(float x) {  // |x| <= 1, A = -0.75
+  const float A = -0.75f;
+  return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+}
+__device__ __forceinline__ float cubic2(float x) {  // 1 < |x| < 2
+  const float A = -0.75f;
+  return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+
+// ATen upsample_bicubic2d, align_corners=False, scale_factor given (UpSample.h:289-311,413)
+__device__ __forceinline__ float bicubic_sample(const float* __restrict__ img, int64_t sH, int H, int W, int Y,
+                                                int X, float rscale) {
+  float ry = rscale * ((float)Y + 0.5f) - 0.5f;
+  float rx = rscale * ((float)X + 0.5f) - 0.5f;
+  float fy = floorf(ry), fx = floorf(rx);
+  int iy = (int)fy, ix = (int)fx;
+  float ty = ry - fy, tx = rx - fx;
+  float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+  float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int yy = min(max(iy - 1 + i, 0), H - 1);
+    const float* row = img + (int64_t)yy * sH;
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int xx = min(max(ix - 1 + j, 0), W - 1);
+      r += __ldg(row + xx) * cx[j];
+    }
+    acc += r * cy[i];
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256)
+upfinish_fwd_kernel(const float* __restrict__ conv, const float* __restrict__ lr, int64_t sN, int64_t sC,
+                    int64_t sH, float* __restrict__ out, int N, int C, int H, int W, int s, float rscale) {
+  const int HO = H * s, WO = W * s, CS = C * s * s;
+  const int64_t total = (int64_t)N * C * HO * WO;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int X = (int)(i % WO);
+    int64_t r = i / WO;
+    int Y = (int)(r % HO);
+    r /= HO;
+    int c = (int)(r % C);
+    int n = (int)(r / C);
+    int y = Y / s, ii = Y % s, x = X / s, jj = X % s;
+    float v = conv[(((int64_t)n * H + y) * W + x) * CS + c * s * s + ii * s + jj];
+    v += bicubic_sample(lr + n * sN + c * sC, sH, H, W, Y, X, rscale);
+    out[i] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+upfinish_bwd_kernel(const float* __restrict__ conv, const float* __restrict__ lr, int64_t sN, int64_t sC,
+                    int64_t sH, const float* __restrict__ dout, float* __restrict__ dconv, int N, int C, int H,
+                    int W, int s, float rscale) {
+  const int HO = H * s, WO = W * s, CS = C * s * s;
+  const int64_t total = (int64_t)N * C * HO * WO;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int X = (int)(i % WO);
+    int64_t r = i / WO;
+    int Y = (int)(r % HO);
+    r /= HO;
+    int c = (int)(r % C);
+    int n = (int)(r / C);
+    int y = Y / s, ii = Y % s, x = X / s, jj = X % s;
+    int64_t ci = (((int64_t)n * H + y) * W + x) * CS + c * s * s + ii * s + jj;
+    float v = conv[ci] + bicubic_sample(lr + n * sN + c * sC, sH, H, W, Y, X, rscale);
+    dconv[ci] = (v >= 0.f && v <= 1.f) ? dout[i] : 0.f;
+  }
+}
+
+inline int ew_blocks(int64_t work) { return (int)imax(1, imin(cdiv(work, 256), kSMs * 16)); }
+inline bool group_ok(int C) {
+  int cg = C >> 3;
+  return !(C & 7) && cg >= 1 && cg <= 32 && !(cg & (cg - 1));
+}
+
+}  // namespace
+
+NV_API int nervecl_tfuse_fwd(const void* feats, int64_t ldf, const float* logits, float* attn, void* out,
+                             int64_t ldo, int dtype, int64_t npix, int T, int C, nervecl_stream_t stream) {
+  if (!feats || !logits || !attn || !out || npix <= 0 || T <= 0 || T > TMAX || C <= 0) return NERVECL_EINVAL;
+  if ((C & 7) || (ldf & 7) || (ldo & 7)) return NERVECL_EALIGN;
+  NV_DISPATCH_DTYPE(dtype, E, (tfuse_fwd_kernel<E><<<ew_blocks(npix * (C >> 3)), 256, 0, as_stream(stream)>>>(
+                                  (const E*)feats, ldf, logits, attn, (E*)out, ldo, npix, T, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_tfuse_bwd(const void* feats, int64_t ldf, const float* attn, const void* dout, int64_t lddo,
+                             const float* nc_bias, int64_t pix_per_image, void* dfeats, int64_t lddf,
+                             float* dlogits, int dtype, int64_t npix, int T, int C, nervecl_stream_t stream) {
+  if (!feats || !attn || !dout || !dfeats || !dlogits || npix <= 0 || T <= 0 || T > TMAX || C <= 0)
+    return NERVECL_EINVAL;
+  if (nc_bias && pix_per_image <= 0) return NERVECL_EINVAL;
+  if (!group_ok(C)) return NERVECL_EUNSUPPORTED;
+  if ((ldf & 7) || (lddo & 7) || (lddf & 7)) return NERVECL_EALIGN;
+  NV_DISPATCH_DTYPE(dtype, E, (tfuse_bwd_kernel<E><<<ew_blocks(npix * (C >> 3)), 256, 0, as_stream(stream)>>>(
+                                  (const E*)feats, ldf, attn, (const E*)dout, lddo, nc_bias, pix_per_image,
+                                  (E*)dfeats, lddf, dlogits, npix, T, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_chan_sum(const void* x, int64_t ldx, int dtype, int N, int64_t pix_per_image, int C,
+                            float scale, float* out, nervecl_stream_t stream) {
+  if (!x || !out || N <= 0 || pix_per_image <= 0 || C <= 0) return NERVECL_EINVAL;
+  if ((C & 3) || (ldx & 3) || C > 1024) return NERVECL_EALIGN;
+  int lanes = 256 / (C >> 2);
+  int chunks = (int)imax(1, imin(cdiv(pix_per_image, lanes * 16), (kSMs * 8) / N + 1));
+  dim3 grid(chunks, N);
+  NV_DISPATCH_DTYPE(dtype, E, (chan_sum_kernel<E><<<grid, 256, C * sizeof(double), as_stream(stream)>>>(
+                                  (const E*)x, ldx, pix_per_image, C, scale, out)));
+  return launch_status();
+}
+
+NV_API int nervecl_ca_gate_fwd(const float* pool, const float* w1, const float* w2, float* hidden, float* gate,
+                               int N, int C, int R, nervecl_stream_t stream) {
+  if (!pool || !w1 || !w2 || !hidden || !gate || N <= 0 || C <= 0 || R <= 0) return NERVECL_EINVAL;
+  ca_gate_fwd_kernel<<<N, 128, R * sizeof(float), as_stream(stream)>>>(pool, w1, w2, hidden, gate, C, R);
+  return launch_status();
+}
+
+NV_API int nervecl_ca_gate_bwd(const float* pool, const float* w1, const float* w2, const float* hidden,
+                               const float* gate, const float* dgate, float* dpool, float* dw1, float* dw2, int N,
+                               int C, int R, nervecl_stream_t stream) {
+  if (!pool || !w1 || !w2 || !hidden || !gate || !dgate || !dpool || !dw1 || !dw2 || N <= 0 || C <= 0 || R <= 0)
+    return NERVECL_EINVAL;
+  ca_gate_bwd_kernel<<<N, 128, (C + R) * sizeof(float), as_stream(stream)>>>(pool, w1, w2, hidden, gate, dgate,
+                                                                               dpool, dw1, dw2, C, R);
+  return launch_status();
+}
+
+NV_API int nervecl_cbam_stats_fwd(const void* x, int64_t ldx, const float* gate, float* stats, int dtype, int N,
+                                  int64_t pix_per_image, int C, nervecl_stream_t stream) {
+  if (!x || !gate || !stats || N <= 0 || pix_per_image <= 0) return NERVECL_EINVAL;
+  if (!group_ok(C)) return NERVECL_EUNSUPPORTED;
+  if (ldx & 7) return NERVECL_EALIGN;
+  int64_t npix = (int64_t)N * pix_per_image;
+  NV_DISPATCH_DTYPE(dtype, E, (cbam_stats_kernel<E><<<ew_blocks(npix * (C >> 3)), 256, 0, as_stream(stream)>>>(
+                                  (const E*)x, ldx, gate, stats, pix_per_image, npix, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_cbam_apply_fwd(const void* x, int64_t ldx, const float* gate, const float* stats,
+                                  const float* w7, float* sgate, void* out, int64_t ldo, int dtype, int N, int H,
+                                  int W, int C, nervecl_stream_t stream) {
+  if (!x || !gate || !stats || !w7 || !sgate || !out || N <= 0 || H <= 0 || W <= 0) return NERVECL_EINVAL;
+  if (!group_ok(C)) return NERVECL_EUNSUPPORTED;
+  if ((ldx & 7) || (ldo & 7)) return NERVECL_EALIGN;
+  int64_t npix = (int64_t)N * H * W;
+  NV_DISPATCH_DTYPE(dtype, E, (cbam_apply_kernel<E><<<ew_blocks(npix * (C >> 3)), 256, 0, as_stream(stream)>>>(
+                                  (const E*)x, ldx, gate, stats, w7, sgate, (E*)out, ldo, N, H, W, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_cbam_bwd_dz(const void* x, int64_t ldx, const float* gate, const float* sgate, const void* dy,
+                               int64_t lddy, float* dz, int dtype, int N, int64_t pix_per_image, int C,
+                               nervecl_stream_t stream) {
+  if (!x || !gate || !sgate || !dy || !dz || N <= 0 || pix_per_image <= 0) return NERVECL_EINVAL;
+  if (!group_ok(C)) return NERVECL_EUNSUPPORTED;
+  if ((ldx & 7) || (lddy & 7)) return NERVECL_EALIGN;
+  int64_t npix = (int64_t)N * pix_per_image;
+  NV_DISPATCH_DTYPE(dtype, E, (cbam_bwd_dz_kernel<E><<<ew_blocks(npix * (C >> 3)), 256, 0, as_stream(stream)>>>(
+                                  (const E*)x, ldx, gate, sgate, (const E*)dy, lddy, dz, pix_per_image, npix, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_cbam_bwd_spatial(const float* dz, const float* stats, const float* w7, float* dstats,
+                                    float* dw7, int N, int H, int W, nervecl_stream_t stream) {
+  if (!dz || !stats || !w7 || !dstats || !dw7 || N <= 0 || H <= 0 || W <= 0) return NERVECL_EINVAL;
+  dim3 grid((unsigned)cdiv(W, 16), (unsigned)cdiv(H, 16), N);
+  cbam_bwd_spatial_kernel<<<grid, 256, 0, as_stream(stream)>>>(dz, stats, w7, dstats, dw7, H, W);
+  return launch_status();
+}
+
+NV_API int nervecl_cbam_bwd_dx(const void* x, int64_t ldx, const float* gate, const float* sgate,
+                               const float* stats, const float* dstats, const void* dy, int64_t lddy, void* dx,
+                               int64_t lddx, float* dgate, int dtype, int N, int64_t pix_per_image, int C,
+                               nervecl_stream_t stream) {
+  if (!x || !gate || !sgate || !stats || !dstats || !dy || !dx || !dgate || N <= 0 || pix_per_image <= 0)
+    return NERVECL_EINVAL;
+  if (!group_ok(C)) return NERVECL_EUNSUPPORTED;
+  if ((ldx & 7) || (lddy & 7) || (lddx & 7)) return NERVECL_EALIGN;
+  int chunks = (int)imax(1, imin(cdiv(pix_per_image * (C >> 3), 256 * 4), (kSMs * 8) / N + 1));
+  dim3 grid(chunks, N);
+  NV_DISPATCH_DTYPE(dtype, E, (cbam_bwd_dx_kernel<E><<<grid, 256, C * sizeof(float), as_stream(stream)>>>(
+                                  (const E*)x, ldx, gate, sgate, stats, dstats, (const E*)dy, lddy, (E*)dx, lddx,
+                                  dgate, pix_per_image, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_upfinish_fwd(const float* conv_out, const float* lr, int64_t sN, int64_t sC, int64_t sH,
+                                float* out, int N, int C, int H, int W, int s, nervecl_stream_t stream) {
+  if (!conv_out || !lr || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0 || s < 1 || s > 8) return NERVECL_EINVAL;
+  int64_t total = (int64_t)N * C * H * s * W * s;
+  float rscale = (float)(1.0 / (double)s);
+  upfinish_fwd_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(conv_out, lr, sN, sC, sH, out, N, C, H, W, s,
+                                                                       rscale);
+  return launch_status();
+}
+
+NV_API int nervecl_upfinish_bwd(const float* conv_out, const float* lr, int64_t sN, int64_t sC, int64_t sH,
+                                const float* dout, float* dconv, int N, int C, int H, int W, int s,
+                                nervecl_stream_t stream) {
+  if (!conv_out || !lr || !dout || !dconv || N <= 0 || C <= 0 || H <= 0 || W <= 0 || s < 1 || s > 8)
+    return NERVECL_EINVAL;
+  int64_t total = (int64_t)N * C * H * s * W * s;
+  float rscale = (float)(1.0 / (double)s);
+  upfinish_bwd_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(conv_out, lr, sN, sC, sH, dout, dconv, N, C,
+                                                                       H, W, s, rscale);
+  return launch_status();
+}

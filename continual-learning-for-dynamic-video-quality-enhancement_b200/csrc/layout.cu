@@ -1,0 +1,310 @@
+// Layout conversion, weight packing and small elementwise gradient-routing kernels.
+#include "common.cuh"
+
+using namespace nv;
+
+NV_API int nervecl_abi_version(void) { return 1; }
+
+NV_API const char* nervecl_error_string(int code) {
+  switch (code) {
+    case NERVECL_OK: return "ok";
+    case NERVECL_EINVAL: return "invalid argument (shape or null pointer)";
+    case NERVECL_EALIGN: return "misaligned pointer or pitch";
+    case NERVECL_EDTYPE: return "unsupported dtype";
+    case NERVECL_EUNSUPPORTED: return "shape not supported by the requested engine";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown nervecl error";
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// (B,T,C,H,W) strided fp32 -> [T][B][H][W][C]
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_frames_kernel(const float* __restrict__ src, int64_t sB, int64_t sT, int64_t sC,
+                                   int64_t sH, T* __restrict__ dst, int B, int Tn, int C, int H, int W) {
+  int64_t total = (int64_t)Tn * B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    int64_t r = i / W;
+    int y = (int)(r % H);
+    r /= H;
+    int b = (int)(r % B);
+    int t = (int)(r / B);
+    const float* s = src + b * sB + t * sT + y * sH + x;
+    T* d = dst + i * C;
+    for (int c = 0; c < C; ++c) stf(d + c, __ldg(s + c * sC));
+  }
+}
+
+NV_API int nervecl_pack_frames(const float* src, int64_t sB, int64_t sT, int64_t sC, int64_t sH,
+                               void* dst, int dtype, int B, int T, int C, int H, int W,
+                               nervecl_stream_t stream) {
+  if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || H <= 0 || W <= 0) return NERVECL_EINVAL;
+  int64_t total = (int64_t)T * B * H * W;
+  int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
+  NV_DISPATCH_DTYPE(dtype, E, (pack_frames_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  src, sB, sT, sC, sH, (E*)dst, B, T, C, H, W)));
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------
+// NHWC slice <-> NCHW fp32 via a 32x32 shared-memory transpose over (pixel, channel)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int64_t ld, float* __restrict__ dst,
+                                    int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int64_t p0 = (int64_t)blockIdx.x * 32;
+  int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t p = p0 + i;
+    int c = c0 + threadIdx.x;
+    if (p < HW && c < C) tile[i][threadIdx.x] = ldf(src + (n * HW + p) * ld + c);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    int64_t p = p0 + threadIdx.x;
+    if (p < HW && c < C) dst[((int64_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t ld,
+                                    int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int64_t p0 = (int64_t)blockIdx.x * 32;
+  int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    int64_t p = p0 + threadIdx.x;
+    if (p < HW && c < C) tile[i][threadIdx.x] = __ldg(src + ((int64_t)n * C + c) * HW + p);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t p = p0 + i;
+    int c = c0 + threadIdx.x;
+    if (p < HW && c < C) stf(dst + (n * HW + p) * ld + c, tile[threadIdx.x][i]);
+  }
+}
+
+NV_API int nervecl_nhwc_to_nchw(const void* src, int64_t ld, int dtype, float* dst, int N, int C, int H,
+                                int W, nervecl_stream_t stream) {
+  if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || ld < C) return NERVECL_EINVAL;
+  int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 32), N), block(32, 8);
+  NV_DISPATCH_DTYPE(dtype, E, (nhwc_to_nchw_kernel<E><<<grid, block, 0, as_stream(stream)>>>(
+                                  (const E*)src, ld, dst, C, HW)));
+  return launch_status();
+}
+
+NV_API int nervecl_nchw_to_nhwc(const float* src, void* dst, int64_t ld, int dtype, int N, int C, int H,
+                                int W, nervecl_stream_t stream) {
+  if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || ld < C) return NERVECL_EINVAL;
+  int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)cdiv(HW, 32), (unsigned)cdiv(C, 32), N), block(32, 8);
+  NV_DISPATCH_DTYPE(dtype, E, (nchw_to_nhwc_kernel<E><<<grid, block, 0, as_stream(stream)>>>(
+                                  src, (E*)dst, ld, C, HW)));
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------
+// OIHW fp32 -> [tap][O][Ipad]   (or the transposed / 180-degree-rotated operator)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int O, int I, int KK,
+                                   int nrows, int cols, int rows, int pad_to, int transpose_flip) {
+  // dst[tap][r][c], r < rows (= rows_pad), c < pad_to (= cols_pad); data where r < nrows, c < cols
+  int64_t total = (int64_t)KK * rows * pad_to;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % pad_to);
+    int64_t r2 = i / pad_to;
+    int r = (int)(r2 % rows);
+    int tap = (int)(r2 / rows);
+    float v = 0.f;
+    if (c < cols && r < nrows) {
+      if (!transpose_flip) {
+        v = __ldg(w + ((int64_t)r * I + c) * KK + tap);  // o = r, i = c
+      } else {
+        v = __ldg(w + ((int64_t)c * I + r) * KK + (KK - 1 - tap));  // o = c, i = r, rotated tap
+      }
+    }
+    stf(dst + i, v);
+  }
+}
+
+NV_API int nervecl_pack_conv_weight(const float* w_oihw, void* dst, int dtype, int O, int I, int KH, int KW,
+                                    int rows_pad, int cols_pad, int transpose_flip, nervecl_stream_t stream) {
+  if (!w_oihw || !dst || O <= 0 || I <= 0 || KH <= 0 || KW != KH) return NERVECL_EINVAL;
+  int nrows = transpose_flip ? I : O;
+  int cols = transpose_flip ? O : I;
+  if (cols_pad < cols || rows_pad < nrows) return NERVECL_EINVAL;
+  int KK = KH * KW;
+  int rows = rows_pad, pad_to = cols_pad;
+  int64_t total = (int64_t)KK * rows * pad_to;
+  int blocks = (int)imin(cdiv(total, 256), kSMs * 8);
+  NV_DISPATCH_DTYPE(dtype, E, (pack_weight_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  w_oihw, (E*)dst, O, I, KK, nrows, cols, rows, pad_to, transpose_flip)));
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------
+// out = (acc ? out : 0) + alpha * x
+// ---------------------------------------------------------------------------------------
+template <typename TX, typename TO>
+__global__ void axpy_kernel(const TX* __restrict__ x, int64_t ldx, TO* __restrict__ out, int64_t ldo,
+                            int64_t npix, int C, float alpha, int accumulate) {
+  int c4n = C >> 2;
+  int64_t total = npix * c4n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / c4n;
+    int c = (int)(i % c4n) << 2;
+    f4 a = ld4(x + p * ldx + c);
+    f4 o;
+    if (accumulate) {
+      o = ld4(out + p * ldo + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o.v[k] += alpha * a.v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o.v[k] = alpha * a.v[k];
+    }
+    st4(out + p * ldo + c, o);
+  }
+}
+
+template <typename TX, typename TO>
+__global__ void axpy_scalar_kernel(const TX* __restrict__ x, int64_t ldx, TO* __restrict__ out, int64_t ldo,
+                                   int64_t npix, int C, float alpha, int accumulate) {
+  int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C;
+    int c = (int)(i % C);
+    float v = alpha * ldf(x + p * ldx + c);
+    if (accumulate) v += ldf(const_cast<const TO*>(out) + p * ldo + c);
+    stf(out + p * ldo + c, v);
+  }
+}
+
+NV_API int nervecl_axpy(const void* x, int64_t ldx, int x_dtype, void* out, int64_t ldo, int out_dtype,
+                        int64_t npix, int C, float alpha, int accumulate, nervecl_stream_t stream) {
+  if (!x || !out || npix <= 0 || C <= 0) return NERVECL_EINVAL;
+  const bool vec = !((C & 3) || (ldx & 3) || (ldo & 3) || !aligned(x, 16) || !aligned(out, 16));
+  int64_t total = vec ? npix * (C >> 2) : npix * C;
+  int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
+  cudaStream_t s = as_stream(stream);
+#define LAUNCH(TX, TO)                                                                                          \
+  do {                                                                                                          \
+    if (vec)                                                                                                    \
+      axpy_kernel<TX, TO><<<blocks, 256, 0, s>>>((const TX*)x, ldx, (TO*)out, ldo, npix, C, alpha, accumulate); \
+    else                                                                                                        \
+      axpy_scalar_kernel<TX, TO><<<blocks, 256, 0, s>>>((const TX*)x, ldx, (TO*)out, ldo, npix, C, alpha,       \
+                                                        accumulate);                                            \
+  } while (0)
+  if (x_dtype == NERVECL_F32 && out_dtype == NERVECL_F32) LAUNCH(float, float);
+  else if (x_dtype == NERVECL_F32 && out_dtype == NERVECL_BF16) LAUNCH(float, bf16);
+  else if (x_dtype == NERVECL_BF16 && out_dtype == NERVECL_F32) LAUNCH(bf16, float);
+  else if (x_dtype == NERVECL_BF16 && out_dtype == NERVECL_BF16) LAUNCH(bf16, bf16);
+  else return NERVECL_EDTYPE;
+#undef LAUNCH
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------
+// out = dy * [(y - y_sub) > 0]
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ y, int64_t ldy,
+                                const T* __restrict__ ysub, int64_t ldys, T* __restrict__ out, int64_t ldo,
+                                int64_t npix, int C) {
+  int c4n = C >> 2;
+  int64_t total = npix * c4n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / c4n;
+    int c = (int)(i % c4n) << 2;
+    f4 g = ld4(dy + p * lddy + c);
+    f4 v = ld4(y + p * ldy + c);
+    if (ysub) {
+      f4 s = ld4(ysub + p * ldys + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v.v[k] -= s.v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g.v[k] = v.v[k] > 0.f ? g.v[k] : 0.f;
+    st4(out + p * ldo + c, g);
+  }
+}
+
+NV_API int nervecl_relu_bwd(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* y_sub,
+                            int64_t ldys, void* out, int64_t ldo, int dtype, int64_t npix, int C,
+                            nervecl_stream_t stream) {
+  if (!dy || !y || !out || npix <= 0 || C <= 0) return NERVECL_EINVAL;
+  if ((C & 3) || (lddy & 3) || (ldy & 3) || (ldo & 3) || (y_sub && (ldys & 3))) return NERVECL_EALIGN;
+  int64_t total = npix * (C >> 2);
+  int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
+  NV_DISPATCH_DTYPE(dtype, E, (relu_bwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  (const E*)dy, lddy, (const E*)y, ldy, (const E*)y_sub, ldys, (E*)out, ldo,
+                                  npix, C)));
+  return launch_status();
+}
+
+NV_API int nervecl_fill_zero(void* p, size_t bytes, nervecl_stream_t stream) {
+  if (!p) return NERVECL_EINVAL;
+  if (bytes == 0) return NERVECL_OK;
+  cudaError_t e = cudaMemsetAsync(p, 0, bytes, as_stream(stream));
+  return e == cudaSuccess ? NERVECL_OK : (int)e;
+}
+
+// ---------------------------------------------------------------------------------------
+// MSE forward + backward in one pass
+// ---------------------------------------------------------------------------------------
+__global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dgrad,
+                           float* __restrict__ loss, int64_t n, float scale) {
+  double acc = 0.0;
+  int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = reinterpret_cast<const float4*>(a)[i];
+    float4 y = reinterpret_cast<const float4*>(b)[i];
+    float4 d = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+    float s = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+    acc += (double)s;
+    if (dgrad) {
+      float k = 2.f * scale;
+      reinterpret_cast<float4*>(dgrad)[i] = make_float4(k * d.x, k * d.y, k * d.z, k * d.w);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = n4 << 2; i < n; ++i) {
+      float d = a[i] - b[i];
+      acc += (double)d * d;
+      if (dgrad) dgrad[i] = 2.f * scale * d;
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double part[8];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) part[w] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    atomicAdd(loss, (float)(t * (double)scale));
+  }
+}
+
+NV_API int nervecl_mse_fwd_bwd(const float* a, const float* b, float* dgrad, float* loss, int64_t n,
+                               float scale, nervecl_stream_t stream) {
+  if (!a || !b || !loss || n <= 0) return NERVECL_EINVAL;
+  if (!aligned(a, 16) || !aligned(b, 16) || (dgrad && !aligned(dgrad, 16))) return NERVECL_EALIGN;
+  int blocks = (int)imin(cdiv(n >> 2, 256) + 1, kSMs * 8);
+  mse_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, b, dgrad, loss, n, scale);
+  return launch_status();
+}

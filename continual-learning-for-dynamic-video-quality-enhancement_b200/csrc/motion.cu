@@ -1,0 +1,337 @@
+// Motion estimation / compensation kernels: 81-displacement correlation and the flow warp.
+#include "common.cuh"
+
+using namespace nv;
+
+namespace {
+
+constexpr int RAD = 4, ND = 9, NDISP = 81;
+
+// ---------------------------------------------------------------------------------------
+// correlation forward.  block = 32 pixels (one row strip) x 9 displacement rows; a thread
+// computes the 9 horizontal displacements of its (pixel, dy) pair, streaming channels 8 at a time.
+// Results are staged in shared memory and written as full pixel rows (coalesced).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(288)
+corr_fwd_kernel(const T* __restrict__ x1, int64_t ld1, const T* __restrict__ x2, int64_t ld2,
+                T* __restrict__ out, int64_t ldo, int N, int H, int W, int C, int cout_pad) {
+  extern __shared__ float stage[];  // [32][cout_pad]
+  const int strips = (W + 31) / 32;
+  const int64_t row = blockIdx.x / strips;  // n*H + y
+  const int x0 = (int)(blockIdx.x % strips) * 32;
+  const int y = (int)(row % H);
+  const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+  const int x = x0 + lane;
+  const int sy = y + i - RAD;
+  float acc[ND];
+#pragma unroll
+  for (int j = 0; j < ND; ++j) acc[j] = 0.f;
+  if (x < W && sy >= 0 && sy < H) {
+    const T* a = x1 + (row * W + x) * ld1;
+    const T* brow = x2 + ((row + (i - RAD)) * W) * ld2;
+    for (int c = 0; c < C; c += 8) {
+      f8 av = ld8(a + c);
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        int sx = x + j - RAD;
+        if (sx < 0 || sx >= W) continue;
+        f8 bv = ld8(brow + (int64_t)sx * ld2 + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j] = fmaf(av.v[k], bv.v[k], acc[j]);
+      }
+    }
+  }
+  const float inv_c = 1.f / (float)C;
+#pragma unroll
+  for (int j = 0; j < ND; ++j) stage[lane * cout_pad + i * ND + j] = acc[j] * inv_c;
+  for (int e = threadIdx.x; e < 32 * (cout_pad - NDISP); e += blockDim.x) {
+    int p = e / (cout_pad - NDISP), c = NDISP + e % (cout_pad - NDISP);
+    stage[p * cout_pad + c] = 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * cout_pad; e += blockDim.x) {
+    int p = e / cout_pad, c = e % cout_pad;
+    if (x0 + p < W) stf(out + (row * W + x0 + p) * ldo + c, stage[e]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// correlation backward.  thread = (pixel, 8 channels).
+//   dx1[p,c] = 1/C sum_d g[p,d]   * x2[p+d,c]
+//   dx2[q,c] = 1/C sum_d g[q-d,d] * x1[q-d,c]
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+corr_bwd_kernel(const T* __restrict__ x1, int64_t ld1, const T* __restrict__ x2, int64_t ld2,
+                const T* __restrict__ g, int64_t ldg, T* __restrict__ dx1, int64_t lddx1, int acc1,
+                T* __restrict__ dx2, int64_t lddx2, int acc2, int N, int H, int W, int C) {
+  const int cg = C >> 3;
+  const int64_t total = (int64_t)N * H * W * cg;
+  const float inv_c = 1.f / (float)C;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(t % cg) << 3;
+    int64_t p = t / cg;
+    int x = (int)(p % W), y = (int)((p / W) % H);
+    float a1[8], a2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
+    for (int i = 0; i < ND; ++i) {
+      int dy = i - RAD;
+      for (int j = 0; j < ND; ++j) {
+        int dx = j - RAD;
+        int d = i * ND + j;
+        // dx1: neighbour p+d of x2
+        int sy = y + dy, sx = x + dx;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          float gv = ldf(g + p * ldg + d);
+          f8 v = ld8(x2 + (p + (int64_t)dy * W + dx) * ld2 + c0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a1[k] = fmaf(gv, v.v[k], a1[k]);
+        }
+        // dx2: source pixel q-d of x1
+        int ty = y - dy, tx = x - dx;
+        if (ty >= 0 && ty < H && tx >= 0 && tx < W) {
+          int64_t q = p - (int64_t)dy * W - dx;
+          float gv = ldf(g + q * ldg + d);
+          f8 v = ld8(x1 + q * ld1 + c0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a2[k] = fmaf(gv, v.v[k], a2[k]);
+        }
+      }
+    }
+    f8 o1, o2;
+    if (acc1) o1 = ld8(dx1 + p * lddx1 + c0); else { for (int k = 0; k < 8; ++k) o1.v[k] = 0.f; }
+    if (acc2) o2 = ld8(dx2 + p * lddx2 + c0); else { for (int k = 0; k < 8; ++k) o2.v[k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o1.v[k] += a1[k] * inv_c;
+      o2.v[k] += a2[k] * inv_c;
+    }
+    st8(dx1 + p * lddx1 + c0, o1);
+    st8(dx2 + p * lddx2 + c0, o2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// warp.  Coordinates replay the reference's fp32 op sequence with explicit round-to-nearest
+// intrinsics (no FMA contraction, no re-association) -> neighbour indices bit-identical to ATen.
+// ---------------------------------------------------------------------------------------
+struct WarpCoord {
+  float ix, iy;     // un-normalised sample position
+  float x0f, y0f;   // floor
+  int x0, y0;
+};
+
+__device__ __forceinline__ float unnorm_coord(int pos, float flow, int size, float inv, int div_mode) {
+  float g = __fadd_rn((float)pos, flow);               // grid + flow            (super_resolution.py:126)
+  g = __fmul_rn(2.0f, g);                              // 2.0 * grid             (:129)
+  g = div_mode ? __fdiv_rn(g, (float)(size - 1))       // / (W-1): ATen-CPU divides,
+               : __fmul_rn(g, inv);                    //          ATen-CUDA multiplies by 1/(W-1)
+  g = __fsub_rn(g, 1.0f);                              // - 1.0
+  // grid_sampler_unnormalize(align_corners=True): ((coord + 1) / 2) * (size - 1)
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+}
+
+__device__ __forceinline__ WarpCoord warp_coord(int x, int y, float fx, float fy, int W, int H, float inv_w,
+                                                float inv_h, int div_mode) {
+  WarpCoord c;
+  c.ix = unnorm_coord(x, fx, W, inv_w, div_mode);
+  c.iy = unnorm_coord(y, fy, H, inv_h, div_mode);
+  c.x0f = floorf(c.ix);
+  c.y0f = floorf(c.iy);
+  // clamp before the int conversion so huge flows cannot overflow (they are out of bounds anyway)
+  c.x0 = (int)fminf(fmaxf(c.x0f, -2.f), (float)W + 1.f);
+  c.y0 = (int)fminf(fmaxf(c.y0f, -2.f), (float)H + 1.f);
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+warp_fwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow, T* __restrict__ out,
+                int64_t ldo, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode,
+                int32_t* __restrict__ idx_out) {
+  const int cg = C >> 3;
+  const int64_t total = (int64_t)N * H * W * cg;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(t % cg) << 3;
+    int64_t p = t / cg;
+    int x = (int)(p % W), y = (int)((p / W) % H);
+    int64_t img = p - (int64_t)y * W - x;  // n*H*W
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+    WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
+    if (idx_out && c0 == 0) {
+      idx_out[p * 2] = (int)c.x0f;
+      idx_out[p * 2 + 1] = (int)c.y0f;
+    }
+    float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
+    float wnw = (x1f - c.ix) * (y1f - c.iy);
+    float wne = (c.ix - c.x0f) * (y1f - c.iy);
+    float wsw = (x1f - c.ix) * (c.iy - c.y0f);
+    float wse = (c.ix - c.x0f) * (c.iy - c.y0f);
+    bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
+    bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const T* base = feat + (img + (int64_t)c.y0 * W + c.x0) * ldf_ + c0;
+    if (yin0 && xin0) { f8 v = ld8(base);                        for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wnw, acc[k]); }
+    if (yin0 && xin1) { f8 v = ld8(base + ldf_);                 for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wne, acc[k]); }
+    if (yin1 && xin0) { f8 v = ld8(base + (int64_t)W * ldf_);    for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wsw, acc[k]); }
+    if (yin1 && xin1) { f8 v = ld8(base + (int64_t)(W + 1) * ldf_); for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wse, acc[k]); }
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+    st8(out + p * ldo + c0, o);
+  }
+}
+
+// blockDim multiple of 32; the cg (= C/8, power of two <= 32) threads of one pixel are adjacent
+// lanes, so the flow gradient is reduced with xor-shuffles.
+template <typename T>
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow,
+                const T* __restrict__ dout, int64_t lddo, float* __restrict__ dfeat, int64_t lddf,
+                float* __restrict__ dflow, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode) {
+  const int cg = C >> 3;
+  const int64_t total = (int64_t)N * H * W * cg;
+  const int64_t total_pad = cdiv(total, 32) * 32;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    float gix = 0.f, giy = 0.f;
+    int64_t p = t / cg;
+    const bool active = t < total;
+    if (active) {
+      int c0 = (int)(t % cg) << 3;
+      int x = (int)(p % W), y = (int)((p / W) % H);
+      int64_t img = p - (int64_t)y * W - x;
+      float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+      WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
+      float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
+      float wnw = (x1f - c.ix) * (y1f - c.iy);
+      float wne = (c.ix - c.x0f) * (y1f - c.iy);
+      float wsw = (x1f - c.ix) * (c.iy - c.y0f);
+      float wse = (c.ix - c.x0f) * (c.iy - c.y0f);
+      bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
+      bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
+      f8 g = ld8(dout + p * lddo + c0);
+      int64_t q = img + (int64_t)c.y0 * W + c.x0;
+      const T* fb = feat + q * ldf_ + c0;
+      float* db = dfeat + q * lddf + c0;
+      if (yin0 && xin0) {
+        f8 v = ld8(fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          atomicAdd(db + k, wnw * g.v[k]);
+          gix -= v.v[k] * (y1f - c.iy) * g.v[k];
+          giy -= v.v[k] * (x1f - c.ix) * g.v[k];
+        }
+      }
+      if (yin0 && xin1) {
+        f8 v = ld8(fb + ldf_);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          atomicAdd(db + lddf + k, wne * g.v[k]);
+          gix += v.v[k] * (y1f - c.iy) * g.v[k];
+          giy -= v.v[k] * (c.ix - c.x0f) * g.v[k];
+        }
+      }
+      if (yin1 && xin0) {
+        f8 v = ld8(fb + (int64_t)W * ldf_);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          atomicAdd(db + (int64_t)W * lddf + k, wsw * g.v[k]);
+          gix -= v.v[k] * (c.iy - c.y0f) * g.v[k];
+          giy += v.v[k] * (x1f - c.ix) * g.v[k];
+        }
+      }
+      if (yin1 && xin1) {
+        f8 v = ld8(fb + (int64_t)(W + 1) * ldf_);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          atomicAdd(db + (int64_t)(W + 1) * lddf + k, wse * g.v[k]);
+          gix += v.v[k] * (c.iy - c.y0f) * g.v[k];
+          giy += v.v[k] * (c.ix - c.x0f) * g.v[k];
+        }
+      }
+    }
+    for (int o = cg >> 1; o > 0; o >>= 1) {
+      gix += __shfl_xor_sync(0xffffffffu, gix, o);
+      giy += __shfl_xor_sync(0xffffffffu, giy, o);
+    }
+    if (active && (t % cg) == 0) {
+      // d ix / d flow_x = ((W-1)/2) * (2 * 1/(W-1)), evaluated in the reference's order
+      float mx = ((float)(W - 1) * 0.5f) * (2.0f * inv_w);
+      float my = ((float)(H - 1) * 0.5f) * (2.0f * inv_h);
+      reinterpret_cast<float2*>(dflow)[p] = make_float2(gix * mx, giy * my);
+    }
+  }
+}
+
+}  // namespace
+
+NV_API int nervecl_corr_fwd(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* out, int64_t ldo,
+                            int dtype, int N, int H, int W, int C, int cout_pad, nervecl_stream_t stream) {
+  if (!x1 || !x2 || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
+  if (cout_pad < NDISP || ldo < cout_pad) return NERVECL_EINVAL;
+  if ((C & 7) || (ld1 & 7) || (ld2 & 7) || !aligned(x1, 16) || !aligned(x2, 16)) return NERVECL_EALIGN;
+  int64_t blocks = (int64_t)N * H * cdiv(W, 32);
+  size_t smem = (size_t)32 * cout_pad * sizeof(float);
+  NV_DISPATCH_DTYPE(dtype, E, (corr_fwd_kernel<E><<<(unsigned)blocks, 288, smem, as_stream(stream)>>>(
+                                  (const E*)x1, ld1, (const E*)x2, ld2, (E*)out, ldo, N, H, W, C, cout_pad)));
+  return launch_status();
+}
+
+NV_API int nervecl_corr_bwd(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* dout,
+                            int64_t lddo, void* dx1, int64_t lddx1, int acc1, void* dx2, int64_t lddx2, int acc2,
+                            int dtype, int N, int H, int W, int C, nervecl_stream_t stream) {
+  if (!x1 || !x2 || !dout || !dx1 || !dx2 || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
+  if ((C & 7) || (ld1 & 7) || (ld2 & 7) || (lddx1 & 7) || (lddx2 & 7)) return NERVECL_EALIGN;
+  int64_t total = (int64_t)N * H * W * (C >> 3);
+  int blocks = (int)imax(1, imin(cdiv(total, 256), kSMs * 16));
+  NV_DISPATCH_DTYPE(dtype, E, (corr_bwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  (const E*)x1, ld1, (const E*)x2, ld2, (const E*)dout, lddo, (E*)dx1, lddx1, acc1,
+                                  (E*)dx2, lddx2, acc2, N, H, W, C)));
+  return launch_status();
+}
+
+static int warp_check(int N, int H, int W, int C) {
+  if (N <= 0 || H <= 1 || W <= 1 || C <= 0) return NERVECL_EINVAL;  // H or W == 1 divides by zero in the reference too
+  if (C & 7) return NERVECL_EALIGN;
+  int cg = C >> 3;
+  if (cg > 32 || (cg & (cg - 1))) return NERVECL_EUNSUPPORTED;
+  return NERVECL_OK;
+}
+
+NV_API int nervecl_warp_fwd(const void* feat, int64_t ldf, const float* flow, void* out, int64_t ldo, int dtype,
+                            int N, int H, int W, int C, int div_mode, int32_t* idx_out, nervecl_stream_t stream) {
+  if (!feat || !flow || !out) return NERVECL_EINVAL;
+  int rc = warp_check(N, H, W, C);
+  if (rc) return rc;
+  if ((ldf & 7) || (ldo & 7) || !aligned(feat, 16) || !aligned(out, 16) || !aligned(flow, 8)) return NERVECL_EALIGN;
+  float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
+  int64_t total = (int64_t)N * H * W * (C >> 3);
+  int blocks = (int)imax(1, imin(cdiv(total, 256), kSMs * 16));
+  NV_DISPATCH_DTYPE(dtype, E, (warp_fwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  (const E*)feat, ldf, flow, (E*)out, ldo, N, H, W, C, inv_w, inv_h, div_mode, idx_out)));
+  return launch_status();
+}
+
+NV_API int nervecl_warp_bwd(const void* feat, int64_t ldf, const float* flow, const void* dout, int64_t lddo,
+                            float* dfeat, int64_t lddf, float* dflow, int dtype, int N, int H, int W, int C,
+                            int div_mode, nervecl_stream_t stream) {
+  if (!feat || !flow || !dout || !dfeat || !dflow) return NERVECL_EINVAL;
+  int rc = warp_check(N, H, W, C);
+  if (rc) return rc;
+  if ((ldf & 7) || (lddo & 7) || !aligned(feat, 16) || !aligned(dout, 16) || !aligned(flow, 8) || !aligned(dflow, 8))
+    return NERVECL_EALIGN;
+  float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
+  int64_t total = (int64_t)N * H * W * (C >> 3);
+  int blocks = (int)imax(1, imin(cdiv(total, 256), kSMs * 16));
+  NV_DISPATCH_DTYPE(dtype, E, (warp_bwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  (const E*)feat, ldf, flow, (const E*)dout, lddo, dfeat, lddf, dflow, N, H, W, C,
+                                  inv_w, inv_h, div_mode)));
+  return launch_status();
+}

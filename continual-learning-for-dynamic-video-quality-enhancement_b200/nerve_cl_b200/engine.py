@@ -1,0 +1,409 @@
+"""Execution engine for the SuperResolutionNet hot path.
+
+Host-side orchestration (Python, as in the reference) of the ``torch.ops.nervecl`` kernels: one
+forward pass is ~60 launches, one backward ~150, versus 1 036 / 2 091 ATen ops in the reference
+(SURVEY.md section 2.1).  The engine owns every intermediate buffer:
+
+* activations are NHWC in the compute dtype (fp32 parity path or bf16), flow / logits / attention /
+  BN statistics / upsampler output are fp32;
+* the T frames go through the shared feature extractor as one batch of T*B images whose BatchNorm
+  statistics are reduced per frame group (the reference calls the extractor T times,
+  super_resolution.py:346-349, so each call has its own batch statistics and running-stat update);
+* ``torch.stack``/``view`` of the aligned features (super_resolution.py:194-197) and the ``torch.cat``
+  chains of the residual dense blocks (:246-252) do not exist: producers write channel slices of one
+  pitched buffer (T*F channels for the aggregator, F+5*32 for each dense block);
+* backward mirrors that: one (F+5*32)-channel gradient buffer per dense block into which each layer's
+  data gradient is accumulated by the convolution epilogue, with the ReLU mask of the slice that just
+  became final applied in the same epilogue.
+
+The whole forward+backward is exposed to autograd as ONE ``torch.autograd.Function`` (see
+``models/super_resolution.py``) whose inputs are the frames and the 131 parameter tensors.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import CONV_AUTO
+
+nv = ops.nv
+Tensor = torch.Tensor
+
+GROWTH = 32      # ResidualDenseBlock growth rate  (super_resolution.py:215)
+RDB_LAYERS = 5   # (super_resolution.py:216)
+CORR_CH = 81     # (2*4+1)^2 displacements          (super_resolution.py:73)
+CORR_PAD = 96    # correlation volume is stored with 96 channels (zeros beyond 81): 16-byte aligned rows
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+class ConvSpec:
+    """One dense convolution of the network: where its parameters live and how they are packed."""
+
+    def __init__(self, name: str, cin: int, cout: int, k: int, bias: bool, cin_pad: Optional[int] = None):
+        self.name, self.cin, self.cout, self.k, self.has_bias = name, cin, cout, k, bias
+        self.cin_pad = cin_pad or cin          # input buffer channels (corr volume is padded)
+
+
+def _align(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+class Activations:
+    """All buffers of one forward pass (kept until its backward has run)."""
+
+    def __init__(self, plan: "Plan"):
+        p, dev, adt = plan, plan.device, plan.adt
+        B, T, H, W, F, s = p.B, p.T, p.H, p.W, p.F, p.scale
+        f32 = torch.float32
+
+        def act(n, c, dtype=adt):
+            return torch.empty((n, H, W, c), device=dev, dtype=dtype)
+
+        self.x_in = act(T * B, 3)
+        self.head = act(T * B, F)
+        self.dwo = [act(T * B, F) for _ in range(3)]
+        self.pwo = [act(T * B, F) for _ in range(3)]
+        self.fact = [act(T * B, F) for _ in range(2)]
+        self.feat = act(T * B, F)
+        self.bn_sums = [torch.zeros((T, F, 2), device=dev, dtype=torch.float64) for _ in range(3)]
+        self.bn_stat = [torch.empty((T, F, 2), device=dev, dtype=f32) for _ in range(3)]
+        self.cat = act(B, T * F)
+        self.corr = {t: act(B, CORR_PAD) for t in p.others}
+        self.fn1 = {t: act(B, 128) for t in p.others}
+        self.fn2 = {t: act(B, 64) for t in p.others}
+        self.fn3 = {t: act(B, 32) for t in p.others}
+        self.flow = {t: act(B, 2, f32) for t in p.others}
+        self.a1, self.a2 = act(B, F), act(B, F)
+        self.logits, self.attn = act(B, T, f32), act(B, T, f32)
+        self.blend = act(B, F)
+        self.pool = torch.zeros((B, F), device=dev, dtype=f32)
+        self.hidden = torch.empty((B, p.R), device=dev, dtype=f32)
+        self.gate = torch.empty((B, F), device=dev, dtype=f32)
+        self.stats = act(B, 2, f32)
+        self.sgate = torch.empty((B, H, W), device=dev, dtype=f32)
+        self.rdb = [act(B, F + RDB_LAYERS * GROWTH) for _ in range(p.NB)]
+        self.trunk = act(B, F)
+        self.fused = act(B, F)
+        self.up = act(B, 3 * s * s, f32)
+        self.lr_centre: Optional[Tensor] = None   # view of the caller's frames (kept for backward)
+        self.training = False
+
+
+class Plan:
+    """Shape-specialised buffer plan + op sequence for one (B,T,H,W,dtype) configuration."""
+
+    def __init__(self, F: int, NB: int, scale: int, R: int, B: int, T: int, H: int, W: int, adt: torch.dtype,
+                 device):
+        self.B, self.T, self.H, self.W = B, T, H, W
+        self.F, self.NB, self.scale, self.R = F, NB, scale, R
+        self.adt, self.device = adt, device
+        self.mid = T // 2
+        self.others = [t for t in range(T) if t != self.mid]
+        self.engine = CONV_AUTO
+        self.div_mode = 0
+        self._free: List[Activations] = []
+        self._bwd_ws = None
+        F = self.F
+        # dense convolutions in registration order of the reference module
+        cs: Dict[str, ConvSpec] = {}
+
+        def add(name, cin, cout, k, bias=True, cin_pad=None):
+            cs[name] = ConvSpec(name, cin, cout, k, bias, cin_pad)
+
+        add("feature_extractor.head.0", 3, F, 3)
+        for j in range(3):
+            add(f"feature_extractor.body.{j}.pointwise", F, F, 1, bias=False)
+        add("motion_estimator.flow_net.0", CORR_CH, 128, 3, cin_pad=CORR_PAD)
+        add("motion_estimator.flow_net.2", 128, 64, 3)
+        add("motion_estimator.flow_net.4", 64, 32, 3)
+        add("motion_estimator.flow_net.6", 32, 2, 3)
+        add("temporal_aggregator.attention.0", T * F, F, 3)
+        add("temporal_aggregator.attention.2", F, F, 3)
+        add("temporal_aggregator.attention.4", F, T, 3)
+        for k in range(self.NB):
+            for i in range(RDB_LAYERS):
+                add(f"residual_blocks.{k}.layers.{i}.0", F + i * GROWTH, GROWTH, 3)
+            add(f"residual_blocks.{k}.lff", F + RDB_LAYERS * GROWTH, F, 1)
+        add("gff.0", F, F, 3)
+        add("upsampler.conv", F, 3 * self.scale ** 2, 3)
+        self.convs = cs
+        # packed weights: forward operator [K*K, Cout, Cin_pad8]; data-gradient operator [K*K, Cin_pad, Cout_pad8]
+        self.wf: Dict[str, Tensor] = {}
+        self.wb: Dict[str, Tensor] = {}
+        for name, c in cs.items():
+            kk = c.k * c.k
+            self.wf[name] = torch.empty((kk, c.cout, _align(c.cin_pad, 8)), device=device, dtype=adt)
+            if name != "feature_extractor.head.0":   # the input frames need no gradient
+                self.wb[name] = torch.empty((kk, c.cin_pad, _align(c.cout, 8)), device=device, dtype=adt)
+
+    # ---- activation-set pool ---------------------------------------------------------------
+    def acquire(self) -> Activations:
+        return self._free.pop() if self._free else Activations(self)
+
+    def release(self, acts: Activations) -> None:
+        acts.lr_centre = None
+        if len(self._free) < 2:
+            self._free.append(acts)
+
+    # ---- weights ---------------------------------------------------------------------------
+    def pack_weights(self, P: Dict[str, Tensor], need_bwd: bool) -> None:
+        for name in self.convs:
+            w = P[name + ".weight"]
+            nv.pack_conv_weight(w, self.wf[name], False)
+            if need_bwd and name in self.wb:
+                nv.pack_conv_weight(w, self.wb[name], True)
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def conv(self, name: str, x: Tensor, out: Tensor, P, *, relu=False, res=None, res_channels=0, alpha=1.0,
+             bias=True) -> None:
+        c = self.convs[name]
+        b = P[name + ".bias"] if (c.has_bias and bias) else None
+        nv.conv2d_fwd(x, self.wf[name], b, res, None, None, out, c.cout, relu, False,
+                      res_channels if res is not None else 0, 0, alpha, self.engine)
+
+    def dgrad(self, name: str, dy: Tensor, out: Tensor, *, cout=None, accumulate=False, res=None, res_channels=0,
+              alpha=1.0, mask=None, mask_sub=None, mask_c0=0) -> None:
+        c = self.convs[name]
+        nv.conv2d_fwd(dy, self.wb[name], None, res, mask, mask_sub, out, cout or c.cin_pad, False, accumulate,
+                      res_channels if res is not None else 0, mask_c0, alpha, self.engine)
+
+    def wgrad(self, name: str, x: Tensor, dy: Tensor, G: Dict[str, Tensor], scale: float = 1.0) -> None:
+        c = self.convs[name]
+        nv.conv2d_wgrad(x, dy, G[name + ".weight"], G[name + ".bias"] if c.has_bias else None, scale, self.engine)
+
+    # =======================================================================================
+    # forward
+    # =======================================================================================
+    def forward(self, lr_frames: Tensor, P: Dict[str, Tensor], BUF: Dict[str, Tensor], training: bool,
+                need_bwd: bool, out: Tensor) -> Activations:
+        """P: parameter name -> fp32 tensor; BUF: BN buffers by name.  Writes the HR frame into ``out``."""
+        B, T, H, W, F, s = self.B, self.T, self.H, self.W, self.F, self.scale
+        A = self.acquire()
+        A.training = training
+        self.pack_weights(P, need_bwd)
+
+        # ---- feature extractor over all T*B frames (super_resolution.py:346-349) ----
+        nv.pack_frames(lr_frames, A.x_in)
+        self.conv("feature_extractor.head.0", A.x_in, A.head, P, relu=True)
+        x = A.head
+        for j in range(3):
+            pre = f"feature_extractor.body.{j}."
+            nv.dwconv3x3_fwd(x, P[pre + "depthwise.weight"], A.dwo[j], False, False)
+            self.conv(pre + "pointwise", A.dwo[j], A.pwo[j], P)
+            if training:
+                nv.fill_zero(A.bn_sums[j])
+                nv.bn_stats(A.pwo[j], T, A.bn_sums[j])
+            nv.bn_finalize(A.bn_sums[j] if training else None, A.bn_stat[j], BUF[pre + "bn.running_mean"],
+                           BUF[pre + "bn.running_var"], BUF[pre + "bn.num_batches_tracked"], B * H * W, T,
+                           BN_MOMENTUM, BN_EPS, training)
+            y = A.fact[j] if j < 2 else A.feat
+            nv.bn_relu_fwd(A.pwo[j], A.bn_stat[j], P[pre + "bn.weight"], P[pre + "bn.bias"],
+                           A.head if j == 2 else None, y, T)
+            x = y
+        feat = A.feat.view(T, B, H, W, F)
+        centre = feat[self.mid]
+
+        # ---- motion estimation + compensation (super_resolution.py:355-363) ----
+        nv.axpy(centre, A.cat[..., self.mid * F:(self.mid + 1) * F], 1.0, False)
+        for t in self.others:
+            nv.corr_fwd(feat[t], centre, A.corr[t])
+            self.conv("motion_estimator.flow_net.0", A.corr[t], A.fn1[t], P, relu=True)
+            self.conv("motion_estimator.flow_net.2", A.fn1[t], A.fn2[t], P, relu=True)
+            self.conv("motion_estimator.flow_net.4", A.fn2[t], A.fn3[t], P, relu=True)
+            self.conv("motion_estimator.flow_net.6", A.fn3[t], A.flow[t], P)
+            nv.warp_fwd(feat[t], A.flow[t], A.cat[..., t * F:(t + 1) * F], self.div_mode, None)
+
+        # ---- temporal aggregation (super_resolution.py:194-209) ----
+        self.conv("temporal_aggregator.attention.0", A.cat, A.a1, P, relu=True)
+        self.conv("temporal_aggregator.attention.2", A.a1, A.a2, P, relu=True)
+        self.conv("temporal_aggregator.attention.4", A.a2, A.logits, P)
+        nv.tfuse_fwd(A.cat, A.logits, A.attn, A.blend)
+        pre = "temporal_aggregator.refine."
+        nv.fill_zero(A.pool)
+        nv.chan_sum(A.blend, 1.0 / (H * W), A.pool)
+        nv.ca_gate_fwd(A.pool, P[pre + "channel_attention.fc.0.weight"], P[pre + "channel_attention.fc.2.weight"],
+                       A.hidden, A.gate)
+        nv.cbam_stats_fwd(A.blend, A.gate, A.stats)
+        trunk_in = A.rdb[0][..., :F] if self.NB > 0 else A.trunk
+        nv.cbam_apply_fwd(A.blend, A.gate, A.stats, P[pre + "spatial_attention.conv.weight"], A.sgate, trunk_in)
+
+        # ---- residual dense blocks (super_resolution.py:245-253), concat-free ----
+        for k in range(self.NB):
+            buf = A.rdb[k]
+            for i in range(RDB_LAYERS):
+                c0 = F + i * GROWTH
+                self.conv(f"residual_blocks.{k}.layers.{i}.0", buf[..., :c0], buf[..., c0:c0 + GROWTH], P, relu=True)
+            nxt = A.rdb[k + 1][..., :F] if k + 1 < self.NB else A.trunk
+            self.conv(f"residual_blocks.{k}.lff", buf, nxt, P, alpha=0.2, res=buf[..., :F], res_channels=F)
+
+        # ---- global fusion, upsampler, bicubic skip, clamp (super_resolution.py:372-382) ----
+        self.conv("gff.0", A.trunk, A.fused, P, relu=True, res=centre, res_channels=F)
+        self.conv("upsampler.conv", A.fused, A.up, P)
+        A.lr_centre = lr_frames[:, self.mid]
+        nv.upfinish_fwd(A.up, A.lr_centre, out, s)
+        return A
+
+    # =======================================================================================
+    # backward
+    # =======================================================================================
+    def _workspace(self):
+        if self._bwd_ws is None:
+            B, T, H, W, F, s, dev, adt = self.B, self.T, self.H, self.W, self.F, self.scale, self.device, self.adt
+            f32 = torch.float32
+
+            def act(n, c, dtype=adt):
+                return torch.empty((n, H, W, c), device=dev, dtype=dtype)
+
+            ws = {}
+            ws["dup"] = act(B, 3 * s * s, f32)
+            ws["dup_a"] = act(B, _align(3 * s * s, 8))
+            ws["dfused"] = act(B, F)
+            ws["dgff"] = act(B, F)
+            ws["dtrunk"] = act(B, F)
+            ws["g"] = [act(B, F + RDB_LAYERS * GROWTH) for _ in range(2)]
+            ws["dz"] = torch.empty((B, H, W), device=dev, dtype=f32)
+            ws["dstats"] = act(B, 2, f32)
+            ws["dblend"] = act(B, F)
+            ws["dgate"] = torch.empty((B, F), device=dev, dtype=f32)
+            ws["dpool"] = torch.empty((B, F), device=dev, dtype=f32)
+            ws["dcat"] = act(B, T * F)
+            ws["dlogits"] = act(B, T, f32)
+            ws["dlogits_a"] = act(B, _align(T, 8))
+            ws["da2"], ws["da1"] = act(B, F), act(B, F)
+            ws["dfeat"] = act(T * B, F)
+            ws["dfeat32"] = act(B, F, f32)
+            ws["dflow"] = act(B, 2, f32)
+            ws["dflow_a"] = act(B, 8)
+            ws["dfn3"], ws["dfn2"], ws["dfn1"] = act(B, 32), act(B, 64), act(B, 128)
+            ws["dcorr"] = act(B, CORR_PAD)
+            ws["t"] = [act(T * B, F) for _ in range(3)]
+            ws["bsums"] = torch.zeros((T, F, 2), device=dev, dtype=torch.float64)
+            self._bwd_ws = ws
+        return self._bwd_ws
+
+    def backward(self, A: Activations, dout: Tensor, P: Dict[str, Tensor], G: Dict[str, Tensor],
+                 on_grads_ready=None) -> None:
+        """Accumulate parameter gradients into ``G`` (name -> fp32 tensor, same shapes as ``P``).
+
+        ``G`` must be zero-initialised by the caller.  ``on_grads_ready(prefix)`` is invoked as soon as
+        every gradient under a parameter-name prefix is final (used to launch bucketed all-reduces
+        while the rest of backward is still running).
+        """
+        B, T, H, W, F, s = self.B, self.T, self.H, self.W, self.F, self.scale
+        ws = self._workspace()
+        ready = on_grads_ready or (lambda prefix: None)
+        feat = A.feat.view(T, B, H, W, F)
+        centre = feat[self.mid]
+        ncs = 3 * s * s
+        training = A.training
+
+        # ---- output stage ----
+        nv.upfinish_bwd(A.up, A.lr_centre, dout, ws["dup"], s)
+        dup = ws["dup_a"][..., :ncs]
+        nv.axpy(ws["dup"], dup, 1.0, False)
+        self.wgrad("upsampler.conv", A.fused, dup, G)
+        ready("upsampler.")
+        self.dgrad("upsampler.conv", dup, ws["dfused"])
+        nv.relu_bwd(ws["dfused"], A.fused, centre, ws["dgff"])
+        self.wgrad("gff.0", A.trunk, ws["dgff"], G)
+        ready("gff.")
+        dblock = ws["dtrunk"]
+        self.dgrad("gff.0", ws["dgff"], dblock)
+
+        # ---- residual dense blocks, last to first ----
+        CT = F + RDB_LAYERS * GROWTH
+        for k in reversed(range(self.NB)):
+            buf, g = A.rdb[k], ws["g"][k & 1]
+            name = f"residual_blocks.{k}.lff"
+            self.wgrad(name, buf, dblock, G, scale=0.2)
+            # g[:, :CT] = 0.2 * lff^T(dblock) (+ dblock on the first F channels: the block skip);
+            # slice 4 (channels >= F+4G) has no other consumer, so its ReLU mask is applied here.
+            self.dgrad(name, dblock, g, cout=CT, alpha=0.2, res=dblock, res_channels=F, mask=buf,
+                       mask_c0=F + (RDB_LAYERS - 1) * GROWTH)
+            for i in reversed(range(RDB_LAYERS)):
+                c0 = F + i * GROWTH
+                name = f"residual_blocks.{k}.layers.{i}.0"
+                dy = g[..., c0:c0 + GROWTH]
+                self.wgrad(name, buf[..., :c0], dy, G)
+                if i >= 1:
+                    self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True, mask=buf, mask_c0=c0 - GROWTH)
+                else:
+                    self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True)
+            ready(f"residual_blocks.{k}.")
+            dblock = g[..., :F]
+        dagg = dblock
+
+        # ---- CBAM ----
+        pre = "temporal_aggregator.refine."
+        w7 = P[pre + "spatial_attention.conv.weight"]
+        nv.cbam_bwd_dz(A.blend, A.gate, A.sgate, dagg, ws["dz"])
+        nv.cbam_bwd_spatial(ws["dz"], A.stats, w7, ws["dstats"], G[pre + "spatial_attention.conv.weight"])
+        nv.fill_zero(ws["dgate"])
+        nv.cbam_bwd_dx(A.blend, A.gate, A.sgate, A.stats, ws["dstats"], dagg, ws["dblend"], ws["dgate"])
+        nv.ca_gate_bwd(A.pool, P[pre + "channel_attention.fc.0.weight"], P[pre + "channel_attention.fc.2.weight"],
+                       A.hidden, A.gate, ws["dgate"], ws["dpool"], G[pre + "channel_attention.fc.0.weight"],
+                       G[pre + "channel_attention.fc.2.weight"])
+        nv.ewc_axpby(ws["dpool"], None, 1.0 / (H * W), 0.0)     # d(mean over H*W)
+
+        # ---- temporal fusion + attention convs ----
+        nv.tfuse_bwd(A.cat, A.attn, ws["dblend"], ws["dpool"], ws["dcat"], ws["dlogits"])
+        dlog = ws["dlogits_a"][..., :T]
+        nv.axpy(ws["dlogits"], dlog, 1.0, False)
+        self.wgrad("temporal_aggregator.attention.4", A.a2, dlog, G)
+        self.dgrad("temporal_aggregator.attention.4", dlog, ws["da2"], mask=A.a2)
+        self.wgrad("temporal_aggregator.attention.2", A.a1, ws["da2"], G)
+        self.dgrad("temporal_aggregator.attention.2", ws["da2"], ws["da1"], mask=A.a1)
+        self.wgrad("temporal_aggregator.attention.0", A.cat, ws["da1"], G)
+        self.dgrad("temporal_aggregator.attention.0", ws["da1"], ws["dcat"], accumulate=True)
+        ready("temporal_aggregator.")
+
+        # ---- alignment: warp, flow_net, correlation ----
+        dfeat = ws["dfeat"].view(T, B, H, W, F)
+        dcat = ws["dcat"]
+        nv.axpy(dcat[..., self.mid * F:(self.mid + 1) * F], dfeat[self.mid], 1.0, False)
+        nv.axpy(ws["dfused"], dfeat[self.mid], 1.0, True)        # gff skip: fused = relu(..) + centre
+        for t in self.others:
+            nv.fill_zero(ws["dfeat32"])
+            nv.warp_bwd(feat[t], A.flow[t], dcat[..., t * F:(t + 1) * F], ws["dfeat32"], ws["dflow"], self.div_mode)
+            nv.axpy(ws["dfeat32"], dfeat[t], 1.0, False)
+            dflow = ws["dflow_a"][..., :2]
+            nv.axpy(ws["dflow"], dflow, 1.0, False)
+            self.wgrad("motion_estimator.flow_net.6", A.fn3[t], dflow, G)
+            self.dgrad("motion_estimator.flow_net.6", dflow, ws["dfn3"], mask=A.fn3[t])
+            self.wgrad("motion_estimator.flow_net.4", A.fn2[t], ws["dfn3"], G)
+            self.dgrad("motion_estimator.flow_net.4", ws["dfn3"], ws["dfn2"], mask=A.fn2[t])
+            self.wgrad("motion_estimator.flow_net.2", A.fn1[t], ws["dfn2"], G)
+            self.dgrad("motion_estimator.flow_net.2", ws["dfn2"], ws["dfn1"], mask=A.fn1[t])
+            self.wgrad("motion_estimator.flow_net.0", A.corr[t][..., :CORR_CH], ws["dfn1"], G)
+            self.dgrad("motion_estimator.flow_net.0", ws["dfn1"], ws["dcorr"])
+            nv.corr_bwd(feat[t], centre, ws["dcorr"], dfeat[t], True, dfeat[self.mid], True)
+        ready("motion_estimator.")
+
+        # ---- feature extractor (all T*B frames at once, BN per frame group) ----
+        # dy: gradient w.r.t. the ReLU output of body layer j.  s0/s1/s2 are scratch: by the time s2
+        # (the previous dy) is overwritten by the depthwise data gradient it has been consumed.
+        dy = ws["dfeat"]
+        s0, s1, s2 = ws["t"]
+        for j in reversed(range(3)):
+            pre = f"feature_extractor.body.{j}."
+            gamma, beta = P[pre + "bn.weight"], P[pre + "bn.bias"]
+            nv.fill_zero(ws["bsums"])
+            nv.bn_relu_bwd_reduce(A.pwo[j], dy, A.bn_stat[j], gamma, beta, T, ws["bsums"])
+            nv.bn_relu_bwd_apply(A.pwo[j], dy, A.bn_stat[j], gamma, beta, ws["bsums"], s0, G[pre + "bn.weight"],
+                                 G[pre + "bn.bias"], T, training)
+            self.wgrad(pre + "pointwise", A.dwo[j], s0, G)
+            self.dgrad(pre + "pointwise", s0, s1)
+            x_in = A.fact[j - 1] if j > 0 else A.head
+            nv.dwconv3x3_wgrad(x_in, s1, G[pre + "depthwise.weight"])
+            if j > 0:
+                nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], s2, True, False)
+                dy = s2
+            else:
+                # extractor skip (feat = body(head) + head): d(head) = d(feat) + depthwise data gradient
+                nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], ws["dfeat"], True, True)
+        nv.relu_bwd(ws["dfeat"], A.head, None, ws["t"][0])
+        self.wgrad("feature_extractor.head.0", A.x_in, ws["t"][0], G)
+        ready("feature_extractor.")

@@ -1,0 +1,321 @@
+"""Drop-in ``SuperResolutionNet`` backed by the sm_100a kernel library.
+
+Same constructor, public attributes, methods, sub-module tree and ``state_dict`` keys as the reference
+``nerve_cl/models/super_resolution.py:256-431`` (so checkpoints, ``EWC`` parameter names and
+``train_baseline.py`` / ``train_continual.py`` keep working), but ``forward`` does not execute the
+sub-modules: they only *hold* the parameters, created by the same torch constructors in the same order
+as the reference, so ``torch.manual_seed(s); SuperResolutionNet(...)`` yields bit-identical initial
+weights.  The arithmetic runs in ``engine.Plan`` through ``torch.ops.nervecl`` as one autograd node.
+
+There is no CPU path: calling ``forward`` on CPU tensors raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import engine as _engine
+from .. import ops as _ops
+from .layers import CBAM, DepthwiseSeparableConv, LiteFlowNetCorrelation, PixelShuffleUpsampler
+
+Tensor = torch.Tensor
+
+
+def _conv_relu(cin: int, cout: int) -> List[nn.Module]:
+    return [nn.Conv2d(cin, cout, 3, 1, 1), nn.ReLU(inplace=True)]
+
+
+class FeatureExtractor(nn.Module):
+    """Parameter holder for reference ``FeatureExtractor`` (super_resolution.py:22-54)."""
+
+    def __init__(self, in_channels: int = 3, num_features: int = 64):
+        super().__init__()
+        self.head = nn.Sequential(*_conv_relu(in_channels, num_features))
+        self.body = nn.Sequential(*[DepthwiseSeparableConv(num_features, num_features) for _ in range(3)])
+
+
+class MotionEstimator(nn.Module):
+    """Parameter holder for reference ``MotionEstimator`` (super_resolution.py:57-101)."""
+
+    def __init__(self, in_channels: int = 64):
+        super().__init__()
+        self.correlation = LiteFlowNetCorrelation(max_displacement=4)
+        widths = [(2 * 4 + 1) ** 2, 128, 64, 32]
+        mods: List[nn.Module] = []
+        for a, b in zip(widths[:-1], widths[1:]):
+            mods += _conv_relu(a, b)
+        mods.append(nn.Conv2d(widths[-1], 2, 3, 1, 1))
+        self.flow_net = nn.Sequential(*mods)
+
+
+class TemporalAggregator(nn.Module):
+    """Parameter holder for reference ``TemporalAggregator`` (super_resolution.py:146-209)."""
+
+    def __init__(self, num_features: int = 64, num_frames: int = 3):
+        super().__init__()
+        self.num_frames = num_frames
+        self.attention = nn.Sequential(
+            *_conv_relu(num_features * num_frames, num_features),
+            *_conv_relu(num_features, num_features),
+            nn.Conv2d(num_features, num_frames, 3, 1, 1),
+            nn.Softmax(dim=1),
+        )
+        self.refine = CBAM(num_features)
+
+
+class ResidualDenseBlock(nn.Module):
+    """Parameter holder for reference ``ResidualDenseBlock`` (super_resolution.py:212-253)."""
+
+    def __init__(self, num_features: int = 64, growth_rate: int = 32, num_layers: int = 5):
+        super().__init__()
+        if growth_rate != _engine.GROWTH or num_layers != _engine.RDB_LAYERS:
+            raise ValueError("the kernel engine is specialised to growth_rate=32, num_layers=5 (reference defaults)")
+        self.layers = nn.ModuleList(
+            nn.Sequential(*_conv_relu(num_features + i * growth_rate, growth_rate)) for i in range(num_layers))
+        self.lff = nn.Conv2d(num_features + num_layers * growth_rate, num_features, 1)
+
+
+class _SRFunction(torch.autograd.Function):
+    """forward + backward of the whole network as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, module: "SuperResolutionNet", lr_frames: Tensor, *params: Tensor):
+        names = module._param_names
+        P = {n: p.detach() for n, p in zip(names, params)}
+        BUF = {n: b for n, b in module.named_buffers()}
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        plan = module._plan_for(lr_frames)
+        B, T, C, H, W = lr_frames.shape
+        s = module.scale_factor
+        out = torch.empty((B, C, H * s, W * s), device=lr_frames.device, dtype=torch.float32)
+        acts = plan.forward(lr_frames.detach(), P, BUF, module.training, need_bwd, out)
+        module._last_acts = acts if module._keep_intermediate else None
+        if need_bwd:
+            ctx.plan, ctx.acts, ctx.module, ctx.P = plan, acts, module, P
+        elif not module._keep_intermediate:
+            plan.release(acts)
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Optional[Tensor]):
+        module, plan, acts, P = ctx.module, ctx.plan, ctx.acts, ctx.P
+        names = module._param_names
+        if acts is None:
+            raise RuntimeError("nerve_cl_b200: backward called twice on the same SuperResolutionNet forward")
+        if dout is None:
+            return (None, None) + (None,) * len(names)
+        # a fresh flat fp32 gradient buffer per backward: autograd may adopt ("steal") the returned
+        # views as param.grad, so it must never be recycled by the engine.
+        flat = torch.empty(module._flat_numel, device=dout.device, dtype=torch.float32)
+        _ops.nv.fill_zero(flat)
+        G = {n: flat[o:o + k].view(shape) for n, (o, k, shape) in module._flat_layout.items()}
+        hook = module._grad_sync.on_ready if module._grad_sync is not None else None
+        if module._grad_sync is not None:
+            module._grad_sync.begin(flat, module._flat_layout)
+        plan.backward(acts, dout.contiguous().float(), P, G, hook)
+        if module._grad_sync is not None:
+            module._grad_sync.finish()
+        module._last_flat_grad = flat
+        ctx.acts = None
+        plan.release(acts)
+        return (None, None) + tuple(G[n] for n in names)
+
+
+class SuperResolutionNet(nn.Module):
+    """Lightweight temporal super-resolution network (reference super_resolution.py:256).
+
+    Args (unchanged from the reference):
+        in_channels: image channels (the kernels are specialised to 3)
+        scale_factor: 2, 3 or 4
+        num_features: feature channels F (multiple of 8; 8 <= F <= 256, power-of-two multiple of 8)
+        num_residual_blocks: number of residual dense blocks
+        temporal_window: reference frames on each side; ``num_frames = 2*temporal_window + 1``
+
+    Extra, non-reference knobs (attributes, not constructor arguments):
+        ``compute_dtype``: ``None`` (default: bf16 under ``torch.autocast('cuda', torch.bfloat16)``,
+        else fp32), ``torch.float32`` or ``torch.bfloat16``.
+        ``conv_engine``: ``ops.CONV_AUTO`` / ``CONV_SIMT`` / ``CONV_TC``.
+        ``warp_div_mode``: 0 replays ATen-CUDA's ``x * (1/(W-1))`` (default), 1 ATen-CPU's ``x / (W-1)``.
+    """
+
+    def __init__(self, in_channels: int = 3, scale_factor: int = 2, num_features: int = 64,
+                 num_residual_blocks: int = 8, temporal_window: int = 1):
+        super().__init__()
+        self.scale_factor = scale_factor
+        self.temporal_window = temporal_window
+        self.num_frames = 2 * temporal_window + 1
+        self.in_channels = in_channels
+        self.num_features = num_features
+        self.num_residual_blocks = num_residual_blocks
+
+        # same construction order as the reference => same RNG stream => identical initial weights
+        self.feature_extractor = FeatureExtractor(in_channels, num_features)
+        self.motion_estimator = MotionEstimator(num_features)
+        self.temporal_aggregator = TemporalAggregator(num_features, self.num_frames)
+        self.residual_blocks = nn.Sequential(*[ResidualDenseBlock(num_features) for _ in range(num_residual_blocks)])
+        self.gff = nn.Sequential(*_conv_relu(num_features, num_features))
+        self.upsampler = PixelShuffleUpsampler(in_channels=num_features, scale_factor=scale_factor,
+                                               out_channels=in_channels)
+        self.bicubic_upsample = nn.Upsample(scale_factor=scale_factor, mode="bicubic", align_corners=False)
+
+        self.compute_dtype: Optional[torch.dtype] = None
+        self.conv_engine = _ops.CONV_AUTO
+        self.warp_div_mode = 0
+        self._plans: Dict[Tuple, _engine.Plan] = {}
+        self._keep_intermediate = False
+        self._last_acts = None
+        self._last_flat_grad: Optional[Tensor] = None
+        self._grad_sync = None
+        self._param_names: List[str] = [n for n, _ in self.named_parameters()]
+        off = 0
+        self._flat_layout: Dict[str, Tuple[int, int, torch.Size]] = {}
+        for n, p in self.named_parameters():
+            self._flat_layout[n] = (off, p.numel(), p.shape)
+            off += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned in the flat buffer
+        self._flat_numel = off
+
+    # ------------------------------------------------------------------------------------
+    def _dtype_now(self) -> torch.dtype:
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
+
+    def _plan_for(self, lr_frames: Tensor) -> _engine.Plan:
+        B, T, C, H, W = lr_frames.shape
+        adt = self._dtype_now()
+        key = (B, T, H, W, adt, lr_frames.device)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:                      # bound workspace growth across shape changes
+                self._plans.pop(next(iter(self._plans)))
+            R = self.temporal_aggregator.refine.channel_attention.fc[0].out_features
+            plan = _engine.Plan(self.num_features, self.num_residual_blocks, self.scale_factor, R, B, T, H, W, adt,
+                                lr_frames.device)
+            self._plans[key] = plan
+        plan.engine = self.conv_engine
+        plan.div_mode = self.warp_div_mode
+        return plan
+
+    def _validate(self, lr_frames: Tensor) -> None:
+        if lr_frames.dim() != 5:
+            raise ValueError(f"expected (B, T, C, H, W) frames, got shape {tuple(lr_frames.shape)}")
+        if not lr_frames.is_cuda:
+            raise RuntimeError("nerve_cl_b200.SuperResolutionNet runs on CUDA (sm_100a) only; there is no CPU "
+                               "fallback. Move the module and its inputs to a B200.")
+        p0 = next(self.parameters())
+        if p0.device != lr_frames.device:
+            raise RuntimeError(f"module parameters are on {p0.device} but the frames are on {lr_frames.device}")
+        B, T, C, H, W = lr_frames.shape
+        if C != 3 or self.in_channels != 3:
+            raise ValueError("the kernel engine is specialised to in_channels=3")
+        if T != self.num_frames:
+            # the reference fails here too: attention.0 expects num_frames*F input channels (:167)
+            raise RuntimeError(f"expected {self.num_frames} frames (temporal_window={self.temporal_window}), got {T}")
+        if H < 2 or W < 2:
+            raise ValueError("H and W must be >= 2 (the reference divides by (W-1), super_resolution.py:129-133)")
+        F = self.num_features
+        if F % 8 or F > 256 or ((F // 8) & (F // 8 - 1)):
+            raise ValueError("num_features must be 8, 16, 32, 64, 128 or 256 for the kernel engine")
+        if lr_frames.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the input frames are not produced by the kernel engine")
+
+    def forward(self, lr_frames: Tensor, return_intermediate: bool = False):
+        """Upscale the centre frame of a (B, T, C, H, W) window -> (B, C, H*s, W*s) in [0, 1]."""
+        self._validate(lr_frames)
+        if lr_frames.dtype != torch.float32:
+            lr_frames = lr_frames.float()
+        self._keep_intermediate = return_intermediate
+        try:
+            out = _SRFunction.apply(self, lr_frames, *self.parameters())
+            if not return_intermediate:
+                return out
+            return out, self._export_intermediate(lr_frames)
+        finally:
+            self._keep_intermediate = False
+            self._last_acts = None
+
+    def _export_intermediate(self, lr_frames: Tensor) -> Dict[str, object]:
+        """NCHW fp32 copies of the tensors the reference returns at super_resolution.py:384-389."""
+        A = self._last_acts
+        B, T, C, H, W = lr_frames.shape
+        F = self.num_features
+        nv = _ops.nv
+
+        def nchw(view: Tensor) -> Tensor:
+            dst = torch.empty((view.shape[0], view.shape[3], H, W), device=view.device, dtype=torch.float32)
+            nv.nhwc_to_nchw(view, dst)
+            return dst
+
+        feat = A.feat.view(T, B, H, W, F)
+        feats = [nchw(feat[t]) for t in range(T)]
+        aligned = [nchw(A.cat[..., t * F:(t + 1) * F]) for t in range(T)]
+        agg_view = A.rdb[0][..., :F] if self.num_residual_blocks > 0 else A.trunk
+        return {"features": feats, "aligned": aligned, "aggregated": nchw(agg_view),
+                "flows": {t: A.flow[t].permute(0, 3, 1, 2).contiguous() for t in A.flow}}
+
+    def forward_single(self, lr_frame: Tensor) -> Tensor:
+        """Upscale one frame by replicating it ``num_frames`` times (super_resolution.py:393-405)."""
+        return self.forward(lr_frame.unsqueeze(1).expand(-1, self.num_frames, -1, -1, -1))
+
+    def get_num_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def get_flops(self, input_size: Tuple[int, int] = (128, 128)) -> int:
+        """The reference's rough estimate (super_resolution.py:411-431), reproduced for API parity.
+
+        It hard-codes F=64 / 8 blocks and ignores flow_net, aggregator and dense growth; use
+        ``conv_macs_per_pixel`` for the exact multiply-accumulate count."""
+        h, w = input_size
+        f, c, s = 64, 3, self.scale_factor
+        return h * w * (c * f * 9 + f * 81 * (self.num_frames - 1) + f * f * 9 * 8 + f * (c * s * s) * 9)
+
+    def conv_macs_per_pixel(self) -> int:
+        """Exact forward conv MACs per LR pixel per sample (closed form of SURVEY.md section 8a)."""
+        F, T, s, NB = self.num_features, self.num_frames, self.scale_factor, self.num_residual_blocks
+        fe = 27 * F + 3 * (9 * F + F * F)
+        flow = 9 * (81 * 128 + 128 * 64 + 64 * 32 + 32 * 2)
+        agg = 9 * (T * F * F + F * F + F * T) + 98
+        rdb = sum(9 * (F + 32 * i) * 32 for i in range(5)) + (F + 160) * F
+        return T * fe + (T - 1) * flow + agg + NB * rdb + 9 * F * F + 9 * F * 3 * s * s
+
+    # ------------------------------------------------------------------------------------
+    def last_flat_grad(self) -> Optional[Tensor]:
+        """The flat fp32 gradient buffer of the most recent backward (parameter order, 16-byte aligned
+        slots) if every ``param.grad`` still aliases it -- lets optimisers / EWC run one fused kernel."""
+        flat = self._last_flat_grad
+        if flat is None:
+            return None
+        for n, p in self.named_parameters():
+            o, k, _ = self._flat_layout[n]
+            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * o:
+                return None
+        return flat
+
+    def set_gradient_sync(self, sync) -> None:
+        """Install a ``distributed.GradSync`` (bucketed all-reduce overlapped with backward)."""
+        self._grad_sync = sync
+
+
+class LightweightSuperResolution(nn.Module):
+    """Reference ``LightweightSuperResolution`` (super_resolution.py:434-470) -- parameter-compatible holder.
+
+    SURVEY.md section 8f ranks this network as a *next* row; its kernels are not built yet, so forward
+    raises instead of silently running a non-native path."""
+
+    def __init__(self, scale_factor: int = 2):
+        super().__init__()
+        self.scale_factor = scale_factor
+        self.net = nn.Sequential(
+            nn.Conv2d(3, 32, 3, 1, 1), nn.ReLU(inplace=True),
+            *[DepthwiseSeparableConv(32, 32) for _ in range(4)],
+            nn.Conv2d(32, 3 * scale_factor ** 2, 3, 1, 1), nn.PixelShuffle(scale_factor))
+        self.bicubic = nn.Upsample(scale_factor=scale_factor, mode="bicubic", align_corners=False)
+
+    def forward(self, x: Tensor) -> Tensor:
+        raise NotImplementedError("LightweightSuperResolution is outside the B200 hot path built so far "
+                                  "(SURVEY.md section 8f, rank 3)")

@@ -1,0 +1,110 @@
+"""End-to-end parity of the CUDA SuperResolutionNet against the golden fixtures (live-reference
+outputs) and against the oracle run on the same inputs.  fp32 path: rel-err <= 1e-4 on outputs,
+gradients and BN buffers (BASELINE.json north_star); bf16 path: PSNR delta <= 0.05 dB."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_case, load_golden, psnr, relerr
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+CASES = ["sr_tiny_x2_train.npz", "sr_tiny_x2_eval.npz", "sr_tiny_x3_train.npz", "sr_tiny_x4_t5_train.npz",
+         "sr_default_x2_train.npz"]
+
+
+def run_case(name, dtype=torch.float32):
+    g = load_golden(name)
+    model, scale, training = build_case(g["meta"], "cuda")
+    model.compute_dtype = dtype
+    x = torch.from_numpy(g["lr_frames"]).cuda()
+    target = torch.from_numpy(g["target"]).cuda()
+    out, inter = model(x, return_intermediate=True)
+    loss = torch.nn.functional.mse_loss(out, target)
+    loss.backward()
+    return g, model, out, inter, loss
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_init_matches_reference(name):
+    g = load_golden(name)
+    model, _, _ = build_case(g["meta"], "cpu")
+    sd = model.state_dict()
+    if "w_sum" in g:
+        sums = np.array([float(v.double().sum()) for v in sd.values()])
+        np.testing.assert_allclose(sums, g["w_sum"], rtol=1e-12, atol=1e-12)
+    else:
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), g["w/" + k]), k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_forward_backward_matches_reference(name):
+    g, model, out, inter, loss = run_case(name)
+    t = model.num_frames
+    assert relerr(inter["features"][t // 2], torch.from_numpy(g["feat_centre"])) <= FP32_TOL
+    assert relerr(inter["aligned"][0], torch.from_numpy(g["aligned0"])) <= FP32_TOL
+    assert relerr(inter["aggregated"], torch.from_numpy(g["aggregated"])) <= FP32_TOL
+    assert relerr(out, torch.from_numpy(g["out"])) <= FP32_TOL
+    assert abs(float(loss) - float(g["loss"])) <= FP32_TOL * abs(float(g["loss"]))
+    # BN buffers after the step
+    sd = model.state_dict()
+    for k in sd:
+        if "running" in k or "tracked" in k:
+            assert relerr(sd[k].float(), torch.from_numpy(g["bn1/" + k]).float()) <= FP32_TOL, k
+    # gradients
+    names = [n for n, _ in model.named_parameters()]
+    if "g_norm" in g:
+        norms = np.array([float(p.grad.double().norm()) for _, p in model.named_parameters()])
+        scale = np.maximum(g["g_norm"], 1e-12 * g["g_norm"].max())
+        np.testing.assert_allclose(norms, g["g_norm"], rtol=2e-4, atol=1e-4 * float(g["g_norm"].max()))
+        head = torch.cat([p.grad.flatten()[:16] for _, p in model.named_parameters()]).cpu().numpy()
+        assert np.abs(head - g["g_head"]).max() <= 2e-4 * np.abs(g["g_head"]).max()
+    else:
+        for n, p in model.named_parameters():
+            ref = torch.from_numpy(g["g/" + n])
+            assert relerr(p.grad, ref) <= FP32_TOL or float((p.grad.cpu() - ref).abs().max()) < 1e-9, n
+
+
+def test_fp32_against_oracle_on_gpu_inputs():
+    """Same seeded inputs through the oracle (CPU fp32) and the CUDA path, a shape not in the fixtures."""
+    from oracle import sr_oracle
+    from nerve_cl_b200.models import SuperResolutionNet
+    torch.manual_seed(5)
+    model = SuperResolutionNet(scale_factor=2, num_features=32, num_residual_blocks=2).cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    x = torch.rand(2, 3, 3, 20, 28)
+    tgt = torch.rand(2, 3, 40, 56)
+    o_out, o_loss, o_grads = sr_oracle.train_step_grads(sd, x, tgt, 2, True)
+    model.compute_dtype = torch.float32
+    out = model(x.cuda())
+    torch.nn.functional.mse_loss(out, tgt.cuda()).backward()
+    assert relerr(out, o_out) <= FP32_TOL
+    for n, p in model.named_parameters():
+        assert relerr(p.grad, o_grads[n]) <= 2 * FP32_TOL, n
+
+
+@pytest.mark.parametrize("name", ["sr_tiny_x2_train.npz", "sr_default_x2_train.npz"])
+def test_bf16_psnr_delta(name):
+    """bf16 path vs the fp32 reference output: |PSNR(bf16, target) - PSNR(ref, target)| <= 0.05 dB and the
+    bf16 output itself within 40 dB PSNR of the reference output."""
+    g, model, out, inter, loss = run_case(name, torch.bfloat16)
+    ref = torch.from_numpy(g["out"])
+    tgt = torch.from_numpy(g["target"])
+    assert abs(psnr(out, tgt) - psnr(ref, tgt)) <= 0.05
+    assert psnr(out, ref) >= 40.0
+
+
+def test_module_contract():
+    from nerve_cl_b200.models import SuperResolutionNet
+    m = SuperResolutionNet(scale_factor=2, num_features=16, num_residual_blocks=1).cuda().eval()
+    with torch.no_grad():
+        y = m(torch.rand(1, 3, 3, 16, 16, device="cuda"))
+        y1 = m.forward_single(torch.rand(1, 3, 16, 16, device="cuda"))
+    assert y.shape == (1, 3, 32, 32) and y1.shape == (1, 3, 32, 32)
+    assert float(y.min()) >= 0 and float(y.max()) <= 1
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 5, 3, 16, 16, device="cuda"))       # wrong T, as in the reference
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 3, 3, 16, 16))                       # CPU input: no fallback
