@@ -85,7 +85,7 @@ class _SRFunction(torch.autograd.Function):
         names = module._param_names
         P = {n: p.detach() for n, p in zip(names, params)}
         BUF = {n: b for n, b in module.named_buffers()}
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_bwd = any(ctx.needs_input_grad[2:])     # False under no_grad or when nothing requires grad
         plan = module._plan_for(lr_frames)
         B, T, C, H, W = lr_frames.shape
         s = module.scale_factor
