@@ -39,6 +39,54 @@ CORR_PAD = 96    # correlation volume is stored with 96 channels (zeros beyond 8
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 
+class KernelTimer:
+    """CUDA-event timing of individual launches on the launching stream (bench.py roofline numbers).
+
+    ``with timer.span(kind, flops, bytes)`` brackets one op; ``summary()`` synchronises and returns
+    kind -> {launches, ms, flops, bytes}."""
+
+    def __init__(self):
+        self.records: List[Tuple[str, float, float, torch.cuda.Event, torch.cuda.Event]] = []
+
+    class _Span:
+        def __init__(self, timer, kind, flops, nbytes):
+            self.t, self.kind, self.flops, self.nbytes = timer, kind, flops, nbytes
+
+        def __enter__(self):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def __exit__(self, *exc):
+            self.e1.record()
+            self.t.records.append((self.kind, self.flops, self.nbytes, self.e0, self.e1))
+
+    def span(self, kind: str, flops: float = 0.0, nbytes: float = 0.0):
+        return KernelTimer._Span(self, kind, flops, nbytes)
+
+    def summary(self) -> Dict[str, Dict[str, float]]:
+        torch.cuda.synchronize()
+        out: Dict[str, Dict[str, float]] = {}
+        for kind, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+class _NoSpan:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOSPAN = _NoSpan()
+
+
 class ConvSpec:
     """One dense convolution of the network: where its parameters live and how they are packed."""
 
@@ -104,6 +152,7 @@ class Plan:
         self.others = [t for t in range(T) if t != self.mid]
         self.engine = CONV_AUTO
         self.div_mode = 0
+        self.timer: Optional[KernelTimer] = None
         self._free: List[Activations] = []
         self._bwd_ws = None
         F = self.F
@@ -157,22 +206,34 @@ class Plan:
                 nv.pack_conv_weight(w, self.wb[name], True)
 
     # ---- helpers ---------------------------------------------------------------------------
+    def _span(self, kind: str, x: Tensor, cin: int, cout: int, k: int):
+        """Timing span for one dense-conv launch; flops = 2 * pixels * Cin * Cout * k^2 (algorithmic)."""
+        if self.timer is None:
+            return _NOSPAN
+        npix = x.shape[0] * x.shape[1] * x.shape[2]
+        return self.timer.span(kind, 2.0 * npix * cin * cout * k * k,
+                               float(npix) * (cin + cout) * x.element_size())
+
     def conv(self, name: str, x: Tensor, out: Tensor, P, *, relu=False, res=None, res_channels=0, alpha=1.0,
              bias=True) -> None:
         c = self.convs[name]
         b = P[name + ".bias"] if (c.has_bias and bias) else None
-        nv.conv2d_fwd(x, self.wf[name], b, res, None, None, out, c.cout, relu, False,
-                      res_channels if res is not None else 0, 0, alpha, self.engine)
+        with self._span("conv_fwd", x, x.shape[-1], c.cout, c.k):
+            nv.conv2d_fwd(x, self.wf[name], b, res, None, None, out, c.cout, relu, False,
+                          res_channels if res is not None else 0, 0, alpha, self.engine)
 
     def dgrad(self, name: str, dy: Tensor, out: Tensor, *, cout=None, accumulate=False, res=None, res_channels=0,
               alpha=1.0, mask=None, mask_sub=None, mask_c0=0) -> None:
         c = self.convs[name]
-        nv.conv2d_fwd(dy, self.wb[name], None, res, mask, mask_sub, out, cout or c.cin_pad, False, accumulate,
-                      res_channels if res is not None else 0, mask_c0, alpha, self.engine)
+        with self._span("conv_dgrad", dy, dy.shape[-1], cout or c.cin_pad, c.k):
+            nv.conv2d_fwd(dy, self.wb[name], None, res, mask, mask_sub, out, cout or c.cin_pad, False, accumulate,
+                          res_channels if res is not None else 0, mask_c0, alpha, self.engine)
 
     def wgrad(self, name: str, x: Tensor, dy: Tensor, G: Dict[str, Tensor], scale: float = 1.0) -> None:
         c = self.convs[name]
-        nv.conv2d_wgrad(x, dy, G[name + ".weight"], G[name + ".bias"] if c.has_bias else None, scale, self.engine)
+        with self._span("conv_wgrad", x, x.shape[-1], dy.shape[-1], c.k):
+            nv.conv2d_wgrad(x, dy, G[name + ".weight"], G[name + ".bias"] if c.has_bias else None, scale,
+                            self.engine)
 
     # =======================================================================================
     # forward

@@ -66,6 +66,8 @@ def _flat(t: Tensor, name: str, dtype=torch.float32) -> int:
 
 lib = torch.library.Library("nervecl", "DEF")
 _impls = {}
+LAUNCHES = [0]          # number of kernel-launching op calls (bench.py reports it as gpu_launches)
+_NO_KERNEL = {"fill_zero"}   # cudaMemsetAsync, not one of our kernels
 
 
 def _op(schema: str):
@@ -74,7 +76,13 @@ def _op(schema: str):
 
     def deco(fn):
         lib.define(schema)
-        lib.impl(name, fn, "CUDA")
+        if name in _NO_KERNEL:
+            impl = fn
+        else:
+            def impl(*a, **k):
+                LAUNCHES[0] += 1
+                return fn(*a, **k)
+        lib.impl(name, impl, "CUDA")
         lib.impl(name, lambda *a, **k: None, "Meta")
         _impls[name] = fn
         return fn

@@ -1,0 +1,349 @@
+"""Per-op parity of the CUDA kernels (called through torch.ops.nervecl -> C ABI) against the oracle /
+plain ATen fp32 on the same seeded inputs.  fp32 tolerance: rel-err <= 1e-4 (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def nv():
+    from nerve_cl_b200 import ops
+    return ops.nv
+
+
+def nhwc(x, dtype=torch.float32, pad_to=0):
+    """NCHW cpu/cuda tensor -> pitched NHWC cuda view."""
+    n, c, h, w = x.shape
+    buf = torch.zeros((n, h, w, max(c, pad_to)), device="cuda", dtype=dtype)
+    buf[..., :c] = x.permute(0, 2, 3, 1).to("cuda", dtype)
+    return buf[..., :c]
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def pack(w, dtype=torch.float32, flip=False):
+    o, i, k, _ = w.shape
+    rows, cols = (i, o) if flip else (o, i)
+    dst = torch.empty((k * k, rows, (cols + 7) // 8 * 8), device="cuda", dtype=dtype)
+    nv().pack_conv_weight(w.cuda().contiguous(), dst, flip)
+    return dst
+
+
+CONV_SHAPES = [  # (N, H, W, Cin, Cout, K)
+    (2, 10, 12, 3, 16, 3), (1, 32, 32, 2, 32, 3), (1, 17, 45, 32, 2, 3), (2, 9, 33, 81, 128, 3),
+    (1, 12, 40, 64, 32, 3), (1, 8, 32, 224, 64, 1), (1, 20, 20, 2, 1, 7), (1, 33, 65, 64, 12, 3),
+    (1, 16, 64, 96, 32, 3), (1, 40, 24, 64, 3, 3),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_fwd_simt_epilogue(shape):
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(n, cout, h, w, generator=g)
+    ref = F.relu(F.conv2d(x, wt, b, 1, k // 2)) * 0.2 + res
+    out = torch.empty((n, h, w, cout), device="cuda")
+    nv().conv2d_fwd(nhwc(x, pad_to=cin + 5), pack(wt), b.cuda(), nhwc(res), None, None, out, cout, True, False,
+                    cout, 0, 0.2, ops.CONV_SIMT)
+    assert relerr(nchw(out), ref) <= TOL
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad_accumulate_mask(shape):
+    """conv2d_fwd on dY with transpose_flip weights == ATen's input gradient; accumulate + ReLU mask."""
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    x = torch.randn(n, cin, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    dy = torch.randn(n, cout, h, w, generator=g)
+    prev = torch.randn(n, cin, h, w, generator=g)
+    act = torch.randn(n, cin, h, w, generator=g)
+    (dx,) = torch.autograd.grad(F.conv2d(x, wt, None, 1, k // 2), x, dy)
+    c0 = cin // 2
+    ref = dx + prev
+    ref[:, c0:] = ref[:, c0:] * (act[:, c0:] > 0)
+    out = nhwc(prev, pad_to=cin + 3)
+    nv().conv2d_fwd(nhwc(dy), pack(wt, flip=True), None, None, nhwc(act), None, out, cin, False, True, 0, c0, 1.0,
+                    ops.CONV_SIMT)
+    assert relerr(nchw(out), ref) <= TOL
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_wgrad_simt(shape):
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape) + 2)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.zeros(cout, cin, k, k, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    dy = torch.randn(n, cout, h, w, generator=g)
+    F.conv2d(x, wt, b, 1, k // 2).backward(dy)
+    dw = torch.zeros_like(wt, device="cuda").detach()
+    db = torch.zeros(cout, device="cuda")
+    nv().conv2d_wgrad(nhwc(x, pad_to=cin + 4), nhwc(dy), dw, db, 0.5, ops.CONV_SIMT)
+    assert relerr(dw, 0.5 * wt.grad) <= TOL
+    assert relerr(db, 0.5 * b.grad) <= TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_depthwise(dtype):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 13, 19, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    wt = torch.randn(16, 1, 3, 3, generator=g, requires_grad=True)
+    xr = x.clone().requires_grad_(True)
+    y = F.conv2d(xr, wt, None, 1, 1, 1, 16)
+    dy = torch.randn_like(y)
+    if dtype == torch.bfloat16:
+        dy = dy.bfloat16().float()
+    y.backward(dy)
+    tol = TOL if dtype == torch.float32 else 2e-2
+    xo = nhwc(x, dtype)
+    yo = torch.empty_like(xo)
+    nv().dwconv3x3_fwd(xo, wt.detach().cuda(), yo, False, False)
+    assert relerr(nchw(yo), y) <= tol
+    dxo = torch.empty_like(xo)
+    nv().dwconv3x3_fwd(nhwc(dy, dtype), wt.detach().cuda(), dxo, True, False)
+    assert relerr(nchw(dxo), xr.grad) <= tol
+    dw = torch.zeros(16, 1, 3, 3, device="cuda")
+    nv().dwconv3x3_wgrad(xo, nhwc(dy, dtype), dw)
+    assert relerr(dw, wt.grad) <= tol
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_relu_groups(training):
+    """T frame groups with separate batch statistics + running-stat update in group order."""
+    T, B, C, H, W = 3, 2, 16, 9, 11
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(T * B, C, H, W, generator=g) * 2 + 0.5
+    gamma = (torch.rand(C, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.1).requires_grad_(True)
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    res = torch.randn(T * B, C, H, W, generator=g)
+    dy = torch.randn(T * B, C, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    rm_r, rv_r = rm.clone(), rv.clone()
+    ys = [F.relu(F.batch_norm(xr[t * B:(t + 1) * B], rm_r, rv_r, gamma, beta, training, 0.1, 1e-5)) for t in range(T)]
+    y = torch.cat(ys) + res
+    y.backward(dy)
+
+    xo = nhwc(x)
+    sums = torch.zeros(T, C, 2, device="cuda", dtype=torch.float64)
+    stat = torch.empty(T, C, 2, device="cuda")
+    rmc, rvc = rm.cuda(), rv.cuda()
+    nbt = torch.zeros((), device="cuda", dtype=torch.int64)
+    if training:
+        nv().bn_stats(xo, T, sums)
+    nv().bn_finalize(sums if training else None, stat, rmc, rvc, nbt, B * H * W, T, 0.1, 1e-5, training)
+    yo = torch.empty_like(xo)
+    nv().bn_relu_fwd(xo, stat, gamma.detach().cuda(), beta.detach().cuda(), nhwc(res), yo, T)
+    assert relerr(nchw(yo), y) <= TOL
+    assert relerr(rmc, rm_r) <= TOL and relerr(rvc, rv_r) <= TOL
+    assert int(nbt) == (T if training else 0)
+    bs = torch.zeros(T, C, 2, device="cuda", dtype=torch.float64)
+    dyo = nhwc(dy)
+    nv().bn_relu_bwd_reduce(xo, dyo, stat, gamma.detach().cuda(), beta.detach().cuda(), T, bs)
+    dx = torch.empty_like(xo)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    nv().bn_relu_bwd_apply(xo, dyo, stat, gamma.detach().cuda(), beta.detach().cuda(), bs, dx, dg, db, T, training)
+    assert relerr(nchw(dx), xr.grad) <= TOL
+    assert relerr(dg, gamma.grad) <= TOL and relerr(db, beta.grad) <= TOL
+
+
+def test_correlation_golden_and_grad():
+    from oracle import sr_oracle
+    gold = load_golden("corr_case.npz")
+    x1, x2 = torch.from_numpy(gold["x1"]), torch.from_numpy(gold["x2"])
+    out = torch.empty((2, 11, 14, 96), device="cuda")
+    nv().corr_fwd(nhwc(x1), nhwc(x2), out)
+    assert relerr(nchw(out[..., :81]), torch.from_numpy(gold["out"])) <= TOL
+    assert float(out[..., 81:].abs().max()) == 0.0
+    a, b = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    dy = torch.randn(2, 81, 11, 14, generator=torch.Generator().manual_seed(8))
+    sr_oracle.correlation(a, b).backward(dy)
+    d1, d2 = torch.empty((2, 11, 14, 8), device="cuda"), torch.empty((2, 11, 14, 8), device="cuda")
+    nv().corr_bwd(nhwc(x1), nhwc(x2), nhwc(dy, pad_to=96), d1, False, d2, False)
+    assert relerr(nchw(d1), a.grad) <= TOL and relerr(nchw(d2), b.grad) <= TOL
+
+
+def test_warp_indices_bit_exact_vs_cpu_golden():
+    """div_mode=1 replays ATen-CPU's division: indices must equal the golden (CPU reference) ones exactly."""
+    from nerve_cl_b200.models import warp_indices, warp_features
+    gold = load_golden("warp_cases.npz")
+    for hw in ("9x13", "36x64"):
+        feat = torch.from_numpy(gold[f"{hw}/feat"]).cuda()
+        feat8 = torch.cat([feat, feat], 1)                      # kernels need C % 8 == 0
+        for i in range(10):
+            flow = torch.from_numpy(gold[f"{hw}/{i}/flow"]).cuda()
+            idx = warp_indices(flow, div_mode=1).cpu().numpy()
+            want = gold[f"{hw}/{i}/idx"].astype(np.int64)
+            # indices far outside the image all mean "zero padding"; compare after clamping to [-2, size+1]
+            h, w = [int(v) for v in hw.split("x")]
+            lo, hi = np.array([-2, -2]), np.array([w + 1, h + 1])
+            assert np.array_equal(np.clip(idx, lo, hi), np.clip(want, lo, hi)), (hw, i)
+            out = warp_features(feat8, flow, div_mode=1)
+            ref = torch.from_numpy(gold[f"{hw}/{i}/out"])
+            assert relerr(out[:, :4], ref) <= TOL or float((out[:, :4].cpu() - ref).abs().max()) < 1e-6, (hw, i)
+
+
+def structured_flow(b, h, w):
+    ys = torch.arange(h).view(1, h, 1).expand(b, h, w)
+    xs = torch.arange(w).view(1, 1, w).expand(b, h, w)
+    fx = ((xs * 7 + ys * 3) % 33 - 16).float() * 0.25 + 2.0 ** -12
+    fy = ((xs * 5 + ys * 11) % 29 - 14).float() * 0.125 - 2.0 ** -11
+    return torch.stack([fx, fy], 1)
+
+
+def test_warp_indices_full_size_cpu_golden_and_live_cuda():
+    """360x640 (BASELINE cfg 2 size): bit-exact vs the CPU-reference golden (div_mode=1) AND vs the oracle
+    run by ATen-CUDA on this GPU (div_mode=0, the reciprocal-multiply path)."""
+    from oracle import sr_oracle
+    from nerve_cl_b200.models import warp_indices
+    gold = load_golden("warp_cases.npz")
+    h, w = 360, 640
+    lo, hi = np.array([-2, -2]), np.array([w + 1, h + 1])
+    flows = {"zero": torch.zeros(1, 2, h, w), "structured": structured_flow(1, h, w)}
+    for name, flow in flows.items():
+        got = warp_indices(flow.cuda(), div_mode=1).cpu().numpy()
+        assert np.array_equal(np.clip(got, lo, hi), np.clip(gold[f"{h}x{w}/{name}/idx"].astype(np.int64), lo, hi)), name
+    g = torch.Generator().manual_seed(77)
+    rnd = 3 * torch.randn(2, 2, h, w, generator=g)
+    for flow in list(flows.values()) + [rnd, rnd.round(), rnd.round() + 0.5]:
+        live = sr_oracle.warp_corner_indices(flow.cuda()).cpu().numpy()          # ATen-CUDA
+        got = warp_indices(flow.cuda(), div_mode=0).cpu().numpy()
+        assert np.array_equal(np.clip(got, lo, hi), np.clip(live, lo, hi))
+
+
+def test_warp_backward():
+    from oracle import sr_oracle
+    from nerve_cl_b200.models import warp_features
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn(2, 16, 12, 15, generator=g)
+    flow = 2.5 * torch.randn(2, 2, 12, 15, generator=g) + 0.013
+    dy = torch.randn(2, 16, 12, 15, generator=g)
+    a, b = feat.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    sr_oracle.warp(a, b).backward(dy)
+    fa, fb = feat.cuda().requires_grad_(True), flow.cuda().requires_grad_(True)
+    warp_features(fa, fb, div_mode=1).backward(dy.cuda())
+    assert relerr(fa.grad, a.grad) <= TOL
+    assert relerr(fb.grad, b.grad) <= TOL
+
+
+def test_temporal_fusion():
+    T, B, C, H, W = 3, 2, 16, 7, 9
+    g = torch.Generator().manual_seed(10)
+    feats = torch.randn(B, T, C, H, W, generator=g, requires_grad=True)
+    logits = torch.randn(B, T, H, W, generator=g, requires_grad=True)
+    bias = torch.randn(B, C, generator=g)
+    dy = torch.randn(B, C, H, W, generator=g)
+    attn = torch.softmax(logits, 1)
+    out = (feats * attn.unsqueeze(2)).sum(1)
+    out.backward(dy + bias[:, :, None, None])
+    cat = nhwc(feats.detach().reshape(B, T * C, H, W))
+    lg = logits.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    at = torch.empty_like(lg)
+    o = torch.empty((B, H, W, C), device="cuda")
+    nv().tfuse_fwd(cat, lg, at, o)
+    assert relerr(nchw(o), out) <= TOL and relerr(at.permute(0, 3, 1, 2), attn) <= TOL
+    dcat, dlg = torch.empty_like(cat), torch.empty_like(lg)
+    nv().tfuse_bwd(cat, at, nhwc(dy), bias.cuda(), dcat, dlg)
+    assert relerr(nchw(dcat), feats.grad.reshape(B, T * C, H, W)) <= TOL
+    assert relerr(dlg.permute(0, 3, 1, 2), logits.grad) <= TOL
+
+
+def test_cbam_forward_backward():
+    from oracle import sr_oracle
+    B, C, H, W = 2, 32, 11, 13
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    sd = {"temporal_aggregator.refine.channel_attention.fc.0.weight": torch.randn(2, C, generator=g).requires_grad_(True),
+          "temporal_aggregator.refine.channel_attention.fc.2.weight": torch.randn(C, 2, generator=g).requires_grad_(True),
+          "temporal_aggregator.refine.spatial_attention.conv.weight": (0.2 * torch.randn(1, 2, 7, 7, generator=g)).requires_grad_(True)}
+    w1, w2, w7 = sd.values()
+    dy = torch.randn(B, C, H, W, generator=g)
+    y = sr_oracle.spatial_attention(sd, sr_oracle.channel_attention(sd, x))
+    y.backward(dy)
+
+    xo = nhwc(x.detach())
+    pool = torch.zeros(B, C, device="cuda")
+    nv().chan_sum(xo, 1.0 / (H * W), pool)
+    hidden, gate = torch.empty(B, 2, device="cuda"), torch.empty(B, C, device="cuda")
+    w1c, w2c, w7c = w1.detach().cuda(), w2.detach().cuda(), w7.detach().cuda()
+    nv().ca_gate_fwd(pool, w1c, w2c, hidden, gate)
+    stats = torch.empty(B, H, W, 2, device="cuda")
+    nv().cbam_stats_fwd(xo, gate, stats)
+    sg, out = torch.empty(B, H, W, device="cuda"), torch.empty_like(xo)
+    nv().cbam_apply_fwd(xo, gate, stats, w7c, sg, out)
+    assert relerr(nchw(out), y) <= TOL
+    dz = torch.empty(B, H, W, device="cuda")
+    dyo = nhwc(dy)
+    nv().cbam_bwd_dz(xo, gate, sg, dyo, dz)
+    dstats, dw7 = torch.empty_like(stats), torch.zeros_like(w7c)
+    nv().cbam_bwd_spatial(dz, stats, w7c, dstats, dw7)
+    dx, dgate = torch.empty_like(xo), torch.zeros(B, C, device="cuda")
+    nv().cbam_bwd_dx(xo, gate, sg, stats, dstats, dyo, dx, dgate)
+    dpool, dw1, dw2 = torch.empty(B, C, device="cuda"), torch.zeros_like(w1c), torch.zeros_like(w2c)
+    nv().ca_gate_bwd(pool, w1c, w2c, hidden, gate, dgate, dpool, dw1, dw2)
+    full_dx = nchw(dx) + (dpool / (H * W))[:, :, None, None]
+    assert relerr(full_dx, x.grad) <= TOL
+    assert relerr(dw1, w1.grad) <= TOL and relerr(dw2, w2.grad) <= TOL and relerr(dw7, w7.grad) <= TOL
+
+
+@pytest.mark.parametrize("s", [2, 3, 4])
+def test_output_stage(s):
+    B, H, W = 2, 9, 12
+    g = torch.Generator().manual_seed(12 + s)
+    conv = (0.3 * torch.randn(B, 3 * s * s, H, W, generator=g)).requires_grad_(True)
+    lr = torch.rand(B, 5, 3, H, W, generator=g)[:, 2]            # strided view like lr_frames[:, mid]
+    dy = torch.randn(B, 3, H * s, W * s, generator=g)
+    ref = torch.clamp(F.interpolate(lr, scale_factor=s, mode="bicubic", align_corners=False)
+                      + F.pixel_shuffle(conv, s), 0, 1)
+    ref.backward(dy)
+    co = conv.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    lrc = torch.rand(B, 5, 3, H, W, device="cuda")
+    lrc[:, 2] = lr.cuda()
+    out = torch.empty(B, 3, H * s, W * s, device="cuda")
+    nv().upfinish_fwd(co, lrc[:, 2], out, s)
+    assert relerr(out, ref) <= TOL
+    dconv = torch.empty_like(co)
+    nv().upfinish_bwd(co, lrc[:, 2], dy.cuda(), dconv, s)
+    assert relerr(dconv.permute(0, 3, 1, 2), conv.grad) <= TOL
+
+
+def test_elementwise_helpers():
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 16, 5, 7, generator=g)
+    y = torch.randn(2, 16, 5, 7, generator=g)
+    o = nhwc(y, torch.bfloat16, pad_to=24)
+    nv().axpy(nhwc(x), o, 0.5, True)
+    assert relerr(nchw(o), y.bfloat16().float() + 0.5 * x) <= 1e-2
+    o3 = torch.zeros(2, 5, 7, 8, device="cuda", dtype=torch.bfloat16)
+    x3 = torch.randn(2, 3, 5, 7, generator=g)
+    nv().axpy(nhwc(x3), o3[..., :3], 1.0, False)                 # scalar path (C % 4 != 0)
+    assert relerr(nchw(o3[..., :3]), x3) <= 1e-2
+    out = torch.empty(2, 5, 7, 16, device="cuda")
+    nv().relu_bwd(nhwc(x), nhwc(y), None, out)
+    assert torch.equal(nchw(out).cpu(), x * (y > 0))
+    a, b = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    loss, dg = torch.zeros(1, device="cuda"), torch.empty(1000, device="cuda")
+    nv().mse_fwd_bwd(a.cuda(), b.cuda(), dg, loss, 1.0 / 1000)
+    assert abs(float(loss) - float(F.mse_loss(a, b))) <= 1e-6
+    assert relerr(dg, 2 * (a - b) / 1000) <= 1e-6
+
+
+def test_ops_reject_cpu_tensors():
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        nv().fill_zero(torch.zeros(4))
