@@ -1,10 +1,453 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution -- placeholder until the engine lands.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate in TMEM).
+//
+// GEMM view of conv2d (stride 1, "same" zero padding) on NHWC activations:
+//     D[pixel, co] = sum over k-blocks (tap, 64- or 32-channel chunk) of  A[pixel + tap, ci] * B[tap][co][ci]
+//   M tile = 128 output pixels (BH x BW patch, BH*BW = 128),  N = Cout rounded up to 16 (<= 256, one N tile),
+//   K loop = K*K taps x ceil(Cin / KC) chunks.
+// There is no im2col buffer: the A tile of one (tap, chunk) is ONE 4-D TMA box {KC, BW, BH, 1} of the
+// activation tensor at coordinates {c0, x0 + kx - r, y0 + ky - r, n}; TMA's out-of-bounds zero fill
+// provides the conv padding, the channel tail and the ragged right/bottom tiles.  The box lands in
+// shared memory as 128 rows of KC bf16 with the 128B (KC=64) / 64B (KC=32) swizzle, which is exactly the
+// canonical K-major UMMA operand layout, so tcgen05.mma consumes it through a shared-memory descriptor.
+//
+// Persistent, warp-specialised CTA (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// owner), warps 2..5 = epilogue (TMEM -> registers -> fused bias/ReLU/scale/residual/accumulate/mask ->
+// global).  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "conv_internal.cuh"
 
+using namespace nv;
+
+namespace {
+
+constexpr int BM = 128;                 // pixels per tile == TMEM lanes == UMMA M
+constexpr int kThreads = 192;           // 6 warps
+constexpr uint32_t kSpinLimit = 400u * 1000u * 1000u;   // deadlock guard: trap instead of hanging the GPU
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand whose rows are one swizzle span (128 B or 64 B):
+// start address >>4 | LBO (unused for swizzled K-major) | SBO = 8 rows * row bytes | version 1 | layout type.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                               // leading byte offset field (ignored here)
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;         // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;      // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return d;
+}
+// Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcArgs {
+  int N, H, W, Cout;
+  int BN;          // Cout rounded up to 16
+  int K;           // kernel size
+  int nchunks;     // ceil(Cin / KC)
+  int bw_shift;    // BW = 1 << bw_shift, BH = 128 >> bw_shift
+  int tiles_x, tiles_y;
+  int stages;
+  int relu, accumulate, res_channels, mask_c0;
+  float alpha;
+  const float* bias;
+  const bf16* res;  int64_t ldres;
+  const bf16* mask; int64_t ldmask;
+  const bf16* msub; int64_t ldmsub;
+  bf16* out;        int64_t ldo;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcArgs a) {
+  constexpr uint32_t ROW_BYTES = KC * 2;
+  constexpr uint32_t A_BYTES = BM * ROW_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A tile | B tile)] 1024-aligned, then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_bytes = (uint32_t)a.BN * ROW_BYTES;
+  const uint32_t stage_bytes = (A_BYTES + b_bytes + 1023u) & ~1023u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+  uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
+  uint64_t* empty_bar = bars + a.stages;           // [stages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * a.stages;       // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = a.N * a.tiles_y * a.tiles_x;
+  const int kblocks = a.K * a.K * a.nchunks;
+  const uint32_t tmem_cols = a.BN * 2 <= 32 ? 32 : a.BN * 2 <= 64 ? 64 : a.BN * 2 <= 128 ? 128 : a.BN * 2 <= 256 ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);     // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int R = a.K / 2;
+  const int BW = 1 << a.bw_shift;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tx = tile % a.tiles_x;
+        int r = tile / a.tiles_x;
+        int ty = r % a.tiles_y;
+        int n = r / a.tiles_y;
+        int x0 = tx << a.bw_shift, y0 = ty * (BM >> a.bw_shift);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          int tap = kb / a.nchunks, chunk = kb - tap * a.nchunks;
+          int ky = tap / a.K, kx = tap - ky * a.K;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], A_BYTES + b_bytes);
+          tma_load_4d(sa, &tmap_x, &full_bar[stage], chunk * KC, x0 + kx - R, y0 + ky - R, n);
+          tma_load_3d(sa + A_BYTES, &tmap_w, &full_bar[stage], chunk * KC, 0, tap);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16((uint32_t)a.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t da = make_kmajor_desc(sa, ROW_BYTES);
+          const uint64_t db = make_kmajor_desc(sa + A_BYTES, ROW_BYTES);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (>>4) address field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                      // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                         // tile row == pixel within the tile
+    const int ty_in = row >> a.bw_shift, tx_in = row & (BW - 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int tx = tile % a.tiles_x;
+      int r = tile / a.tiles_x;
+      int ty = r % a.tiles_y;
+      int n = r / a.tiles_y;
+      const int y = ty * (BM >> a.bw_shift) + ty_in, x = (tx << a.bw_shift) + tx_in;
+      const bool valid = (y < a.H) && (x < a.W);
+      const int64_t p = ((int64_t)n * a.H + y) * a.W + x;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.BN);
+      for (int c0 = 0; c0 < a.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid && c0 < a.Cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c0 + j < a.Cout) f[j] += __ldg(a.bias + c0 + j);
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= a.alpha;
+          const bool full16 = (c0 + 16 <= a.Cout);
+          if (a.res && c0 < a.res_channels) {
+            const bf16* rp = a.res + p * a.ldres + c0;
+            if (c0 + 16 <= a.res_channels) {
+              f8 r0 = ld8(rp), r1 = ld8(rp + 8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { f[j] += r0.v[j]; f[8 + j] += r1.v[j]; }
+            } else {
+              for (int j = 0; j < 16 && c0 + j < a.res_channels; ++j) f[j] += ldf(rp + j);
+            }
+          }
+          bf16* op = a.out + p * a.ldo + c0;
+          if (a.accumulate) {
+            if (full16) {
+              f8 o0 = ld8(op), o1 = ld8(op + 8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { f[j] += o0.v[j]; f[8 + j] += o1.v[j]; }
+            } else {
+              for (int j = 0; j < 16 && c0 + j < a.Cout; ++j) f[j] += ldf(op + j);
+            }
+          }
+          if (a.mask && c0 + 16 > a.mask_c0) {
+            const bf16* mp = a.mask + p * a.ldmask + c0;
+            const bf16* sp = a.msub ? a.msub + p * a.ldmsub + c0 : nullptr;
+            for (int j = 0; j < 16 && c0 + j < a.Cout; ++j) {
+              if (c0 + j < a.mask_c0) continue;
+              float m = ldf(mp + j);
+              if (sp) m -= ldf(sp + j);
+              if (!(m > 0.f)) f[j] = 0.f;
+            }
+          }
+          if (full16) {
+            f8 o0, o1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o0.v[j] = f[j]; o1.v[j] = f[8 + j]; }
+            st8(op, o0);
+            st8(op + 8, o1);
+          } else {
+            for (int j = 0; j < 16 && c0 + j < a.Cout; ++j) stf(op + j, f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+inline int tile_bw_shift(int W) {
+  int s = 7;                          // BW = 128
+  while (s > 3 && (1 << s) > W) --s;  // largest power of two <= W, at least 8
+  return s;
+}
+
+inline int pick_kc(int cin) { return (cin % 64 == 0) ? 64 : 32; }
+
+}  // namespace
+
 namespace nv {
-bool conv_tc_fwd_supported(const nervecl_conv_params&) { return false; }
-int conv_tc_fwd(const nervecl_conv_params&, cudaStream_t) { return NERVECL_EUNSUPPORTED; }
+
+bool conv_tc_fwd_supported(const nervecl_conv_params& a) {
+  if (a.dtype != NERVECL_BF16 || a.out_dtype != NERVECL_BF16) return false;
+  if (a.K != 1 && a.K != 3) return false;
+  if (a.Cin < 16 || a.Cin % 8 || a.Cout < 16 || a.Cout > 256) return false;
+  if (a.ldx % 8 || a.w_ld % 8 || a.ldo % 8) return false;
+  if (!aligned(a.x, 16) || !aligned(a.w, 16) || !aligned(a.out, 16)) return false;
+  if (a.res && (a.ldres % 8 || !aligned(a.res, 16))) return false;
+  if (a.accumulate && a.Cout % 8) return false;
+  if (a.w_rows < a.Cout) return false;
+  if ((int64_t)a.N * a.H * a.W < 128) return false;
+  return encode_fn() != nullptr;
+}
+
+int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return NERVECL_EUNSUPPORTED;
+  const int KC = pick_kc(a.Cin);
+  const int BN = (a.Cout + 15) / 16 * 16;
+  const int bw_shift = tile_bw_shift(a.W);
+  const int BW = 1 << bw_shift, BH = BM >> bw_shift;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+  CUtensorMap tx, tw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ldx * 2, (cuuint64_t)a.W * a.ldx * 2, (cuuint64_t)a.H * a.W * a.ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERVECL_EUNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.w_ld, (cuuint64_t)a.w_rows, (cuuint64_t)(a.K * a.K)};
+    cuuint64_t strides[2] = {(cuuint64_t)a.w_ld * 2, (cuuint64_t)a.w_rows * a.w_ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a.w), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERVECL_EUNSUPPORTED;
+  }
+
+  TcArgs t;
+  t.N = a.N; t.H = a.H; t.W = a.W; t.Cout = a.Cout; t.BN = BN; t.K = a.K;
+  t.nchunks = (a.Cin + KC - 1) / KC;
+  t.bw_shift = bw_shift;
+  t.tiles_x = (a.W + BW - 1) / BW;
+  t.tiles_y = (a.H + BH - 1) / BH;
+  t.relu = a.relu; t.accumulate = a.accumulate; t.res_channels = a.res ? a.res_channels : 0; t.mask_c0 = a.mask_c0;
+  t.alpha = a.alpha;
+  t.bias = a.bias;
+  t.res = (const bf16*)a.res; t.ldres = a.ldres;
+  t.mask = (const bf16*)a.mask; t.ldmask = a.ldmask;
+  t.msub = (const bf16*)a.mask_sub; t.ldmsub = a.ldmask_sub;
+  t.out = (bf16*)a.out; t.ldo = a.ldo;
+
+  const size_t stage_bytes = ((size_t)BM * KC * 2 + (size_t)BN * KC * 2 + 1023) & ~(size_t)1023;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return NERVECL_EUNSUPPORTED;
+  t.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+
+  const int64_t num_tiles = (int64_t)a.N * t.tiles_y * t.tiles_x;
+  int dev = 0, sms = kSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)imin(num_tiles, sms);
+  cudaError_t e;
+  if (KC == 64) {
+    e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    conv_tc_kernel<64><<<grid, kThreads, smem, s>>>(tx, tw, t);
+  } else {
+    e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    conv_tc_kernel<32><<<grid, kThreads, smem, s>>>(tx, tw, t);
+  }
+  return launch_status();
+}
+
 bool conv_tc_wgrad_supported(const void*, int64_t, const void*, int64_t, int, int, int, int, int, int, int) {
   return false;
 }
@@ -12,4 +455,5 @@ int conv_tc_wgrad(const void*, int64_t, const void*, int64_t, float*, float*, in
                   cudaStream_t) {
   return NERVECL_EUNSUPPORTED;
 }
+
 }  // namespace nv

@@ -347,3 +347,71 @@ def test_elementwise_helpers():
 def test_ops_reject_cpu_tensors():
     with pytest.raises((RuntimeError, NotImplementedError)):
         nv().fill_zero(torch.zeros(4))
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 implicit-GEMM engine (bf16): same contract as the SIMT engine, checked against fp32 ATen on
+# bf16-rounded operands (error budget: fp32 accumulation order + one bf16 rounding of the output)
+# ---------------------------------------------------------------------------------------------
+TC_SHAPES = [  # (N, H, W, Cin, Cout, K)
+    (1, 16, 128, 64, 32, 3), (2, 20, 72, 96, 32, 3), (1, 9, 200, 192, 32, 3), (1, 24, 40, 64, 64, 3),
+    (1, 16, 64, 224, 64, 1), (1, 12, 136, 32, 192, 3), (2, 8, 16, 128, 64, 3), (1, 33, 65, 96, 128, 3),
+    (1, 30, 257, 160, 32, 3), (3, 11, 23, 64, 64, 1), (1, 16, 32, 32, 224, 1), (1, 360, 640, 64, 32, 3),
+]
+BF16_TOL = 6e-3
+
+
+def bf(x):
+    return x.bfloat16().float()
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_fwd_tcgen05_epilogue(shape):
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape) + 7)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    res = bf(torch.randn(n, cout, h, w, generator=g))
+    ref = F.relu(F.conv2d(x, wt, b, 1, k // 2)) * 0.2 + res
+    out = torch.full((n, h, w, cout + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    nv().conv2d_fwd(nhwc(x, torch.bfloat16, pad_to=cin + 8), pack(wt, torch.bfloat16), b.cuda(),
+                    nhwc(res, torch.bfloat16), None, None, out[..., :cout], cout, True, False, cout, 0, 0.2,
+                    ops.CONV_TC)
+    assert relerr(nchw(out[..., :cout]), ref) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0          # never writes outside its slice
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES[:11])
+def test_conv_dgrad_tcgen05_accumulate_mask(shape):
+    from nerve_cl_b200 import ops
+    n, h, w, cout, cin, k = shape          # roles swapped: dY has `cout` channels, dX has `cin`
+    g = torch.Generator().manual_seed(sum(shape) + 8)
+    x = torch.randn(n, cin, h, w, generator=g, requires_grad=True)
+    wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cout * k * k) ** 0.5)
+    dy = bf(torch.randn(n, cout, h, w, generator=g))
+    prev = bf(torch.randn(n, cin, h, w, generator=g))
+    act = bf(torch.randn(n, cin, h, w, generator=g))
+    (dx,) = torch.autograd.grad(F.conv2d(x, wt, None, 1, k // 2), x, dy)
+    c0 = (cin // 2) // 8 * 8 + 3
+    ref = 0.5 * dx + prev
+    ref[:, c0:] = ref[:, c0:] * (act[:, c0:] > 0)
+    out = nhwc(prev, torch.bfloat16, pad_to=cin + 8)
+    nv().conv2d_fwd(nhwc(dy, torch.bfloat16), pack(wt, torch.bfloat16, flip=True), None, None,
+                    nhwc(act, torch.bfloat16), None, out, cin, False, True, 0, c0, 0.5, ops.CONV_TC)
+    assert relerr(nchw(out), ref) <= BF16_TOL
+
+
+def test_conv_tc_matches_simt_bitwise_inputs():
+    """Same bf16 operands through both engines: results agree to bf16 rounding (different summation order)."""
+    from nerve_cl_b200 import ops
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(1, 96, 40, 136, generator=g)
+    wt = torch.randn(32, 96, 3, 3, generator=g) / 30
+    xo, wp = nhwc(x, torch.bfloat16), pack(wt, torch.bfloat16)
+    o1 = torch.empty((1, 40, 136, 32), device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    nv().conv2d_fwd(xo, wp, None, None, None, None, o1, 32, False, False, 0, 0, 1.0, ops.CONV_SIMT)
+    nv().conv2d_fwd(xo, wp, None, None, None, None, o2, 32, False, False, 0, 0, 1.0, ops.CONV_TC)
+    assert relerr(o2, o1.float()) <= BF16_TOL
