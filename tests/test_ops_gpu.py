@@ -415,3 +415,29 @@ def test_conv_tc_matches_simt_bitwise_inputs():
     nv().conv2d_fwd(xo, wp, None, None, None, None, o1, 32, False, False, 0, 0, 1.0, ops.CONV_SIMT)
     nv().conv2d_fwd(xo, wp, None, None, None, None, o2, 32, False, False, 0, 0, 1.0, ops.CONV_TC)
     assert relerr(o2, o1.float()) <= BF16_TOL
+
+
+WG_SHAPES = [  # (N, H, W, Cin, Cout, K)
+    (1, 16, 128, 64, 32, 3), (2, 20, 72, 96, 32, 3), (1, 9, 200, 192, 32, 3), (1, 24, 40, 64, 64, 3),
+    (1, 16, 64, 224, 64, 1), (2, 8, 16, 128, 64, 3), (1, 33, 65, 81, 128, 3), (1, 30, 257, 160, 32, 3),
+    (3, 11, 23, 64, 64, 1), (1, 40, 136, 192, 64, 3), (2, 90, 160, 64, 32, 3),
+]
+
+
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_conv_wgrad_tcgen05(shape):
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape) + 9)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    dy = bf(torch.randn(n, cout, h, w, generator=g))
+    wt = torch.zeros(cout, cin, k, k, requires_grad=True)
+    b = torch.zeros(cout, requires_grad=True)
+    F.conv2d(x, wt, b, 1, k // 2).backward(dy)
+    dw = torch.zeros(cout, cin, k, k, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    pad = (cin + 7) // 8 * 8 + 8
+    nv().conv2d_wgrad(nhwc(x, torch.bfloat16, pad_to=pad), nhwc(dy, torch.bfloat16, pad_to=cout + 8), dw, db, 0.5,
+                      ops.CONV_TC)
+    assert relerr(dw, 0.5 * wt.grad) <= 1e-3          # operands are exact bf16, accumulation is fp32
+    assert relerr(db, 0.5 * b.grad) <= 1e-3
