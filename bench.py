@@ -264,6 +264,8 @@ def run_native(args):
     plan = next(iter(model._plans.values()))
     timer = KernelTimer()
     plan.timer = timer
+    import nerve_cl_b200.engine as _eng
+    _eng.nv.timer = timer
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ops.LAUNCHES[0]
@@ -271,7 +273,19 @@ def run_native(args):
     launches = ops.LAUNCHES[0] - launches0
     clocks = sampler.stop()
     plan.timer = None
-    ksum = timer.summary()
+    _eng.nv.timer = None
+    kdetail = timer.summary()
+    ksum = {}
+    for k, d in kdetail.items():
+        agg = ksum.setdefault(k.split("|")[0], {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for f in agg:
+            agg[f] += d[f]
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "bench_detail.json"), "w") as f:
+            json.dump({k: {"launches_per_step": d["launches"] / args.steps, "ms_per_step": d["ms"] / args.steps,
+                           "tflops": d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 and d["flops"] else None}
+                       for k, d in sorted(kdetail.items(), key=lambda kv: -kv[1]["ms"])}, f, indent=1)
 
     # ---- end to end: pinned host -> device copies and loss read-back inside the timed region ----
     losses = []
@@ -312,9 +326,11 @@ def run_native(args):
             "share_of_step": conv_ms / ms if ms else None,
             "by_kind": {k: {"launches": d["launches"], "ms": round(d["ms"], 3),
                             "tflops": d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0}
-                        for k, d in ksum.items()},
+                        for k, d in ksum.items() if k.startswith("conv")},
         },
         "loss_last": losses[-1] if losses else None,
+        "other_kernels_ms_per_step": {k: round(d["ms"] / args.steps, 3) for k, d in
+                                      sorted(ksum.items(), key=lambda kv: -kv[1]["ms"]) if not k.startswith("conv")},
     }
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -21,7 +21,8 @@ using namespace nv::tc;
 
 namespace {
 
-constexpr int kThreads = 192;           // 6 warps
+constexpr int kEpiWarps = 8;                       // 2 warps per TMEM lane quarter, splitting the columns
+constexpr int kThreads = 32 * (2 + kEpiWarps);     // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
 
 struct TcArgs {
   int N, H, W, Cout;
@@ -37,10 +38,135 @@ struct TcArgs {
   const bf16* res;  int64_t ldres;
   const bf16* mask; int64_t ldmask;
   const bf16* msub; int64_t ldmsub;
-  bf16* out;        int64_t ldo;
+  void* out;        int64_t ldo;
 };
 
-template <int KC>
+// 16 consecutive bf16 (two 16-byte loads) -> fp32
+__device__ __forceinline__ void unpack16(const uint4 (&r)[2], float (&f)[16]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r[h]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(p[i]);
+      f[h * 8 + 2 * i] = t.x;
+      f[h * 8 + 2 * i + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ void load16(const bf16* p, uint4 (&r)[2]) {
+  r[0] = *reinterpret_cast<const uint4*>(p);
+  r[1] = *reinterpret_cast<const uint4*>(p + 8);
+}
+__device__ __forceinline__ void store16(bf16* p, const float (&f)[16]) {
+  uint4 r[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&r[h]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = __floats2bfloat162_rn(f[h * 8 + 2 * i], f[h * 8 + 2 * i + 1]);
+  }
+  *reinterpret_cast<uint4*>(p) = r[0];
+  *reinterpret_cast<uint4*>(p + 8) = r[1];
+}
+__device__ __forceinline__ void store16(float* p, const float (&f)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(p + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+// One 16-column chunk of the epilogue in two phases so that the TMEM load and every global load of
+// (up to) two chunks are in flight together before anything is consumed.
+template <typename OutT>
+struct EpiChunk {
+  uint32_t v[16];
+  uint4 acc[2], res[2], msk[2], sub[2];
+  bool vec, has_res, has_mask;
+
+  __device__ __forceinline__ void issue(const TcArgs& a, uint32_t taddr, int c0, bool valid, int64_t p) {
+    tmem_ld16(taddr + (uint32_t)c0, v);
+    // fast path: the chunk lies fully inside every channel range it touches
+    vec = valid && (c0 + 16 <= a.Cout) && !(a.res && c0 < a.res_channels && c0 + 16 > a.res_channels) &&
+          !(a.mask && c0 < a.mask_c0 && c0 + 16 > a.mask_c0);
+    has_res = a.res && c0 < a.res_channels;
+    has_mask = a.mask && c0 >= a.mask_c0;
+    if (vec) {
+      if (a.accumulate) load16(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c0, acc);
+      if (has_res) load16(a.res + p * a.ldres + c0, res);
+      if (has_mask) {
+        load16(a.mask + p * a.ldmask + c0, msk);
+        if (a.msub) load16(a.msub + p * a.ldmsub + c0, sub);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void finish(const TcArgs& a, int c0, bool valid, int64_t p) {
+    if (!valid || c0 >= a.Cout) return;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    OutT* op = reinterpret_cast<OutT*>(a.out) + p * a.ldo + c0;
+    if (vec) {
+      if (a.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(a.bias + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 b = __ldg(b4 + i);
+          f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] *= a.alpha;
+      float t[16];
+      if (has_res) {
+        unpack16(res, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] += t[j];
+      }
+      if (a.accumulate) {
+        unpack16(acc, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] += t[j];
+      }
+      if (has_mask) {
+        unpack16(msk, t);
+        if (a.msub) {
+          float u[16];
+          unpack16(sub, u);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] -= u[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = t[j] > 0.f ? f[j] : 0.f;
+      }
+      store16(op, f);
+    } else {
+      // ragged chunk (Cout tail, or a range boundary inside the chunk): element-wise
+      for (int j = 0; j < 16; ++j) {
+        const int c = c0 + j;
+        if (c >= a.Cout) break;
+        float x = f[j];
+        if (a.bias) x += __ldg(a.bias + c);
+        if (a.relu) x = fmaxf(x, 0.f);
+        x *= a.alpha;
+        if (a.res && c < a.res_channels) x += ldf(a.res + p * a.ldres + c);
+        if (a.accumulate) x += ldf(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c);
+        if (a.mask && c >= a.mask_c0) {
+          float m = ldf(a.mask + p * a.ldmask + c);
+          if (a.msub) m -= ldf(a.msub + p * a.ldmsub + c);
+          if (!(m > 0.f)) x = 0.f;
+        }
+        stf(op + j, x);
+      }
+    }
+  }
+};
+
+template <int KC, typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcArgs a) {
   constexpr uint32_t ROW_BYTES = KC * 2;
@@ -71,7 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);     // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);     // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -113,6 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      bool ready = false;     // result of an early, non-blocking probe of the next stage's barrier
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -120,27 +247,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.BN);
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (!ready) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t da = make_kmajor_desc(sa, ROW_BYTES);
           const uint64_t db = make_kmajor_desc(sa + A_BYTES, ROW_BYTES);
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == a.stages) { nstage = 0; nphase ^= 1; }
+          // probe the next stage now: its latency overlaps the MMA issue below
+          ready = mbar_try_wait(&full_bar[nstage], nphase);
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (>>4) address field
             umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          stage = nstage;
+          phase = nphase;
         }
         umma_commit(&tfull_bar[acc]);                      // accumulator ready for the epilogue
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2;                      // which half of the 16-column chunks
     const int row = q * 32 + lane;                         // tile row == pixel within the tile
     const int ty_in = row >> a.bw_shift, tx_in = row & (BW - 1);
+    const int nch = a.BN >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -155,65 +290,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.BN);
-      for (int c0 = 0; c0 < a.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
+      for (int c = part; c < nch; c += 4) {
+        EpiChunk<OutT> e0, e1;
+        const bool two = c + 2 < nch;
+        e0.issue(a, taddr, c * 16, valid, p);
+        if (two) e1.issue(a, taddr, (c + 2) * 16, valid, p);
         tmem_ld_wait();
-        if (valid && c0 < a.Cout) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (a.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (c0 + j < a.Cout) f[j] += __ldg(a.bias + c0 + j);
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] *= a.alpha;
-          const bool full16 = (c0 + 16 <= a.Cout);
-          if (a.res && c0 < a.res_channels) {
-            const bf16* rp = a.res + p * a.ldres + c0;
-            if (c0 + 16 <= a.res_channels) {
-              f8 r0 = ld8(rp), r1 = ld8(rp + 8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { f[j] += r0.v[j]; f[8 + j] += r1.v[j]; }
-            } else {
-              for (int j = 0; j < 16 && c0 + j < a.res_channels; ++j) f[j] += ldf(rp + j);
-            }
-          }
-          bf16* op = a.out + p * a.ldo + c0;
-          if (a.accumulate) {
-            if (full16) {
-              f8 o0 = ld8(op), o1 = ld8(op + 8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { f[j] += o0.v[j]; f[8 + j] += o1.v[j]; }
-            } else {
-              for (int j = 0; j < 16 && c0 + j < a.Cout; ++j) f[j] += ldf(op + j);
-            }
-          }
-          if (a.mask && c0 + 16 > a.mask_c0) {
-            const bf16* mp = a.mask + p * a.ldmask + c0;
-            const bf16* sp = a.msub ? a.msub + p * a.ldmsub + c0 : nullptr;
-            for (int j = 0; j < 16 && c0 + j < a.Cout; ++j) {
-              if (c0 + j < a.mask_c0) continue;
-              float m = ldf(mp + j);
-              if (sp) m -= ldf(sp + j);
-              if (!(m > 0.f)) f[j] = 0.f;
-            }
-          }
-          if (full16) {
-            f8 o0, o1;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { o0.v[j] = f[j]; o1.v[j] = f[8 + j]; }
-            st8(op, o0);
-            st8(op + 8, o1);
-          } else {
-            for (int j = 0; j < 16 && c0 + j < a.Cout; ++j) stf(op + j, f[j]);
-          }
-        }
+        e0.finish(a, c * 16, valid, p);
+        if (two) e1.finish(a, (c + 2) * 16, valid, p);
       }
       tc_fence_before();
       __syncwarp();
@@ -228,23 +312,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------
-inline int pick_kc(int cin) { return (cin % 64 == 0) ? 64 : 32; }
+inline int pick_kc(int cin) { return cin >= 64 ? 64 : 32; }   // channel tails are zero-filled by TMA
 
 }  // namespace
 
 namespace nv {
 
 bool conv_tc_fwd_supported(const nervecl_conv_params& a) {
-  if (a.dtype != NERVECL_BF16 || a.out_dtype != NERVECL_BF16) return false;
+  if (a.dtype != NERVECL_BF16) return false;
+  if (a.out_dtype != NERVECL_BF16 && a.out_dtype != NERVECL_F32) return false;
   if (a.K != 1 && a.K != 3) return false;
-  if (a.Cin < 16 || a.Cin % 8 || a.Cout < 16 || a.Cout > 256) return false;
-  if (a.ldx % 8 || a.w_ld % 8 || a.ldo % 8) return false;
-  if (!aligned(a.x, 16) || !aligned(a.w, 16) || !aligned(a.out, 16)) return false;
+  if (a.Cin < 8 || a.Cin % 8 || a.Cout < 1 || a.Cout > 256) return false;
+  if (a.ldx % 8 || a.w_ld % 8 || !aligned(a.x, 16) || !aligned(a.w, 16)) return false;
+  if (a.Cout >= 16) {   // vector epilogue: 16 consecutive channels per thread
+    const int v = a.out_dtype == NERVECL_BF16 ? 8 : 4;
+    if (a.ldo % v || !aligned(a.out, 16)) return false;
+  }
+  if (a.bias && !aligned(a.bias, 16)) return false;
   if (a.res && (a.ldres % 8 || !aligned(a.res, 16))) return false;
-  if (a.accumulate && a.Cout % 8) return false;
+  if (a.mask && (a.ldmask % 8 || !aligned(a.mask, 16))) return false;
+  if (a.mask_sub && (a.ldmask_sub % 8 || !aligned(a.mask_sub, 16))) return false;
+  if (a.accumulate && a.out_dtype != NERVECL_BF16) return false;
   if (a.w_rows < a.Cout) return false;
   if ((int64_t)a.N * a.H * a.W < 128) return false;
   return encode_fn() != nullptr;
@@ -293,7 +381,7 @@ int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.res = (const bf16*)a.res; t.ldres = a.ldres;
   t.mask = (const bf16*)a.mask; t.ldmask = a.ldmask;
   t.msub = (const bf16*)a.mask_sub; t.ldmsub = a.ldmask_sub;
-  t.out = (bf16*)a.out; t.ldo = a.ldo;
+  t.out = a.out; t.ldo = a.ldo;
 
   const size_t stage_bytes = ((size_t)BM * KC * 2 + (size_t)BN * KC * 2 + 1023) & ~(size_t)1023;
   int stages = (int)((200 * 1024) / stage_bytes);
@@ -304,16 +392,19 @@ int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s) {
 
   const int64_t num_tiles = (int64_t)a.N * t.tiles_y * t.tiles_x;
   const int grid = (int)imin(num_tiles, sm_count());
-  cudaError_t e;
-  if (KC == 64) {
-    e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    conv_tc_kernel<64><<<grid, kThreads, smem, s>>>(tx, tw, t);
-  } else {
-    e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    conv_tc_kernel<32><<<grid, kThreads, smem, s>>>(tx, tw, t);
-  }
+  cudaError_t e = cudaSuccess;
+#define NV_LAUNCH_TC(KCV, OT)                                                                                   \
+  do {                                                                                                          \
+    e = cudaFuncSetAttribute(conv_tc_kernel<KCV, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e != cudaSuccess) return (int)e;                                                                        \
+    conv_tc_kernel<KCV, OT><<<grid, kThreads, smem, s>>>(tx, tw, t);                                            \
+  } while (0)
+  const bool f32out = a.out_dtype == NERVECL_F32;
+  if (KC == 64 && !f32out) NV_LAUNCH_TC(64, bf16);
+  else if (KC == 64) NV_LAUNCH_TC(64, float);
+  else if (!f32out) NV_LAUNCH_TC(32, bf16);
+  else NV_LAUNCH_TC(32, float);
+#undef NV_LAUNCH_TC
   return launch_status();
 }
 

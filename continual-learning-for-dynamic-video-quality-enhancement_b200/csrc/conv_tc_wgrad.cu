@@ -39,6 +39,26 @@ __device__ __forceinline__ uint32_t make_idesc_bf16_mn(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// bias gradient for channel counts the vectorised chan_sum kernel does not take (C % 4 != 0, C <= 32)
+__global__ void __launch_bounds__(256)
+colsum_small_kernel(const bf16* __restrict__ dy, int64_t ldy, int64_t npix, int C, float scale, float* __restrict__ db) {
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) acc[c] += ldf(dy + p * ldy + c);
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c < C) {
+      float v = warp_sum(acc[c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(db + c, scale * v);
+    }
+  }
+}
+
 struct WgArgs {
   int N, H, W, Cin, Cout, K;
   int NM;            // UMMA N (Cout rounded up to 16)
@@ -210,7 +230,7 @@ bool conv_tc_wgrad_supported(const void* x, int64_t ldx, const void* dy, int64_t
                              int Cin, int Cout, int K) {
   if (dtype != NERVECL_BF16) return false;
   if (K != 1 && K != 3) return false;
-  if (Cin < 16 || Cout < 16 || Cout > 128 || (Cout > 32 && Cout % 64)) return false;
+  if (Cin < 1 || Cout < 1 || Cout > 128 || (Cout > 32 && Cout % 64)) return false;
   if (ldx % 8 || ldy % 8 || !aligned(x, 16) || !aligned(dy, 16)) return false;
   if ((int64_t)N * H * W < 128) return false;
   return encode_fn() != nullptr;
@@ -277,8 +297,12 @@ int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float
   conv_tc_wgrad_kernel<<<grid, kThreads, smem, s>>>(tx, td, a);
   int rc = launch_status();
   if (rc) return rc;
-  if (db) return nervecl_chan_sum(dy, ldy, NERVECL_BF16, 1, (int64_t)N * H * W, Cout, scale, db, (nervecl_stream_t)s);
-  return NERVECL_OK;
+  if (!db) return NERVECL_OK;
+  if (Cout % 4 == 0)
+    return nervecl_chan_sum(dy, ldy, NERVECL_BF16, 1, (int64_t)N * H * W, Cout, scale, db, (nervecl_stream_t)s);
+  const int64_t npix = (int64_t)N * H * W;
+  colsum_small_kernel<<<(int)imin(cdiv(npix, 256 * 8), sms * 4), 256, 0, s>>>((const bf16*)dy, ldy, npix, Cout, scale, db);
+  return launch_status();
 }
 
 }  // namespace nv

@@ -21,7 +21,8 @@ NV_API const char* nervecl_error_string(int code) {
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pack_frames_kernel(const float* __restrict__ src, int64_t sB, int64_t sT, int64_t sC,
-                                   int64_t sH, T* __restrict__ dst, int B, int Tn, int C, int H, int W) {
+                                   int64_t sH, T* __restrict__ dst, int64_t ldd, int B, int Tn, int C, int H,
+                                   int W) {
   int64_t total = (int64_t)Tn * B * H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -32,19 +33,20 @@ __global__ void pack_frames_kernel(const float* __restrict__ src, int64_t sB, in
     int b = (int)(r % B);
     int t = (int)(r / B);
     const float* s = src + b * sB + t * sT + y * sH + x;
-    T* d = dst + i * C;
+    T* d = dst + i * ldd;
     for (int c = 0; c < C; ++c) stf(d + c, __ldg(s + c * sC));
+    for (int c = C; c < (int)ldd; ++c) stf(d + c, 0.f);     // zero the channel padding
   }
 }
 
 NV_API int nervecl_pack_frames(const float* src, int64_t sB, int64_t sT, int64_t sC, int64_t sH,
-                               void* dst, int dtype, int B, int T, int C, int H, int W,
+                               void* dst, int64_t ldd, int dtype, int B, int T, int C, int H, int W,
                                nervecl_stream_t stream) {
-  if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || H <= 0 || W <= 0) return NERVECL_EINVAL;
+  if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || H <= 0 || W <= 0 || ldd < C) return NERVECL_EINVAL;
   int64_t total = (int64_t)T * B * H * W;
   int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
   NV_DISPATCH_DTYPE(dtype, E, (pack_frames_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
-                                  src, sB, sT, sC, sH, (E*)dst, B, T, C, H, W)));
+                                  src, sB, sT, sC, sH, (E*)dst, ldd, B, T, C, H, W)));
   return launch_status();
 }
 

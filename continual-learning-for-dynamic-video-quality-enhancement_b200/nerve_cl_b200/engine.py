@@ -29,8 +29,33 @@ import torch
 from . import ops
 from ._lib import CONV_AUTO
 
-nv = ops.nv
 Tensor = torch.Tensor
+
+
+class _OpsProxy:
+    """``torch.ops.nervecl`` with optional per-op CUDA-event timing (set ``.timer`` to a KernelTimer)."""
+
+    _SPANNED_ELSEWHERE = {"conv2d_fwd", "conv2d_wgrad"}      # timed with FLOP counts by Plan._span
+
+    def __init__(self):
+        self.timer = None
+        self._raw = ops.nv
+
+    def __getattr__(self, name):
+        fn = getattr(self._raw, name)
+        if name in self._SPANNED_ELSEWHERE:
+            return fn
+
+        def call(*a, **k):
+            t = self.timer
+            if t is None:
+                return fn(*a, **k)
+            with t.span(name):
+                return fn(*a, **k)
+        return call
+
+
+nv = _OpsProxy()
 
 GROWTH = 32      # ResidualDenseBlock growth rate  (super_resolution.py:215)
 RDB_LAYERS = 5   # (super_resolution.py:216)
@@ -110,7 +135,7 @@ class Activations:
         def act(n, c, dtype=adt):
             return torch.empty((n, H, W, c), device=dev, dtype=dtype)
 
-        self.x_in = act(T * B, 3)
+        self.x_in = act(T * B, 8)              # RGB + 5 zero channels: 16-byte pixels (TMA-addressable)
         self.head = act(T * B, F)
         self.dwo = [act(T * B, F) for _ in range(3)]
         self.pwo = [act(T * B, F) for _ in range(3)]
@@ -162,7 +187,7 @@ class Plan:
         def add(name, cin, cout, k, bias=True, cin_pad=None):
             cs[name] = ConvSpec(name, cin, cout, k, bias, cin_pad)
 
-        add("feature_extractor.head.0", 3, F, 3)
+        add("feature_extractor.head.0", 3, F, 3, cin_pad=8)
         for j in range(3):
             add(f"feature_extractor.body.{j}.pointwise", F, F, 1, bias=False)
         add("motion_estimator.flow_net.0", CORR_CH, 128, 3, cin_pad=CORR_PAD)
@@ -211,7 +236,7 @@ class Plan:
         if self.timer is None:
             return _NOSPAN
         npix = x.shape[0] * x.shape[1] * x.shape[2]
-        return self.timer.span(kind, 2.0 * npix * cin * cout * k * k,
+        return self.timer.span(f"{kind}|{cin}>{cout}k{k}", 2.0 * npix * cin * cout * k * k,
                                float(npix) * (cin + cout) * x.element_size())
 
     def conv(self, name: str, x: Tensor, out: Tensor, P, *, relu=False, res=None, res_channels=0, alpha=1.0,
@@ -466,5 +491,5 @@ class Plan:
                 # extractor skip (feat = body(head) + head): d(head) = d(feat) + depthwise data gradient
                 nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], ws["dfeat"], True, True)
         nv.relu_bwd(ws["dfeat"], A.head, None, ws["t"][0])
-        self.wgrad("feature_extractor.head.0", A.x_in, ws["t"][0], G)
+        self.wgrad("feature_extractor.head.0", A.x_in[..., :3], ws["t"][0], G)
         ready("feature_extractor.")

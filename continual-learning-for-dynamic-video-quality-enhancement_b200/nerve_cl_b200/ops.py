@@ -94,7 +94,7 @@ def _op(schema: str):
 # --------------------------------------------------------------------------------------------
 @_op("pack_frames(Tensor src, Tensor(a!) dst) -> ()")
 def _pack_frames(src: Tensor, dst: Tensor) -> None:
-    """src (B,T,C,H,W) fp32 (any batch/frame/channel/row strides) -> dst [T*B,H,W,C]."""
+    """src (B,T,C,H,W) fp32 (any batch/frame/channel/row strides) -> dst [T*B,H,W,Cpad>=C], padding zeroed."""
     _cuda(src, "src")
     if src.dim() != 5 or src.dtype != torch.float32:
         raise RuntimeError("nervecl.pack_frames: src must be (B,T,C,H,W) float32")
@@ -102,10 +102,10 @@ def _pack_frames(src: Tensor, dst: Tensor) -> None:
         src = src.contiguous()
     b, t, c, h, w = src.shape
     dp, ld, n, dh, dw, dc = _nhwc(dst, "dst")
-    if (n, dh, dw, dc) != (t * b, h, w, c) or ld != c:
-        raise RuntimeError("nervecl.pack_frames: dst must be contiguous [T*B,H,W,C]")
+    if (n, dh, dw) != (t * b, h, w) or dc < c or ld != dc:
+        raise RuntimeError("nervecl.pack_frames: dst must be contiguous [T*B,H,W,Cpad] with Cpad >= C")
     _lib.check(_lib.load().nervecl_pack_frames(src.data_ptr(), src.stride(0), src.stride(1), src.stride(2),
-                                              src.stride(3), dp, _dt(dst), b, t, c, h, w, _stream()),
+                                              src.stride(3), dp, ld, _dt(dst), b, t, c, h, w, _stream()),
                "pack_frames")
 
 

@@ -60,10 +60,11 @@ int nervecl_has_tcgen05(void);
 
 /* (B,T,C,H,W) fp32 frames with arbitrary batch/frame/channel/row strides (unit column stride; a
  * stride-0 `expand`ed T as in experiments/train_baseline.py:82 is fine) -> frame-major NHWC
- * [T][B][H][W][C] in `dtype`.  Replaces the per-frame slicing lr_frames[:, t] at
- * super_resolution.py:346-349. */
+ * [T][B][H][W][ldd] in `dtype`; channels C..ldd-1 are written as zero (the head conv reads 8-channel
+ * pixels so that its rows are 16-byte aligned for TMA).  Replaces the per-frame slicing
+ * lr_frames[:, t] at super_resolution.py:346-349. */
 int nervecl_pack_frames(const float* src, int64_t sB, int64_t sT, int64_t sC, int64_t sH,
-                        void* dst, int dtype, int B, int T, int C, int H, int W,
+                        void* dst, int64_t ldd, int dtype, int B, int T, int C, int H, int W,
                         nervecl_stream_t stream);
 
 /* NHWC (dtype) channel slice -> NCHW fp32 contiguous.  Used only to hand intermediates back to

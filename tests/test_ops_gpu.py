@@ -417,7 +417,25 @@ def test_conv_tc_matches_simt_bitwise_inputs():
     assert relerr(o2, o1.float()) <= BF16_TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 24, 136, 64, 12, 3), (2, 17, 40, 32, 2, 3), (1, 20, 64, 64, 3, 3),
+                                   (2, 12, 48, 8, 64, 3)])
+def test_conv_fwd_tcgen05_fp32_out_small_channels(shape):
+    """fp32 output (flow / logits / upsampler) and channel counts below one MMA chunk (Cout < 16, Cin = 8)."""
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, k = shape
+    g = torch.Generator().manual_seed(sum(shape) + 17)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, wt, b, 1, k // 2)
+    out = torch.full((n, h, w, cout), 7.0, device="cuda", dtype=torch.float32)
+    nv().conv2d_fwd(nhwc(x, torch.bfloat16), pack(wt, torch.bfloat16), b.cuda(), None, None, None, out, cout,
+                    False, False, 0, 0, 1.0, ops.CONV_TC)
+    assert relerr(nchw(out), ref) <= 1e-3
+
+
 WG_SHAPES = [  # (N, H, W, Cin, Cout, K)
+    (1, 20, 72, 64, 12, 3), (2, 17, 40, 32, 2, 3), (1, 24, 64, 3, 64, 3),
     (1, 16, 128, 64, 32, 3), (2, 20, 72, 96, 32, 3), (1, 9, 200, 192, 32, 3), (1, 24, 40, 64, 64, 3),
     (1, 16, 64, 224, 64, 1), (2, 8, 16, 128, 64, 3), (1, 33, 65, 81, 128, 3), (1, 30, 257, 160, 32, 3),
     (3, 11, 23, 64, 64, 1), (1, 40, 136, 192, 64, 3), (2, 90, 160, 64, 32, 3),
@@ -437,7 +455,7 @@ def test_conv_wgrad_tcgen05(shape):
     dw = torch.zeros(cout, cin, k, k, device="cuda")
     db = torch.zeros(cout, device="cuda")
     pad = (cin + 7) // 8 * 8 + 8
-    nv().conv2d_wgrad(nhwc(x, torch.bfloat16, pad_to=pad), nhwc(dy, torch.bfloat16, pad_to=cout + 8), dw, db, 0.5,
+    nv().conv2d_wgrad(nhwc(x, torch.bfloat16, pad_to=pad), nhwc(dy, torch.bfloat16, pad_to=(cout + 7) // 8 * 8 + 8), dw, db, 0.5,
                       ops.CONV_TC)
     assert relerr(dw, 0.5 * wt.grad) <= 1e-3          # operands are exact bf16, accumulation is fp32
     assert relerr(db, 0.5 * b.grad) <= 1e-3
