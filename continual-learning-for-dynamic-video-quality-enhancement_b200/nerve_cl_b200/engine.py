@@ -345,7 +345,9 @@ class Plan:
 
             ws = {}
             ws["dup"] = act(B, 3 * s * s, f32)
-            ws["dup_a"] = act(B, _align(3 * s * s, 8))
+            # fp32 gradients of the three fp32-output convs, re-cast to the activation dtype in buffers whose
+            # channel count is padded to a multiple of 8 (pad channels stay zero: never written after this)
+            ws["dup_a"] = torch.zeros((B, H, W, _align(3 * s * s, 8)), device=dev, dtype=adt)
             ws["dfused"] = act(B, F)
             ws["dgff"] = act(B, F)
             ws["dtrunk"] = act(B, F)
@@ -357,12 +359,12 @@ class Plan:
             ws["dpool"] = torch.empty((B, F), device=dev, dtype=f32)
             ws["dcat"] = act(B, T * F)
             ws["dlogits"] = act(B, T, f32)
-            ws["dlogits_a"] = act(B, _align(T, 8))
+            ws["dlogits_a"] = torch.zeros((B, H, W, _align(T, 8)), device=dev, dtype=adt)
             ws["da2"], ws["da1"] = act(B, F), act(B, F)
             ws["dfeat"] = act(T * B, F)
             ws["dfeat32"] = act(B, F, f32)
             ws["dflow"] = act(B, 2, f32)
-            ws["dflow_a"] = act(B, 8)
+            ws["dflow_a"] = torch.zeros((B, H, W, 8), device=dev, dtype=adt)
             ws["dfn3"], ws["dfn2"], ws["dfn1"] = act(B, 32), act(B, 64), act(B, 128)
             ws["dcorr"] = act(B, CORR_PAD)
             ws["t"] = [act(T * B, F) for _ in range(3)]
@@ -392,7 +394,7 @@ class Plan:
         nv.axpy(ws["dup"], dup, 1.0, False)
         self.wgrad("upsampler.conv", A.fused, dup, G)
         ready("upsampler.")
-        self.dgrad("upsampler.conv", dup, ws["dfused"])
+        self.dgrad("upsampler.conv", ws["dup_a"], ws["dfused"])      # padded view: zero channels x zero weights
         nv.relu_bwd(ws["dfused"], A.fused, centre, ws["dgff"])
         self.wgrad("gff.0", A.trunk, ws["dgff"], G)
         ready("gff.")
@@ -439,7 +441,7 @@ class Plan:
         dlog = ws["dlogits_a"][..., :T]
         nv.axpy(ws["dlogits"], dlog, 1.0, False)
         self.wgrad("temporal_aggregator.attention.4", A.a2, dlog, G)
-        self.dgrad("temporal_aggregator.attention.4", dlog, ws["da2"], mask=A.a2)
+        self.dgrad("temporal_aggregator.attention.4", ws["dlogits_a"], ws["da2"], mask=A.a2)
         self.wgrad("temporal_aggregator.attention.2", A.a1, ws["da2"], G)
         self.dgrad("temporal_aggregator.attention.2", ws["da2"], ws["da1"], mask=A.a1)
         self.wgrad("temporal_aggregator.attention.0", A.cat, ws["da1"], G)
@@ -458,7 +460,7 @@ class Plan:
             dflow = ws["dflow_a"][..., :2]
             nv.axpy(ws["dflow"], dflow, 1.0, False)
             self.wgrad("motion_estimator.flow_net.6", A.fn3[t], dflow, G)
-            self.dgrad("motion_estimator.flow_net.6", dflow, ws["dfn3"], mask=A.fn3[t])
+            self.dgrad("motion_estimator.flow_net.6", ws["dflow_a"], ws["dfn3"], mask=A.fn3[t])
             self.wgrad("motion_estimator.flow_net.4", A.fn2[t], ws["dfn3"], G)
             self.dgrad("motion_estimator.flow_net.4", ws["dfn3"], ws["dfn2"], mask=A.fn2[t])
             self.wgrad("motion_estimator.flow_net.2", A.fn1[t], ws["dfn2"], G)
