@@ -24,7 +24,12 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
   cudaStream_t s = as_stream(stream);
   int engine = p->engine;
   if (engine == NERVECL_CONV_AUTO) engine = conv_tc_fwd_supported(*p) ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
-  if (engine == NERVECL_CONV_TC) {
+  if (engine == NERVECL_CONV_TC) {               // best tcgen05 kernel for the shape
+    if (conv_rows_supported(*p)) return conv_rows_fwd(*p, s);
+    if (!conv_tc_fwd_supported(*p)) return NERVECL_EUNSUPPORTED;
+    return conv_tc_fwd(*p, s);
+  }
+  if (engine == NERVECL_CONV_TC_TAPS) {          // per-tap kernel only (1x1, small shapes; A/B comparisons)
     if (!conv_tc_fwd_supported(*p)) return NERVECL_EUNSUPPORTED;
     return conv_tc_fwd(*p, s);
   }

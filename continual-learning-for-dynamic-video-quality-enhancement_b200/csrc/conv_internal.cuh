@@ -11,6 +11,9 @@ int conv_simt_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int
 // tcgen05 / TMEM / TMA implicit GEMM (conv_tc.cu)
 bool conv_tc_fwd_supported(const nervecl_conv_params& a);
 int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s);
+// row-streaming 3x3 tcgen05 kernel (conv_tc_rows.cu)
+bool conv_rows_supported(const nervecl_conv_params& a);
+int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s);
 bool conv_tc_wgrad_supported(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H,
                              int W, int Cin, int Cout, int K);
 int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float* dw, float* db, int N, int H,

@@ -1,0 +1,147 @@
+// Fused epilogue shared by the tcgen05 convolution kernels: one thread = one output pixel (TMEM lane), 16
+// consecutive output channels per chunk.  v = acc; +bias; ReLU; *alpha; +res; +out (accumulate); ReLU-mask.
+#pragma once
+#include "tc_common.cuh"
+
+namespace nv {
+namespace tc {
+
+struct EpiArgs {
+  int Cout;
+  int relu, accumulate, res_channels, mask_c0;
+  float alpha;
+  const float* bias;
+  const bf16* res;  int64_t ldres;
+  const bf16* mask; int64_t ldmask;
+  const bf16* msub; int64_t ldmsub;
+  void* out;        int64_t ldo;
+};
+
+// 16 consecutive bf16 (two 16-byte loads) -> fp32
+__device__ __forceinline__ void unpack16(const uint4 (&r)[2], float (&f)[16]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r[h]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(p[i]);
+      f[h * 8 + 2 * i] = t.x;
+      f[h * 8 + 2 * i + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ void load16(const bf16* p, uint4 (&r)[2]) {
+  r[0] = *reinterpret_cast<const uint4*>(p);
+  r[1] = *reinterpret_cast<const uint4*>(p + 8);
+}
+__device__ __forceinline__ void store16(bf16* p, const float (&f)[16]) {
+  uint4 r[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&r[h]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = __floats2bfloat162_rn(f[h * 8 + 2 * i], f[h * 8 + 2 * i + 1]);
+  }
+  *reinterpret_cast<uint4*>(p) = r[0];
+  *reinterpret_cast<uint4*>(p + 8) = r[1];
+}
+__device__ __forceinline__ void store16(float* p, const float (&f)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(p + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+// One 16-column chunk of the epilogue in two phases so that the TMEM load and every global load of
+// (up to) two chunks are in flight together before anything is consumed.
+template <typename OutT>
+struct EpiChunk {
+  uint32_t v[16];
+  uint4 acc[2], res[2], msk[2], sub[2];
+  bool vec, has_res, has_mask;
+
+  __device__ __forceinline__ void issue(const EpiArgs& a, uint32_t taddr, int c0, bool valid, int64_t p) {
+    tmem_ld16(taddr + (uint32_t)c0, v);
+    // fast path: the chunk lies fully inside every channel range it touches
+    vec = valid && (c0 + 16 <= a.Cout) && !(a.res && c0 < a.res_channels && c0 + 16 > a.res_channels) &&
+          !(a.mask && c0 < a.mask_c0 && c0 + 16 > a.mask_c0);
+    has_res = a.res && c0 < a.res_channels;
+    has_mask = a.mask && c0 >= a.mask_c0;
+    if (vec) {
+      if (a.accumulate) load16(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c0, acc);
+      if (has_res) load16(a.res + p * a.ldres + c0, res);
+      if (has_mask) {
+        load16(a.mask + p * a.ldmask + c0, msk);
+        if (a.msub) load16(a.msub + p * a.ldmsub + c0, sub);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void finish(const EpiArgs& a, int c0, bool valid, int64_t p) {
+    if (!valid || c0 >= a.Cout) return;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    OutT* op = reinterpret_cast<OutT*>(a.out) + p * a.ldo + c0;
+    if (vec) {
+      if (a.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(a.bias + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 b = __ldg(b4 + i);
+          f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] *= a.alpha;
+      float t[16];
+      if (has_res) {
+        unpack16(res, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] += t[j];
+      }
+      if (a.accumulate) {
+        unpack16(acc, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] += t[j];
+      }
+      if (has_mask) {
+        unpack16(msk, t);
+        if (a.msub) {
+          float u[16];
+          unpack16(sub, u);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] -= u[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = t[j] > 0.f ? f[j] : 0.f;
+      }
+      store16(op, f);
+    } else {
+      // ragged chunk (Cout tail, or a range boundary inside the chunk): element-wise
+      for (int j = 0; j < 16; ++j) {
+        const int c = c0 + j;
+        if (c >= a.Cout) break;
+        float x = f[j];
+        if (a.bias) x += __ldg(a.bias + c);
+        if (a.relu) x = fmaxf(x, 0.f);
+        x *= a.alpha;
+        if (a.res && c < a.res_channels) x += ldf(a.res + p * a.ldres + c);
+        if (a.accumulate) x += ldf(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c);
+        if (a.mask && c >= a.mask_c0) {
+          float m = ldf(a.mask + p * a.ldmask + c);
+          if (a.msub) m -= ldf(a.msub + p * a.ldmsub + c);
+          if (!(m > 0.f)) x = 0.f;
+        }
+        stf(op + j, x);
+      }
+    }
+  }
+};
+
+
+}  // namespace tc
+}  // namespace nv

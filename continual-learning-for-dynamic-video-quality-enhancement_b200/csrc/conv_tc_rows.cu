@@ -1,0 +1,377 @@
+// Row-streaming 3x3 convolution for sm_100a: tcgen05.mma + TMEM accumulator ring + TMA, bf16 in / fp32 accumulate.
+//
+// Why not the per-tap kernel (conv_tc.cu): there every (tap, chunk) k-block re-fetches its shifted 128-pixel A
+// tile through TMA -- 9x the L2 traffic of the input -- and with N = Cout = 32 each SS-mode MMA reads 5 KB of
+// shared memory per 16 tensor cycles, so the kernel sat at ~10 % tensor-pipe activity (profiles/r01a_summary.md).
+//
+// Here a persistent CTA owns work items (image n, 128-pixel column strip, R output rows) and streams the
+// item's R+2 input rows top to bottom:
+//   * TMA brings each halo'd input row {64 ch, 130 px} per 64-channel chunk into shared memory ONCE
+//     (128B swizzle, out-of-image pixels / rows / channels are zero-filled = conv padding);
+//   * the horizontal taps kx = 0,1,2 are three K-major smem descriptors into that same row, offset by one
+//     pixel (128 B): the 128B swizzle is a function of the absolute smem address, so an operand may start at
+//     any pixel of a 1024-aligned buffer;
+//   * the vertical taps are merged into N: input row r contributes W[ky=2] to output row r-1, W[ky=1] to r and
+//     W[ky=0] to r+1, whose accumulators occupy ADJACENT column slots of a TMEM ring, so one tcgen05.mma with
+//     N = 3*NOUT (A = row r, B = [W(ky=2) | W(ky=1) | W(ky=0)] rows) updates all three: 4 KB of A per 3*NOUT
+//     columns instead of per NOUT columns.  (3*NOUT > 256 falls back to one MMA per ky.)
+//   * all 9*Cin*NOUT weights stay resident in shared memory; output row o is final after input row o+1 and
+//     is drained by 8 epilogue warps (fused bias / ReLU / scale / residual / accumulate / ReLU-mask / store)
+//     while the MMAs of the following rows run.
+// Output channels beyond what fits (smem for weights, 128 TMEM columns per row) are split over blockIdx.y.
+#include "conv_internal.cuh"
+#include "conv_tc_epilogue.cuh"
+#include "tc_common.cuh"
+#include <cstdlib>
+
+using namespace nv;
+using namespace nv::tc;
+
+namespace {
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);     // warp 0 = TMA, warp 1 = MMA issuer, warps 2..9 = epilogue
+constexpr int KC = 64;                             // channels per chunk = one 128-byte swizzle span
+constexpr uint32_t ROWB = KC * 2;                  // bytes per pixel row of a chunk
+constexpr int PXB = BM + 2;                        // staged pixels per input row (one halo pixel each side)
+constexpr uint32_t CHUNK_BYTES = (PXB * ROWB + 1023u) & ~1023u;
+constexpr int kMaxSlots = 32;
+constexpr size_t kSmemBudget = 226 * 1024;
+
+struct RowArgs : EpiArgs {
+  int N, H, W;
+  int NOUT;         // output channels per CTA (multiple of 16, <= 128)
+  int nchunks;      // 64-channel chunks of Cin
+  int ksteps_last;  // 16-channel k-steps of the last chunk
+  int strips, R, segs;
+  int stages;       // input-row ring depth
+  int slots;        // TMEM accumulator ring depth
+  int merged;       // vertical taps merged into N
+  int dbg;          // NERVECL_ROWS_DBG bits (profiling only): 1 no MMAs, 2 no row loads, 4 no epilogue stores
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const RowArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t blk_bytes = (uint32_t)a.NOUT * ROWB;          // one ky block of one (kx, chunk) weight tile
+  const uint32_t wtile_bytes = 3u * blk_bytes;
+  const uint32_t w_bytes = 3u * (uint32_t)a.nchunks * wtile_bytes;
+  const uint32_t stage_bytes = (uint32_t)a.nchunks * CHUNK_BYTES;
+  uint8_t* w_smem = smem;
+  uint8_t* ring = smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * stage_bytes);
+  uint64_t* row_full = bars;                        // [stages]  TMA -> MMA
+  uint64_t* row_empty = row_full + a.stages;        // [stages]  MMA -> TMA
+  uint64_t* acc_full = row_empty + a.stages;        // [slots]   MMA -> epilogue
+  uint64_t* acc_empty = acc_full + a.slots;         // [slots]   epilogue -> MMA
+  uint64_t* w_bar = acc_empty + a.slots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = a.N * a.strips * a.segs;
+  const int grp = blockIdx.y;                       // output-channel group
+  const int S = a.slots;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&row_full[s], 1);
+      mbar_init(&row_empty[s], 1);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kEpiWarps);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, w_bytes);
+      for (int kx = 0; kx < 3; ++kx)
+        for (int c = 0; c < a.nchunks; ++c)
+          for (int b = 0; b < 3; ++b)     // block b holds ky = 2 - b
+            tma_load_3d(w_smem + (size_t)(kx * a.nchunks + c) * wtile_bytes + (size_t)b * blk_bytes, &tmap_w, w_bar,
+                        c * KC, grp * a.NOUT, (2 - b) * 3 + kx);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int seg = item % a.segs;
+        const int t = item / a.segs;
+        const int strip = t % a.strips, n = t / a.strips;
+        const int y0 = seg * a.R, rows = min(a.R, a.H - y0), x0 = strip * BM;
+        for (int ri = 0; ri < rows + 2; ++ri) {
+          mbar_wait(&row_empty[stage], phase ^ 1);
+          if (a.dbg & 2) { mbar_arrive(&row_full[stage]); if (++stage == a.stages) { stage = 0; phase ^= 1; } continue; }
+          mbar_expect_tx(&row_full[stage], (uint32_t)a.nchunks * (PXB * ROWB));
+          uint8_t* dst = ring + (size_t)stage * stage_bytes;
+          for (int c = 0; c < a.nchunks; ++c)
+            tma_load_4d(dst + (size_t)c * CHUNK_BYTES, &tmap_x, &row_full[stage], c * KC, x0 - 1, y0 - 1 + ri, n);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // Everything below runs on ONE thread whose instruction latency is the issue-rate limit (a dependent
+    // scalar instruction costs ~5 cycles, an N=96 MMA only 48), so the per-MMA work is a table lookup
+    // (descriptor low words precomputed once per CTA) plus two adds.  Accumulators are zeroed by the
+    // epilogue warps, so every MMA accumulates and the tap grouping of a row never changes mid-row.
+    // All 32 lanes run the (warp-uniform) control flow; one elected lane issues the MMAs and commits, so
+    // ptxas keeps descriptors in uniform registers instead of emitting a per-MMA lane-election loop.
+    {
+      const uint32_t w_lo = (smem_u32(w_smem) & 0x3FFFFu) >> 4;
+      const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);     // | LBO field (unused) = 1
+      const uint32_t stage_lo = stage_bytes >> 4, blk_lo = blk_bytes >> 4, wtile_lo = wtile_bytes >> 4;
+      const uint64_t desc_hi = make_kmajor_desc(0, ROWB) & 0xFFFFFFFF00000000ull;
+      const uint32_t id1 = make_idesc_bf16((uint32_t)a.NOUT), id2 = make_idesc_bf16(2u * a.NOUT),
+                     id3 = make_idesc_bf16(3u * a.NOUT);
+      int stage = 0;
+      uint32_t phase = 0;
+      int jbase = 0;                      // output rows issued so far by this CTA (running index -> TMEM slot)
+      mbar_wait(w_bar, 0);
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int seg = item % a.segs;
+        const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
+        int s2 = jbase % S;               // slot of output row oi = ri (the row this input row starts)
+        uint32_t r2 = (uint32_t)(jbase / S);   // how many times that slot has been used before
+        for (int ri = 0; ri < rows + 2; ++ri) {
+          // input row ri feeds output rows oi = ri - ky (0 <= oi < rows); weight block b = 2 - ky <-> oi = ri - 2 + b
+          const int blo = max(0, 2 - ri), bhi = min(2, rows + 1 - ri);
+          const int s1 = s2 ? s2 - 1 : S - 1, s0 = s1 ? s1 - 1 : S - 1;
+          // group adjacent blocks whose accumulator slots are adjacent columns into one MMA (merged mode)
+          uint32_t gb0, gb1 = 0, gb2 = 0, gc0, gc1 = 0, gc2 = 0, gi0, gi1 = 0, gi2 = 0;
+          int ng;
+          {
+            const bool m01 = a.merged && blo == 0 && bhi >= 1 && s1 == s0 + 1;
+            const bool m12 = a.merged && blo <= 1 && bhi == 2 && s2 == s1 + 1;
+            auto sbf = [&](int b) { return b == 0 ? s0 : b == 1 ? s1 : s2; };
+            int b = blo;
+            int nb = 1;
+            if (b == 0 && m01) nb = m12 ? 3 : 2; else if (b == 1 && m12) nb = 2;
+            gb0 = (uint32_t)b * blk_lo; gc0 = (uint32_t)(sbf(b) * a.NOUT); gi0 = nb == 3 ? id3 : nb == 2 ? id2 : id1;
+            ng = 1;
+            b += nb;
+            if (b <= bhi) {
+              nb = (b == 1 && m12) ? 2 : 1;
+              gb1 = (uint32_t)b * blk_lo; gc1 = (uint32_t)(sbf(b) * a.NOUT); gi1 = nb == 2 ? id2 : id1;
+              ng = 2;
+              b += nb;
+              if (b <= bhi) { gb2 = (uint32_t)b * blk_lo; gc2 = (uint32_t)(sbf(b) * a.NOUT); gi2 = id1; ng = 3; }
+            }
+          }
+          if (bhi == 2) mbar_wait(&acc_empty[s2], r2 & 1u);     // slot of the new output row is drained + zeroed
+          mbar_wait(&row_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_lo;
+          if (elect_one()) {
+            if (!(a.dbg & 1)) {
+              for (int g = 0; g < ng; ++g) {
+                const uint32_t d = tmem_base + (g == 0 ? gc0 : g == 1 ? gc1 : gc2);
+                const uint32_t b_lo = w_lo + (g == 0 ? gb0 : g == 1 ? gb1 : gb2);
+                const uint32_t id = g == 0 ? gi0 : g == 1 ? gi1 : gi2;
+                for (int c = 0; c < a.nchunks; ++c) {
+                  const int ks = (c == a.nchunks - 1) ? a.ksteps_last : KC / 16;
+#pragma unroll
+                  for (int kx = 0; kx < 3; ++kx) {
+                    const uint32_t al = a_lo + (uint32_t)c * (CHUNK_BYTES >> 4) + (uint32_t)kx * (ROWB >> 4);
+                    const uint32_t bl = b_lo + (uint32_t)(kx * a.nchunks + c) * wtile_lo;
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)
+                      if (k < ks) umma_bf16_acc(d, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)((1u << 16) | (bl + 2u * k)), id);
+                  }
+                }
+              }
+            }
+            umma_commit(&row_empty[stage]);                       // input row consumed when these MMAs retire
+            if (ri >= 2) umma_commit(&acc_full[s0]);              // output row ri-2 (slot s0) is final
+          }
+          __syncwarp();
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          if (++s2 == S) { s2 = 0; ++r2; }
+        }
+        jbase += rows;
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..9) =================
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2;                      // which half of the 16-column chunks
+    const int row = q * 32 + lane;                         // pixel within the strip
+    const int c_lo = grp * a.NOUT;
+    const int nch = (min(a.Cout, c_lo + a.NOUT) - c_lo + 15) >> 4;
+    const int nch_all = a.NOUT >> 4;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // zero the whole accumulator ring once, then publish every slot as empty
+    for (int col = part * 16; col < S * a.NOUT; col += 32) tmem_st16_zero(lane_addr + (uint32_t)col);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int sl = 0; sl < S; ++sl) mbar_arrive(&acc_empty[sl]);
+    int slot = 0;
+    uint32_t par = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int seg = item % a.segs;
+      const int t = item / a.segs;
+      const int strip = t % a.strips, n = t / a.strips;
+      const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
+      const int x = strip * BM + row;
+      const bool valid = x < a.W;
+      int64_t p = ((int64_t)n * a.H + y0) * a.W + x;
+      for (int oi = 0; oi < rows; ++oi, p += a.W) {
+        mbar_wait(&acc_full[slot], par);
+        tc_fence_after();
+        const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT);
+        // column address such that (taddr + absolute channel) is the accumulator column of that channel
+        const uint32_t taddr = tcol - (uint32_t)c_lo;
+        for (int c = part; c < nch_all; c += 4) {
+          EpiChunk<OutT> e0, e1;
+          const bool two = c + 2 < nch_all;
+          const bool live0 = c < nch && !(a.dbg & 4), live1 = two && c + 2 < nch && !(a.dbg & 4);
+          if (live0) e0.issue(a, taddr, c_lo + c * 16, valid, p);
+          if (live1) e1.issue(a, taddr, c_lo + (c + 2) * 16, valid, p);
+          tmem_ld_wait();
+          tmem_st16_zero(tcol + (uint32_t)(c * 16));            // re-arm the slot for its next output row
+          if (two) tmem_st16_zero(tcol + (uint32_t)((c + 2) * 16));
+          if (live0) e0.finish(a, c_lo + c * 16, valid, p);
+          if (live1) e1.finish(a, c_lo + (c + 2) * 16, valid, p);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+        if (++slot == S) { slot = 0; par ^= 1u; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct RowPlan {
+  int NOUT, nsplit, nchunks, ksteps_last, stages, slots, merged, strips, R, segs;
+  size_t smem;
+};
+
+// Choose the per-CTA channel group, ring depths and the rows-per-item that minimises the longest CTA.
+bool plan_rows(const nervecl_conv_params& a, int sms, RowPlan& p) {
+  p.nchunks = (a.Cin + KC - 1) / KC;
+  p.ksteps_last = (a.Cin - (p.nchunks - 1) * KC + 15) / 16;
+  const int cout16 = (a.Cout + 15) / 16 * 16;
+  const size_t stage_bytes = (size_t)p.nchunks * CHUNK_BYTES;
+  p.nsplit = 0;
+  for (int ns = 1; ns <= 16; ++ns) {
+    const int nout = ((cout16 + ns - 1) / ns + 15) / 16 * 16;
+    if (nout > 128) continue;
+    const size_t w_bytes = (size_t)9 * p.nchunks * nout * ROWB;
+    const size_t fixed = 1024 + w_bytes + (2 * 8 + 2 * kMaxSlots + 2) * sizeof(uint64_t) + 64;
+    if (fixed + 2 * stage_bytes > kSmemBudget) continue;
+    p.nsplit = ns;
+    p.NOUT = nout;
+    p.stages = (int)imin(8, (int64_t)((kSmemBudget - fixed) / stage_bytes));
+    p.smem = fixed + (size_t)p.stages * stage_bytes;
+    break;
+  }
+  if (!p.nsplit) return false;
+  p.slots = (int)imin(kMaxSlots, 512 / p.NOUT);
+  p.merged = 3 * p.NOUT <= 256;
+  p.strips = (a.W + BM - 1) / BM;
+  const int ctas = (int)imax(1, sms / p.nsplit);
+  int64_t best = -1;
+  p.R = a.H;
+  for (int R = (int)imin(a.H, 6); R <= a.H && R <= 96; ++R) {
+    const int segs = (a.H + R - 1) / R;
+    const int64_t items = (int64_t)a.N * p.strips * segs;
+    const int64_t cost = ((items + ctas - 1) / ctas) * (R + 3);
+    if (best < 0 || cost <= best) { best = cost; p.R = R; }
+  }
+  p.segs = (a.H + p.R - 1) / p.R;
+  if (p.smem < 120 * 1024) p.smem = 120 * 1024;     // one CTA per SM: each allocates all 512 TMEM columns
+  return true;
+}
+
+}  // namespace
+
+namespace nv {
+
+bool conv_rows_supported(const nervecl_conv_params& a) {
+  if (!conv_tc_fwd_supported(a)) return false;       // dtype / alignment / epilogue constraints are the same
+  if (a.K != 3) return false;
+  if (a.Cin < 32 || a.Cin % 16 || a.Cin > 512) return false;
+  if (a.W < 64 || a.H < 3) return false;
+  RowPlan p;
+  return plan_rows(a, sm_count(), p);
+}
+
+int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return NERVECL_EUNSUPPORTED;
+  const int sms = sm_count();
+  RowPlan p;
+  if (!plan_rows(a, sms, p)) return NERVECL_EUNSUPPORTED;
+
+  CUtensorMap tx, tw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ldx * 2, (cuuint64_t)a.W * a.ldx * 2, (cuuint64_t)a.H * a.W * a.ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)PXB, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERVECL_EUNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.w_ld, (cuuint64_t)a.w_rows, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)a.w_ld * 2, (cuuint64_t)a.w_rows * a.w_ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.NOUT, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a.w), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERVECL_EUNSUPPORTED;
+  }
+
+  RowArgs t;
+  t.Cout = a.Cout; t.relu = a.relu; t.accumulate = a.accumulate; t.res_channels = a.res ? a.res_channels : 0;
+  t.mask_c0 = a.mask_c0; t.alpha = a.alpha; t.bias = a.bias;
+  t.res = (const bf16*)a.res; t.ldres = a.ldres;
+  t.mask = (const bf16*)a.mask; t.ldmask = a.ldmask;
+  t.msub = (const bf16*)a.mask_sub; t.ldmsub = a.ldmask_sub;
+  t.out = a.out; t.ldo = a.ldo;
+  t.N = a.N; t.H = a.H; t.W = a.W;
+  t.NOUT = p.NOUT; t.nchunks = p.nchunks; t.ksteps_last = p.ksteps_last;
+  t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
+  { const char* d = getenv("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
+
+  const int64_t items = (int64_t)a.N * p.strips * p.segs;
+  dim3 grid((unsigned)imin(items, imax(1, sms / p.nsplit)), (unsigned)p.nsplit);
+  cudaError_t e;
+  if (a.out_dtype == NERVECL_F32) {
+    e = cudaFuncSetAttribute(conv_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return (int)e;
+    conv_rows_kernel<float><<<grid, kThreads, p.smem, s>>>(tx, tw, t);
+  } else {
+    e = cudaFuncSetAttribute(conv_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return (int)e;
+    conv_rows_kernel<bf16><<<grid, kThreads, p.smem, s>>>(tx, tw, t);
+  }
+  return launch_status();
+}
+
+}  // namespace nv

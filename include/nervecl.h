@@ -46,7 +46,9 @@ enum {
 enum {
   NERVECL_CONV_AUTO = 0, /* tcgen05 when the shape qualifies, else SIMT */
   NERVECL_CONV_SIMT = 1, /* fp32-accumulate CUDA-core direct conv (any shape, f32 or bf16) */
-  NERVECL_CONV_TC = 2    /* tcgen05/TMEM/TMA implicit GEMM (bf16, Cin%8==0, Cout in {16..256 step 16}) */
+  NERVECL_CONV_TC = 2,   /* tcgen05/TMEM/TMA implicit GEMM (bf16, Cin%8==0, Cout <= 256): the row-streaming
+                            kernel for 3x3 / Cin%16==0 / W>=64, else the per-tap kernel */
+  NERVECL_CONV_TC_TAPS = 3 /* force the per-tap tcgen05 kernel */
 };
 
 int nervecl_abi_version(void);

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the dense-conv kernels at the cfg-2 shapes (B=16, 360x640): CUDA-event time and
+algorithmic TFLOP/s per layer shape, row-streaming/auto tcgen05 engine vs the per-tap kernel."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "continual-learning-for-dynamic-video-quality-enhancement_b200"))
+from nerve_cl_b200 import ops  # noqa: E402
+
+nv = ops.nv
+B, H, W = int(os.environ.get("B", 16)), 360, 640
+dev = "cuda"
+
+
+def bench(fn, iters=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def fwd_case(cin, cout, k, ld_in, ld_out, engines, accumulate=False, mask=False):
+    x = torch.randn((B, H, W, ld_in), device=dev, dtype=torch.bfloat16)
+    out = torch.zeros((B, H, W, ld_out), device=dev, dtype=torch.bfloat16)
+    w = torch.randn((k * k, cout, (cin + 7) // 8 * 8), device=dev, dtype=torch.bfloat16) * 0.05
+    bias = torch.randn(cout, device=dev)
+    m = torch.randn((B, H, W, ld_out), device=dev, dtype=torch.bfloat16) if mask else None
+    flops = 2.0 * B * H * W * cin * cout * k * k
+    res = []
+    for eng in engines:
+        try:
+            ms = bench(lambda: nv.conv2d_fwd(x[..., :cin], w, None if accumulate else bias, None,
+                                             m[..., :cout] if mask else None, None, out[..., :cout], cout,
+                                             not accumulate, accumulate, 0, 0, 1.0, eng))
+            res.append(f"{ms:7.3f} ms {flops / ms / 1e9:7.1f} TF")
+        except RuntimeError as e:
+            res.append(f"unsupported ({str(e)[-30:]})")
+    print(f"fwd {cin:3d}->{cout:3d} k{k} acc={int(accumulate)}: " + " | ".join(res), flush=True)
+
+
+def wgrad_case(cin, cout, k, ld_in, ld_dy):
+    x = torch.randn((B, H, W, ld_in), device=dev, dtype=torch.bfloat16)
+    dy = torch.randn((B, H, W, ld_dy), device=dev, dtype=torch.bfloat16)
+    dw = torch.zeros((cout, cin, k, k), device=dev)
+    db = torch.zeros(cout, device=dev)
+    flops = 2.0 * B * H * W * cin * cout * k * k
+    ms = bench(lambda: nv.conv2d_wgrad(x[..., :cin], dy[..., :cout], dw, db, 1.0, ops.CONV_TC))
+    print(f"wgrad {cin:3d}->{cout:3d} k{k}: {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+    engines = [ops.CONV_TC, ops.CONV_TC_TAPS]
+    if which in ("fwd", "all"):
+        print("engines: rows/auto | per-tap")
+        for cin in (64, 96, 128, 160, 192):
+            fwd_case(cin, 32, 3, 224, 224, engines)
+        fwd_case(96, 128, 3, 96, 128, engines)
+        fwd_case(128, 64, 3, 128, 64, engines)
+        fwd_case(192, 64, 3, 192, 64, engines)
+        fwd_case(64, 64, 3, 64, 64, engines)
+        fwd_case(224, 64, 1, 224, 64, engines)
+    if which == "rows":
+        fwd_case(64, 32, 3, 224, 224, [ops.CONV_TC])
+        fwd_case(64, 32, 3, 256, 256, [ops.CONV_TC])
+        fwd_case(192, 32, 3, 224, 224, [ops.CONV_TC])
+        fwd_case(192, 32, 3, 256, 256, [ops.CONV_TC])
+    if which in ("dgrad", "all"):
+        for cout in (64, 96, 128, 160, 192):
+            fwd_case(32, cout, 3, 224, 224, engines, accumulate=True, mask=True)
+        fwd_case(64, 224, 1, 64, 224, engines)
+    if which in ("wgrad", "all"):
+        for cin in (64, 96, 128, 160, 192):
+            wgrad_case(cin, 32, 3, 224, 224)
+        wgrad_case(224, 64, 1, 224, 64)
