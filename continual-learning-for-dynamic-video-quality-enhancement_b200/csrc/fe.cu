@@ -4,6 +4,19 @@
 
 using namespace nv;
 
+namespace nv {   // fe_fast.cu
+bool fe_fast_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b);
+int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int dtype, int N, int H, int W, int C,
+                 int flip, int accumulate, cudaStream_t s);
+int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy, int dtype, float* dw, int N, int H, int W,
+                       int C, cudaStream_t s);
+int bn_relu_fwd_fast(const void* x, int64_t ldx, const float* stat, const float* gamma, const float* beta, const void* res,
+                     int64_t ldres, void* y, int64_t ldy, int dtype, int C, int64_t npix, int groups, cudaStream_t s);
+int bn_bwd_apply_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
+                      const float* beta, const double* bsums, void* dx, int64_t lddx, float* dgamma, float* dbeta, int dtype,
+                      int C, int64_t npix, int groups, int training, cudaStream_t s);
+}
+
 namespace {
 
 // ---------------------------------------------------------------------------------------
@@ -328,6 +341,9 @@ NV_API int nervecl_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, voi
                                  int N, int H, int W, int C, int flip, int accumulate, nervecl_stream_t stream) {
   if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if ((C & 7) || (ldx & 7) || (ldy & 7) || !aligned(x, 16) || !aligned(y, 16)) return NERVECL_EALIGN;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (fe_fast_supported(C, ldx, ldy, x, y))
+    return dwconv_slide(x, ldx, w, y, ldy, dtype, N, H, W, C, flip, accumulate, as_stream(stream));
   int64_t total = (int64_t)N * H * W * (C >> 3);
   NV_DISPATCH_DTYPE(dtype, E, (dwconv_kernel<E><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
                                   (const E*)x, ldx, w, (E*)y, ldy, N, H, W, C, flip, accumulate)));
@@ -338,6 +354,9 @@ NV_API int nervecl_dwconv3x3_wgrad(const void* x, int64_t ldx, const void* dy, i
                                    float* dw, int N, int H, int W, int C, nervecl_stream_t stream) {
   if (!x || !dy || !dw || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (ldy & 3) || C > 1024) return NERVECL_EALIGN;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (fe_fast_supported(C, ldx, ldy, x, dy))
+    return dwconv_wgrad_slide(x, ldx, dy, ldy, dtype, dw, N, H, W, C, as_stream(stream));
   int64_t npix = (int64_t)N * H * W;
   int lanes = 256 / (C >> 2);
   if (lanes < 1) return NERVECL_EUNSUPPORTED;
@@ -376,6 +395,9 @@ NV_API int nervecl_bn_relu_fwd(const void* x, int64_t ldx, const float* stat, co
                                int dtype, int C, int64_t npix, int groups, nervecl_stream_t stream) {
   if (!x || !stat || !gamma || !beta || !y || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (ldy & 3) || (res && (ldres & 3))) return NERVECL_EALIGN;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (fe_fast_supported(C, ldx, ldy, x, y) && (!res || (!(ldres & 7) && aligned(res, 16))))
+    return bn_relu_fwd_fast(x, ldx, stat, gamma, beta, res, ldres, y, ldy, dtype, C, npix, groups, as_stream(stream));
   dim3 grid(ew_blocks(npix * (C >> 2)), groups);
   NV_DISPATCH_DTYPE(dtype, E, (bn_relu_fwd_kernel<E><<<grid, 256, 0, as_stream(stream)>>>(
                                   (const E*)x, ldx, stat, gamma, beta, (const E*)res, ldres, (E*)y, ldy, C, npix)));
@@ -403,6 +425,10 @@ NV_API int nervecl_bn_relu_bwd_apply(const void* x, int64_t ldx, const void* dy,
   if (!x || !dy || !stat || !gamma || !beta || !bsums || !dx || C <= 0 || npix <= 0 || groups <= 0)
     return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (lddy & 3) || (lddx & 3)) return NERVECL_EALIGN;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (fe_fast_supported(C, ldx, lddy, x, dy) && !(lddx & 7) && aligned(dx, 16))
+    return bn_bwd_apply_fast(x, ldx, dy, lddy, stat, gamma, beta, bsums, dx, lddx, dgamma, dbeta, dtype, C, npix, groups,
+                             training, as_stream(stream));
   dim3 grid(ew_blocks(npix * (C >> 2)), groups);
   NV_DISPATCH_DTYPE(dtype, E, (bn_bwd_apply_kernel<E><<<grid, 256, 0, as_stream(stream)>>>(
                                   (const E*)x, ldx, (const E*)dy, lddy, stat, gamma, beta, bsums, (E*)dx, lddx,

@@ -157,7 +157,10 @@ class Activations:
         self.gate = torch.empty((B, F), device=dev, dtype=f32)
         self.stats = act(B, 2, f32)
         self.sgate = torch.empty((B, H, W), device=dev, dtype=f32)
-        self.rdb = [act(B, F + RDB_LAYERS * GROWTH) for _ in range(p.NB)]
+        # dense-block buffers: F + 5*32 channels at a pixel pitch rounded up to 64 channels (128 B), so that
+        # every 64-channel TMA box row of the conv kernels is one aligned 128-byte line
+        ct = F + RDB_LAYERS * GROWTH
+        self.rdb = [act(B, _align(ct, 64))[..., :ct] for _ in range(p.NB)]
         self.trunk = act(B, F)
         self.fused = act(B, F)
         self.up = act(B, 3 * s * s, f32)
@@ -351,7 +354,8 @@ class Plan:
             ws["dfused"] = act(B, F)
             ws["dgff"] = act(B, F)
             ws["dtrunk"] = act(B, F)
-            ws["g"] = [act(B, F + RDB_LAYERS * GROWTH) for _ in range(2)]
+            ct = F + RDB_LAYERS * GROWTH
+            ws["g"] = [act(B, _align(ct, 64))[..., :ct] for _ in range(2)]
             ws["dz"] = torch.empty((B, H, W), device=dev, dtype=f32)
             ws["dstats"] = act(B, 2, f32)
             ws["dblend"] = act(B, F)

@@ -179,6 +179,31 @@ def test_correlation_golden_and_grad():
     assert relerr(nchw(d1), a.grad) <= TOL and relerr(nchw(d2), b.grad) <= TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 150), (1, 9, 64), (1, 50, 70)])
+def test_correlation_tiled_bf16(shape):
+    """bf16 / C=64 shared-memory kernels (forward, both gradients, accumulate flags, ragged strips and row
+    segments) against the oracle on bf16-rounded inputs."""
+    from oracle import sr_oracle
+    n, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x1 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    x2 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    a, b = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    ref = sr_oracle.correlation(a, b)
+    out = torch.full((n, h, w, 104), 7.0, device="cuda", dtype=torch.bfloat16)
+    nv().corr_fwd(nhwc(x1, torch.bfloat16, pad_to=72), nhwc(x2, torch.bfloat16), out[..., :96])
+    assert relerr(nchw(out[..., :81]), ref) <= 6e-3
+    assert float(out[..., 81:96].float().abs().max()) == 0.0 and float((out[..., 96:].float() - 7).abs().max()) == 0.0
+    dy = torch.randn(n, 81, h, w, generator=g).bfloat16().float()
+    ref.backward(dy)
+    p1 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    d1 = nhwc(p1, torch.bfloat16, pad_to=72)
+    d2 = torch.empty((n, h, w, 64), device="cuda", dtype=torch.bfloat16)
+    nv().corr_bwd(nhwc(x1, torch.bfloat16), nhwc(x2, torch.bfloat16), nhwc(dy, torch.bfloat16, pad_to=96), d1, True,
+                  d2, False)
+    assert relerr(nchw(d1), a.grad + p1) <= 8e-3 and relerr(nchw(d2), b.grad) <= 8e-3
+
+
 def test_warp_indices_bit_exact_vs_cpu_golden():
     """div_mode=1 replays ATen-CPU's division: indices must equal the golden (CPU reference) ones exactly."""
     from nerve_cl_b200.models import warp_indices, warp_features
