@@ -46,7 +46,15 @@ NV_API int nervecl_conv2d_wgrad(const void* x, int64_t ldx, const void* dy, int6
   cudaStream_t s = as_stream(stream);
   bool tc_ok = conv_tc_wgrad_supported(x, ldx, dy, ldy, dtype, N, H, W, Cin, Cout, K);
   if (engine == NERVECL_CONV_AUTO) engine = tc_ok ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
-  if (engine == NERVECL_CONV_TC) {
+  if (engine == NERVECL_CONV_TC && K == 3 && Cin >= 32 && Cout % 4 == 0 &&
+      wgrad_rows_supported(x, ldx, dy, ldy, dtype, N, H, W, Cin, Cout)) {
+    const int32_t col0 = 0, ncols = Cout, cin = Cin;
+    float* dwp = dw;
+    float* dbp = db;
+    return nervecl_conv3x3_wgrad_grouped(x, ldx, dy, ldy, dtype, N, H, W, Cin, Cout, 1, &col0, &ncols, &cin, &dwp,
+                                         db ? &dbp : nullptr, scale, stream);
+  }
+  if (engine == NERVECL_CONV_TC || engine == NERVECL_CONV_TC_TAPS) {
     if (!tc_ok) return NERVECL_EUNSUPPORTED;
     return conv_tc_wgrad(x, ldx, dy, ldy, dw, db, N, H, W, Cin, Cout, K, scale, s);
   }

@@ -19,4 +19,11 @@ bool conv_tc_wgrad_supported(const void* x, int64_t ldx, const void* dy, int64_t
 int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float* dw, float* db, int N, int H,
                   int W, int Cin, int Cout, int K, float scale, cudaStream_t s);
 
+// grouped row-resident 3x3 weight gradient (conv_tc_wgrad_rows.cu)
+bool wgrad_rows_supported(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H, int W, int Cx,
+                          int Cy);
+int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, int H, int W, int Cx, int Cy, int ngroups,
+               const int32_t* col0, const int32_t* ncols, const int32_t* cin, float* const* dw, float scale,
+               cudaStream_t s);
+
 }  // namespace nv

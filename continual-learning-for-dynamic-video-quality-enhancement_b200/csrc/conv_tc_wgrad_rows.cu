@@ -1,0 +1,311 @@
+// Grouped, row-resident tcgen05 weight gradient for 3x3 convolutions that share one input buffer.
+//
+//   dW_g[o, c, ky, kx] += scale * sum_p dY[p, col0_g + o] * X[p + (ky-1, kx-1), c]      c < cin_g
+//
+// The five 3x3 layers of a residual dense block all read prefixes of ONE 224-channel buffer and their
+// output gradients are adjacent channel slices of ONE gradient buffer, so their weight gradients are one
+// GEMM  D[c, (g,o)] = X^T dY  per tap with M = channels, N = 160 (all layers), K = pixels -- instead of five
+// N = 32 GEMMs whose SS-mode MMAs are shared-memory bound at 40 % of the tensor rate.  (Entries with
+// c >= cin_g are computed and dropped: 57 % of the dense product is used, at ~2.5x the MMA efficiency.)
+//
+// A CTA owns one (128-channel M tile, ky) class: its three taps kx = 0,1,2 accumulate in 3*N TMEM columns
+// for the CTA's whole lifetime.  Per 128-pixel row tile TMA brings the halo'd X row y+ky-1 {64 ch x 130 px}
+// per 64-channel chunk and the dY row {64 ch x 128 px} per chunk into shared memory once; both land as the
+// canonical MN-major 128B-swizzled UMMA layout (K = pixel rows), and the three kx taps are three A
+// descriptors offset by one pixel row (absolute-address swizzle, as in conv_tc_rows.cu).  M tiles that only
+// matter to the later layers (channels >= 128 feed only layers with cin > 128) use the matching suffix of
+// the dY columns.  At the end the accumulators are drained with fp32 atomics into the OIHW gradients.
+#include "conv_internal.cuh"
+#include "tc_common.cuh"
+
+using namespace nv;
+using namespace nv::tc;
+
+extern "C" int nervecl_chan_sum(const void* x, int64_t ldx, int dtype, int N, int64_t pix_per_image, int C,
+                                float scale, float* out, nervecl_stream_t stream);
+
+namespace {
+
+constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 drain
+constexpr int KC = 64;
+constexpr uint32_t ROWB = 128;
+constexpr int PXB = BM + 2;
+constexpr uint32_t XCHUNK = (PXB * ROWB + 1023u) & ~1023u;    // 17408: one 64-channel chunk of a halo'd X row
+constexpr uint32_t YCHUNK = BM * ROWB;                          // 16384: one 64-channel chunk of a dY row
+constexpr int kMaxGroups = 8;
+constexpr int kMaxClasses = 12;
+
+struct WgGroup { int col0, ncols, cin; float* dw; };
+
+struct WgrArgs {
+  int N, H, W, strips;
+  int ngroups;
+  WgGroup grp[kMaxGroups];
+  int nclasses;
+  // per class: M tile, ky, first dY column, UMMA N, dY chunks, first CTA of the class, CTAs in the class
+  int c_mt[kMaxClasses], c_ky[kMaxClasses], c_col0[kMaxClasses], c_n16[kMaxClasses], c_nby[kMaxClasses],
+      c_cta0[kMaxClasses], c_ctas[kMaxClasses];
+  int stages;
+  float scale;
+};
+
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((8u * ROWB) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_mn(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgrArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // which class does this CTA belong to?
+  int cls = 0;
+  for (int c = 1; c < a.nclasses; ++c)
+    if ((int)blockIdx.x >= a.c_cta0[c]) cls = c;
+  const int mt = a.c_mt[cls], ky = a.c_ky[cls], col0 = a.c_col0[cls], n16 = a.c_n16[cls], nby = a.c_nby[cls];
+  const int idx = blockIdx.x - a.c_cta0[cls], nctas = a.c_ctas[cls];
+  const uint32_t stage_bytes = 2u * XCHUNK + 3u * YCHUNK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + a.stages;
+  uint64_t* done_bar = empty_bar + a.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_tiles = (int64_t)a.N * a.H * a.strips;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_dy);
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = 2u * (PXB * ROWB) + (uint32_t)nby * YCHUNK;
+      for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
+        const int strip = (int)(rt % a.strips);
+        const int64_t r = rt / a.strips;
+        const int y = (int)(r % a.H), n = (int)(r / a.H);
+        const int x0 = strip * BM;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], bytes);
+        uint8_t* sx = smem + (size_t)stage * stage_bytes;
+        uint8_t* sy = sx + 2 * XCHUNK;
+        for (int c = 0; c < 2; ++c)
+          tma_load_4d(sx + (size_t)c * XCHUNK, &tmap_x, &full_bar[stage], mt * 128 + c * KC, x0 - 1, y + ky - 1, n);
+        for (int c = 0; c < nby; ++c)
+          tma_load_4d(sy + (size_t)c * YCHUNK, &tmap_dy, &full_bar[stage], col0 + c * KC, x0, y, n);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_mn((uint32_t)n16);
+    const uint64_t hi = mn_desc(0, 0) & 0xFFFFFFFF00000000ull;
+    const uint32_t lbo_a = ((XCHUNK >> 4) & 0x3FFF) << 16, lbo_b = ((YCHUNK >> 4) & 0x3FFF) << 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t started = 0;
+    for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sx = (smem_u32(smem + (size_t)stage * stage_bytes) & 0x3FFFFu) >> 4;
+      const uint32_t sy = sx + ((2u * XCHUNK) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t d = tmem_base + (uint32_t)(kx * n16);
+#pragma unroll
+          for (int ks = 0; ks < BM / 16; ++ks) {
+            // K step = 16 pixel rows of 128 B; tap kx starts kx pixel rows into the halo'd X row
+            const uint64_t da = hi | (uint64_t)(lbo_a | (sx + (uint32_t)((kx + 16 * ks) * 8)));
+            const uint64_t db = hi | (uint64_t)(lbo_b | (sy + (uint32_t)(16 * ks * 8)));
+            umma_bf16(d, da, db, idesc, started | (uint32_t)ks);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      started = 1;
+      if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // drain: TMEM -> fp32 atomics into the OIHW gradients
+    const int q = warp & 3;
+    const int c = mt * 128 + q * 32 + lane;                  // input channel of this lane
+    const bool any = idx < row_tiles;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (any) {
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tap = ky * 3 + kx;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kx * n16);
+        for (int c0 = 0; c0 < n16; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = col0 + c0 + j;
+            for (int g = 0; g < a.ngroups; ++g) {
+              const int o = col - a.grp[g].col0;
+              if (o >= 0 && o < a.grp[g].ncols) {
+                if (c < a.grp[g].cin)
+                  atomicAdd(a.grp[g].dw + ((int64_t)o * a.grp[g].cin + c) * 9 + tap, a.scale * __uint_as_float(v[j]));
+                break;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+namespace nv {
+
+bool wgrad_rows_supported(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H, int W, int Cx,
+                          int Cy) {
+  if (dtype != NERVECL_BF16) return false;
+  if (Cx < 16 || Cy < 8 || Cy > 160) return false;
+  if (ldx % 8 || ldy % 8 || !aligned(x, 16) || !aligned(dy, 16)) return false;
+  if (W < 64 || (int64_t)N * H * W < 1024) return false;
+  if ((Cx + 127) / 128 * 3 > kMaxClasses) return false;
+  return encode_fn() != nullptr;
+}
+
+// groups must be sorted by ascending cin (so that the columns an M tile needs are a suffix)
+int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, int H, int W, int Cx, int Cy, int ngroups,
+               const int32_t* col0, const int32_t* ncols, const int32_t* cin, float* const* dw, float scale,
+               cudaStream_t s) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return NERVECL_EUNSUPPORTED;
+  if (ngroups < 1 || ngroups > kMaxGroups) return NERVECL_EINVAL;
+  WgrArgs a;
+  a.N = N; a.H = H; a.W = W; a.strips = (W + BM - 1) / BM;
+  a.ngroups = ngroups;
+  a.scale = scale;
+  for (int g = 0; g < ngroups; ++g) {
+    if (g && cin[g] < cin[g - 1]) return NERVECL_EINVAL;
+    if (col0[g] < 0 || col0[g] + ncols[g] > Cy || cin[g] > Cx || !dw[g]) return NERVECL_EINVAL;
+    a.grp[g] = WgGroup{col0[g], ncols[g], cin[g], dw[g]};
+  }
+  const int sms = sm_count();
+  const int MT = (Cx + 127) / 128;
+  // classes and their relative cost (MMA cycles per row tile vs bytes staged per row tile)
+  double cost[kMaxClasses];
+  double total_cost = 0;
+  a.nclasses = 0;
+  for (int mt = 0; mt < MT; ++mt) {
+    // columns needed by this M tile: groups with cin > mt*128
+    int lo = Cy, hi = 0;
+    for (int g = 0; g < ngroups; ++g)
+      if (cin[g] > mt * 128) { lo = lo < col0[g] ? lo : col0[g]; hi = hi > col0[g] + ncols[g] ? hi : col0[g] + ncols[g]; }
+    if (hi <= lo) continue;
+    lo = lo / 8 * 8;                                           // 16-byte aligned TMA start
+    const int n16 = (hi - lo + 15) / 16 * 16;
+    if (3 * n16 > 512) return NERVECL_EUNSUPPORTED;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int c = a.nclasses++;
+      a.c_mt[c] = mt; a.c_ky[c] = ky; a.c_col0[c] = lo; a.c_n16[c] = n16; a.c_nby[c] = (n16 + KC - 1) / KC;
+      const double mma = 24.0 * n16 / 2.0;
+      const double ld = (2.0 * PXB * ROWB + a.c_nby[c] * YCHUNK) / 48.0;
+      cost[c] = mma > ld ? mma : ld;
+      total_cost += cost[c];
+    }
+  }
+  if (a.nclasses == 0) return NERVECL_OK;
+  int used = 0;
+  for (int c = 0; c < a.nclasses; ++c) {
+    int n = (int)(sms * cost[c] / total_cost);
+    if (n < 1) n = 1;
+    a.c_ctas[c] = n;
+    used += n;
+  }
+  for (int c = 0; used < sms; c = (c + 1) % a.nclasses) { ++a.c_ctas[c]; ++used; }   // hand out the remainder
+  int acc = 0;
+  for (int c = 0; c < a.nclasses; ++c) { a.c_cta0[c] = acc; acc += a.c_ctas[c]; }
+  const int grid = acc;
+
+  CUtensorMap tx, td;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)PXB, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERVECL_EUNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cy, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)W * ldy * 2, (cuuint64_t)H * W * ldy * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)BM, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NERVECL_EUNSUPPORTED;
+  }
+  a.stages = 2;
+  const size_t smem = 1024 + (size_t)a.stages * (2 * XCHUNK + 3 * YCHUNK) + (2 * a.stages + 1) * sizeof(uint64_t) + 16;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  wgrad_rows_kernel<<<grid, kThreads, smem, s>>>(tx, td, a);
+  return launch_status();
+}
+
+}  // namespace nv
+
+NV_API int nervecl_conv3x3_wgrad_grouped(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H,
+                                         int W, int Cx, int Cy, int ngroups, const int32_t* col0_host,
+                                         const int32_t* ncols_host, const int32_t* cin_host, float* const* dw_host,
+                                         float* const* db_host, float scale, nervecl_stream_t stream) {
+  if (!x || !dy || !col0_host || !ncols_host || !cin_host || !dw_host) return NERVECL_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || Cx <= 0 || Cy <= 0 || ldx < Cx || ldy < Cy) return NERVECL_EINVAL;
+  if (!wgrad_rows_supported(x, ldx, dy, ldy, dtype, N, H, W, Cx, Cy)) return NERVECL_EUNSUPPORTED;
+  cudaStream_t s = as_stream(stream);
+  int rc = wgrad_rows(x, ldx, dy, ldy, N, H, W, Cx, Cy, ngroups, col0_host, ncols_host, cin_host, dw_host, scale, s);
+  if (rc) return rc;
+  if (db_host) {
+    for (int g = 0; g < ngroups; ++g) {
+      if (!db_host[g]) continue;
+      if (ncols_host[g] % 4 || col0_host[g] % 4) return NERVECL_EALIGN;
+      rc = nervecl_chan_sum(reinterpret_cast<const bf16*>(dy) + col0_host[g], ldy, NERVECL_BF16, 1, (int64_t)N * H * W,
+                            ncols_host[g], scale, db_host[g], stream);
+      if (rc) return rc;
+    }
+  }
+  return NERVECL_OK;
+}

@@ -48,6 +48,9 @@ _SIGNATURES = {
     "nervecl_conv2d_fwd": [C.POINTER(ConvParams), c_vp],
     "nervecl_conv2d_wgrad": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                              c_i32, c_f32, c_i32, c_vp],
+    "nervecl_conv3x3_wgrad_grouped": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                      C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_vp),
+                                      C.POINTER(c_vp), c_f32, c_vp],
     "nervecl_dwconv3x3_fwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_dwconv3x3_wgrad": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_bn_stats": [c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp],

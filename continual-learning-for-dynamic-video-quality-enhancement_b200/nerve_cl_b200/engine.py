@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from ._lib import CONV_AUTO
+from ._lib import CONV_AUTO, CONV_SIMT
 
 Tensor = torch.Tensor
 
@@ -35,7 +35,7 @@ Tensor = torch.Tensor
 class _OpsProxy:
     """``torch.ops.nervecl`` with optional per-op CUDA-event timing (set ``.timer`` to a KernelTimer)."""
 
-    _SPANNED_ELSEWHERE = {"conv2d_fwd", "conv2d_wgrad"}      # timed with FLOP counts by Plan._span
+    _SPANNED_ELSEWHERE = {"conv2d_fwd", "conv2d_wgrad", "conv3x3_wgrad_grouped"}      # timed with FLOP counts by Plan._span
 
     def __init__(self):
         self.timer = None
@@ -242,6 +242,12 @@ class Plan:
         return self.timer.span(f"{kind}|{cin}>{cout}k{k}", 2.0 * npix * cin * cout * k * k,
                                float(npix) * (cin + cout) * x.element_size())
 
+    def _span_flops(self, kind: str, x: Tensor, flops_per_px: float):
+        if self.timer is None:
+            return _NOSPAN
+        npix = x.shape[0] * x.shape[1] * x.shape[2]
+        return self.timer.span(kind, flops_per_px * npix, 0.0)
+
     def conv(self, name: str, x: Tensor, out: Tensor, P, *, relu=False, res=None, res_channels=0, alpha=1.0,
              bias=True) -> None:
         c = self.convs[name]
@@ -415,15 +421,26 @@ class Plan:
             # slice 4 (channels >= F+4G) has no other consumer, so its ReLU mask is applied here.
             self.dgrad(name, dblock, g, cout=CT, alpha=0.2, res=dblock, res_channels=F, mask=buf,
                        mask_c0=F + (RDB_LAYERS - 1) * GROWTH)
+            grouped = self.adt == torch.bfloat16 and self.engine != CONV_SIMT and W >= 64
             for i in reversed(range(RDB_LAYERS)):
                 c0 = F + i * GROWTH
                 name = f"residual_blocks.{k}.layers.{i}.0"
                 dy = g[..., c0:c0 + GROWTH]
-                self.wgrad(name, buf[..., :c0], dy, G)
+                if not grouped:
+                    self.wgrad(name, buf[..., :c0], dy, G)
                 if i >= 1:
                     self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True, mask=buf, mask_c0=c0 - GROWTH)
                 else:
                     self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True)
+            if grouped:
+                # all five layers' weight/bias gradients in one GEMM: X = the block buffer, dY = g[:, F:]
+                names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
+                cx = F + (RDB_LAYERS - 1) * GROWTH
+                with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
+                                                                        for i in range(RDB_LAYERS))):
+                    nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names],
+                                             [G[n + ".bias"] for n in names],
+                                             [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
             ready(f"residual_blocks.{k}.")
             dblock = g[..., :F]
         dagg = dblock

@@ -192,6 +192,32 @@ def _conv2d_wgrad(x, dy, dw, db, scale, engine) -> None:
                                                scale, engine, _stream()), "conv2d_wgrad")
 
 
+@_op("conv3x3_wgrad_grouped(Tensor x, Tensor dy, Tensor(a!)[] dw, Tensor(b!)[] db, int[] col0, float scale) -> ()")
+def _conv3x3_wgrad_grouped(x, dy, dw, db, col0, scale) -> None:
+    """Weight/bias gradients of several 3x3 convs reading channel prefixes of ``x`` whose output gradients are
+    the slices ``dy[..., col0[g] : col0[g] + dw[g].shape[0]]`` (see ``nervecl_conv3x3_wgrad_grouped``).
+    ``dw[g]`` is OIHW fp32 (its shape gives ncols and cin); ``db`` is empty or one fp32 vector per group."""
+    xp, ldx, n, h, w, cx = _nhwc(x, "x")
+    yp, ldy, yn, yh, yw, cy = _nhwc(dy, "dy")
+    if (yn, yh, yw) != (n, h, w) or x.dtype != dy.dtype:
+        raise RuntimeError("nervecl.conv3x3_wgrad_grouped: x / dy mismatch")
+    ng = len(dw)
+    if len(col0) != ng or (len(db) not in (0, ng)):
+        raise RuntimeError("nervecl.conv3x3_wgrad_grouped: list lengths differ")
+    for t in dw:
+        if t.dim() != 4 or t.shape[2:] != (3, 3):
+            raise RuntimeError("nervecl.conv3x3_wgrad_grouped: dw must be OIHW with 3x3 taps")
+    i32 = C.c_int32 * ng
+    vps = C.c_void_p * ng
+    c0 = i32(*[int(v) for v in col0])
+    nc = i32(*[int(t.shape[0]) for t in dw])
+    ci = i32(*[int(t.shape[1]) for t in dw])
+    dwp = vps(*[_flat(t, "dw") for t in dw])
+    dbp = vps(*[_flat(t, "db") for t in db]) if len(db) else None
+    _lib.check(_lib.load().nervecl_conv3x3_wgrad_grouped(xp, ldx, yp, ldy, _dt(x), n, h, w, cx, cy, ng, c0, nc, ci, dwp,
+                                                        dbp, scale, _stream()), "conv3x3_wgrad_grouped")
+
+
 # --------------------------------------------------------------------------------------------
 # feature-extractor body
 # --------------------------------------------------------------------------------------------

@@ -130,6 +130,19 @@ int nervecl_conv2d_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy
                          float* dw, float* db, int N, int H, int W, int Cin, int Cout, int K,
                          float scale, int engine, nervecl_stream_t stream);
 
+/* Weight (+bias) gradients of `ngroups` 3x3 convolutions that read channel PREFIXES [0, cin_g) of one input
+ * buffer x (Cx channels) and whose output gradients are the channel slices [col0_g, col0_g + ncols_g) of one
+ * buffer dy (Cy <= 160 channels) -- the five layers of a ResidualDenseBlock (super_resolution.py:234-252;
+ * ATen convolution_backward's weight/bias outputs for each of them) in one tcgen05 GEMM:
+ *   dw_g[o, c, ky, kx] += scale * sum_p dy[p, col0_g + o] * x[p + (ky-1, kx-1), c] ;  db_g[o] += scale * sum_p dy
+ * Host arrays have ngroups entries, sorted by ascending cin; dw_g is fp32 OIHW [ncols_g][cin_g][3][3];
+ * db_host may be NULL (or hold NULL entries).  bf16 only. */
+int nervecl_conv3x3_wgrad_grouped(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype,
+                                  int N, int H, int W, int Cx, int Cy, int ngroups,
+                                  const int32_t* col0_host, const int32_t* ncols_host,
+                                  const int32_t* cin_host, float* const* dw_host, float* const* db_host,
+                                  float scale, nervecl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Depthwise 3x3 (groups=C, no bias): efficient_layers.py:37-46,63.
  * w is the parameter itself, fp32 [C][1][3][3].  flip=1 applies the 180-degree rotated filter

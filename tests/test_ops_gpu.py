@@ -488,3 +488,25 @@ def test_conv_wgrad_tcgen05(shape):
                       ops.CONV_TC)
     assert relerr(dw, 0.5 * wt.grad) <= 1e-3          # operands are exact bf16, accumulation is fp32
     assert relerr(db, 0.5 * b.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 20, 200), (2, 33, 128), (1, 9, 640)])
+def test_conv3x3_wgrad_grouped_dense_block(shape):
+    """One GEMM for the weight/bias gradients of the five dense-block layers (channel-prefix inputs of one
+    buffer, adjacent output-gradient slices) == five separate ATen convolution_backward calls."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 31)
+    buf = bf(torch.randn(n, 224, h, w, generator=g))
+    dy = bf(torch.randn(n, 160, h, w, generator=g))
+    dws = [torch.zeros(32, 64 + 32 * i, 3, 3, device="cuda") for i in range(5)]
+    dbs = [torch.zeros(32, device="cuda") for _ in range(5)]
+    xb = nhwc(buf, torch.bfloat16, pad_to=256)
+    gb = nhwc(torch.cat([torch.zeros(n, 64, h, w), dy], 1), torch.bfloat16, pad_to=256)
+    nv().conv3x3_wgrad_grouped(xb[..., :192], gb[..., 64:224], dws, dbs, [32 * i for i in range(5)], 0.5)
+    for i in range(5):
+        cin = 64 + 32 * i
+        wt = torch.zeros(32, cin, 3, 3, requires_grad=True)
+        b = torch.zeros(32, requires_grad=True)
+        F.conv2d(buf[:, :cin], wt, b, 1, 1).backward(dy[:, 32 * i:32 * i + 32])
+        assert relerr(dws[i], 0.5 * wt.grad) <= 1e-3, i
+        assert relerr(dbs[i], 0.5 * b.grad) <= 1e-3, i
