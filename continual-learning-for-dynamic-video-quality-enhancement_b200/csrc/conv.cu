@@ -23,6 +23,11 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   int engine = p->engine;
+  if (p->x2) {                                   // second input: row-streaming engine only
+    if (p->Cin2 <= 0 || p->ldx2 < p->Cin2) return NERVECL_EINVAL;
+    if ((engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) || !conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
+    return conv_rows_fwd(*p, s);
+  }
   if (engine == NERVECL_CONV_AUTO) engine = conv_tc_fwd_supported(*p) ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
   if (engine == NERVECL_CONV_TC) {               // best tcgen05 kernel for the shape
     if (conv_rows_supported(*p)) return conv_rows_fwd(*p, s);

@@ -59,7 +59,9 @@ struct EpiChunk {
   uint4 acc[2], res[2], msk[2], sub[2];
   bool vec, has_res, has_mask;
 
-  __device__ __forceinline__ void issue(const EpiArgs& a, uint32_t taddr, int c0, bool valid, int64_t p) {
+  // have_pm: the 16 mask values of this chunk were already fetched by the caller (prefetched rows ahead)
+  __device__ __forceinline__ void issue(const EpiArgs& a, uint32_t taddr, int c0, bool valid, int64_t p,
+                                        bool have_pm = false, uint4 pm0 = uint4{0, 0, 0, 0}, uint4 pm1 = uint4{0, 0, 0, 0}) {
     tmem_ld16(taddr + (uint32_t)c0, v);
     // fast path: the chunk lies fully inside every channel range it touches
     vec = valid && (c0 + 16 <= a.Cout) && !(a.res && c0 < a.res_channels && c0 + 16 > a.res_channels) &&
@@ -70,7 +72,8 @@ struct EpiChunk {
       if (a.accumulate) load16(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c0, acc);
       if (has_res) load16(a.res + p * a.ldres + c0, res);
       if (has_mask) {
-        load16(a.mask + p * a.ldmask + c0, msk);
+        if (have_pm) { msk[0] = pm0; msk[1] = pm1; }
+        else load16(a.mask + p * a.ldmask + c0, msk);
         if (a.msub) load16(a.msub + p * a.ldmsub + c0, sub);
       }
     }

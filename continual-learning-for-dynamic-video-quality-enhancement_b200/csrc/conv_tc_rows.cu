@@ -7,7 +7,8 @@
 // Here a persistent CTA owns work items (image n, 128-pixel column strip, R output rows) and streams the
 // item's R+2 input rows top to bottom:
 //   * TMA brings each halo'd input row {64 ch, 130 px} per 64-channel chunk into shared memory ONCE
-//     (128B swizzle, out-of-image pixels / rows / channels are zero-filled = conv padding);
+//     (128B swizzle, out-of-image pixels / rows / channels are zero-filled = conv padding); the ring is
+//     chunk-granular, so wide inputs still get several stages;
 //   * the horizontal taps kx = 0,1,2 are three K-major smem descriptors into that same row, offset by one
 //     pixel (128 B): the 128B swizzle is a function of the absolute smem address, so an operand may start at
 //     any pixel of a 1024-aligned buffer;
@@ -15,14 +16,18 @@
 //     W[ky=0] to r+1, whose accumulators occupy ADJACENT column slots of a TMEM ring, so one tcgen05.mma with
 //     N = 3*NOUT (A = row r, B = [W(ky=2) | W(ky=1) | W(ky=0)] rows) updates all three: 4 KB of A per 3*NOUT
 //     columns instead of per NOUT columns.  (3*NOUT > 256 falls back to one MMA per ky.)
-//   * all 9*Cin*NOUT weights stay resident in shared memory; output row o is final after input row o+1 and
-//     is drained by 8 epilogue warps (fused bias / ReLU / scale / residual / accumulate / ReLU-mask / store)
-//     while the MMAs of the following rows run.
+//   * all weights stay resident in shared memory; output row o is final after input row o+1 and is drained by
+//     8 epilogue warps (fused bias / ReLU / scale / residual / accumulate / ReLU-mask / store), which also
+//     re-zero the accumulator slot (every MMA accumulates) and prefetch the ReLU-mask operand rows ahead;
+//   * an optional SECOND input tensor x2 is a virtual channel concat ([x | x2], no copy); with x2_center its
+//     channels only see the centre tap -- a fused 1x1 branch (the dense block's LFF data gradient).
 // Output channels beyond what fits (smem for weights, 128 TMEM columns per row) are split over blockIdx.y.
 #include "conv_internal.cuh"
 #include "conv_tc_epilogue.cuh"
 #include "tc_common.cuh"
+#include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 using namespace nv;
 using namespace nv::tc;
@@ -36,35 +41,51 @@ constexpr uint32_t ROWB = KC * 2;                  // bytes per pixel row of a c
 constexpr int PXB = BM + 2;                        // staged pixels per input row (one halo pixel each side)
 constexpr uint32_t CHUNK_BYTES = (PXB * ROWB + 1023u) & ~1023u;
 constexpr int kMaxSlots = 32;
+constexpr int kMaxStages = 12;
 constexpr size_t kSmemBudget = 226 * 1024;
 
 struct RowArgs : EpiArgs {
   int N, H, W;
   int NOUT;         // output channels per CTA (multiple of 16, <= 128)
-  int nchunks;      // 64-channel chunks of Cin
-  int ksteps_last;  // 16-channel k-steps of the last chunk
+  int nchunks;      // 64-channel chunks of x
+  int ksteps_last;  // 16-channel k-steps of the last x chunk
+  int nchunks2;     // 64-channel chunks of x2 (0: no second input)
+  int ksteps2_last;
+  int x2_center;    // x2 channels only have a centre tap
   int strips, R, segs;
-  int stages;       // input-row ring depth
+  int cps;          // chunks per ring stage (a stage is filled / released as a unit)
+  int stages;       // ring depth in stages
   int slots;        // TMEM accumulator ring depth
   int merged;       // vertical taps merged into N
-  int dbg;          // NERVECL_ROWS_DBG bits (profiling only): 1 no MMAs, 2 no row loads, 4 no epilogue stores
+  int dbg;          // NERVECL_ROWS_DBG bits (profiling only): 1 no MMAs, 2 no row loads, 4 no epilogue work
 };
 
-template <typename OutT>
+// weight tile index of (kx, chunk): x chunks first, then x2 chunks (one tile per chunk when centre-only)
+__device__ __forceinline__ int wtile_index(const RowArgs& a, int kx, int c) {
+  if (c < a.nchunks) return kx * a.nchunks + c;
+  const int c2 = c - a.nchunks;
+  return 3 * a.nchunks + (a.x2_center ? c2 : kx * a.nchunks2 + c2);
+}
+
+template <typename OutT, bool PF>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const RowArgs a) {
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
+                 const __grid_constant__ CUtensorMap tmap_w, const RowArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t blk_bytes = (uint32_t)a.NOUT * ROWB;          // one ky block of one (kx, chunk) weight tile
   const uint32_t wtile_bytes = 3u * blk_bytes;
-  const uint32_t w_bytes = 3u * (uint32_t)a.nchunks * wtile_bytes;
-  const uint32_t stage_bytes = (uint32_t)a.nchunks * CHUNK_BYTES;
+  const int nct = a.nchunks + a.nchunks2;
+  const int ntiles = 3 * a.nchunks + (a.x2_center ? 1 : 3) * a.nchunks2;
+  const uint32_t w_bytes = (uint32_t)ntiles * wtile_bytes;
   uint8_t* w_smem = smem;
   uint8_t* ring = smem + w_bytes;
+  const uint32_t stage_bytes = (uint32_t)a.cps * CHUNK_BYTES;
+  const int ngrp = nct / a.cps;                     // stages per input row
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * stage_bytes);
-  uint64_t* row_full = bars;                        // [stages]  TMA -> MMA
-  uint64_t* row_empty = row_full + a.stages;        // [stages]  MMA -> TMA
-  uint64_t* acc_full = row_empty + a.stages;        // [slots]   MMA -> epilogue
+  uint64_t* ch_full = bars;                         // [stages]  TMA -> MMA
+  uint64_t* ch_empty = ch_full + a.stages;          // [stages]  MMA -> TMA
+  uint64_t* acc_full = ch_empty + a.stages;         // [slots]   MMA -> epilogue
   uint64_t* acc_empty = acc_full + a.slots;         // [slots]   epilogue -> MMA
   uint64_t* w_bar = acc_empty + a.slots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
@@ -77,9 +98,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_w);
+    if (a.nchunks2) prefetch_tmap(&tmap_x2);
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&row_full[s], 1);
-      mbar_init(&row_empty[s], 1);
+      mbar_init(&ch_full[s], 1);
+      mbar_init(&ch_empty[s], 1);
     }
     for (int s = 0; s < S; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -98,11 +120,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       mbar_expect_tx(w_bar, w_bytes);
-      for (int kx = 0; kx < 3; ++kx)
-        for (int c = 0; c < a.nchunks; ++c)
+      for (int c = 0; c < nct; ++c)
+        for (int kx = 0; kx < 3; ++kx) {
+          if (c >= a.nchunks && a.x2_center && kx != 1) continue;
           for (int b = 0; b < 3; ++b)     // block b holds ky = 2 - b
-            tma_load_3d(w_smem + (size_t)(kx * a.nchunks + c) * wtile_bytes + (size_t)b * blk_bytes, &tmap_w, w_bar,
+            tma_load_3d(w_smem + (size_t)wtile_index(a, kx, c) * wtile_bytes + (size_t)b * blk_bytes, &tmap_w, w_bar,
                         c * KC, grp * a.NOUT, (2 - b) * 3 + kx);
+        }
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -111,34 +135,41 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int strip = t % a.strips, n = t / a.strips;
         const int y0 = seg * a.R, rows = min(a.R, a.H - y0), x0 = strip * BM;
         for (int ri = 0; ri < rows + 2; ++ri) {
-          mbar_wait(&row_empty[stage], phase ^ 1);
-          if (a.dbg & 2) { mbar_arrive(&row_full[stage]); if (++stage == a.stages) { stage = 0; phase ^= 1; } continue; }
-          mbar_expect_tx(&row_full[stage], (uint32_t)a.nchunks * (PXB * ROWB));
-          uint8_t* dst = ring + (size_t)stage * stage_bytes;
-          for (int c = 0; c < a.nchunks; ++c)
-            tma_load_4d(dst + (size_t)c * CHUNK_BYTES, &tmap_x, &row_full[stage], c * KC, x0 - 1, y0 - 1 + ri, n);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          for (int gi = 0; gi < ngrp; ++gi) {
+            mbar_wait(&ch_empty[stage], phase ^ 1);
+            if (a.dbg & 2) {
+              mbar_arrive(&ch_full[stage]);
+            } else {
+              mbar_expect_tx(&ch_full[stage], (uint32_t)a.cps * (PXB * ROWB));
+              for (int cc = 0; cc < a.cps; ++cc) {
+                const int c = gi * a.cps + cc;
+                uint8_t* dst = ring + (size_t)stage * stage_bytes + (size_t)cc * CHUNK_BYTES;
+                if (c < a.nchunks) tma_load_4d(dst, &tmap_x, &ch_full[stage], c * KC, x0 - 1, y0 - 1 + ri, n);
+                else tma_load_4d(dst, &tmap_x2, &ch_full[stage], (c - a.nchunks) * KC, x0 - 1, y0 - 1 + ri, n);
+              }
+            }
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // Everything below runs on ONE thread whose instruction latency is the issue-rate limit (a dependent
-    // scalar instruction costs ~5 cycles, an N=96 MMA only 48), so the per-MMA work is a table lookup
-    // (descriptor low words precomputed once per CTA) plus two adds.  Accumulators are zeroed by the
-    // epilogue warps, so every MMA accumulates and the tap grouping of a row never changes mid-row.
     // All 32 lanes run the (warp-uniform) control flow; one elected lane issues the MMAs and commits, so
-    // ptxas keeps descriptors in uniform registers instead of emitting a per-MMA lane-election loop.
+    // ptxas keeps descriptors in uniform registers instead of emitting a per-MMA lane-election loop.  A
+    // dependent scalar instruction costs ~5 cycles and an N=96 MMA only 48, so the per-MMA work is two adds.
+    // Accumulators are zeroed by the epilogue warps: every MMA accumulates.
     {
       const uint32_t w_lo = (smem_u32(w_smem) & 0x3FFFFu) >> 4;
       const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);     // | LBO field (unused) = 1
-      const uint32_t stage_lo = stage_bytes >> 4, blk_lo = blk_bytes >> 4, wtile_lo = wtile_bytes >> 4;
+      const uint32_t blk_lo = blk_bytes >> 4, wtile_lo = wtile_bytes >> 4;
       const uint64_t desc_hi = make_kmajor_desc(0, ROWB) & 0xFFFFFFFF00000000ull;
       const uint32_t id1 = make_idesc_bf16((uint32_t)a.NOUT), id2 = make_idesc_bf16(2u * a.NOUT),
                      id3 = make_idesc_bf16(3u * a.NOUT);
       int stage = 0;
       uint32_t phase = 0;
       int jbase = 0;                      // output rows issued so far by this CTA (running index -> TMEM slot)
+      bool ready = false;                 // early, non-blocking probe of the next chunk's barrier succeeded
       mbar_wait(w_bar, 0);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int seg = item % a.segs;
@@ -171,33 +202,54 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
           }
           if (bhi == 2) mbar_wait(&acc_empty[s2], r2 & 1u);     // slot of the new output row is drained + zeroed
-          mbar_wait(&row_full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_lo;
-          if (elect_one()) {
-            if (!(a.dbg & 1)) {
-              for (int g = 0; g < ng; ++g) {
-                const uint32_t d = tmem_base + (g == 0 ? gc0 : g == 1 ? gc1 : gc2);
-                const uint32_t b_lo = w_lo + (g == 0 ? gb0 : g == 1 ? gb1 : gb2);
-                const uint32_t id = g == 0 ? gi0 : g == 1 ? gi1 : gi2;
-                for (int c = 0; c < a.nchunks; ++c) {
-                  const int ks = (c == a.nchunks - 1) ? a.ksteps_last : KC / 16;
+          for (int gi = 0; gi < ngrp; ++gi) {
+            if (!ready) mbar_wait(&ch_full[stage], phase);
+            tc_fence_after();
+            int nstage = stage + 1;
+            uint32_t nphase = phase;
+            if (nstage == a.stages) { nstage = 0; nphase ^= 1; }
+            if (elect_one()) {
+              if (!(a.dbg & 1)) {
+                for (int cc = 0; cc < a.cps; ++cc) {
+                  const int c = gi * a.cps + cc;
+                  const uint32_t a_lo = ring_lo + (uint32_t)stage * (stage_bytes >> 4) + (uint32_t)cc * (CHUNK_BYTES >> 4);
+                  const bool second = c >= a.nchunks;
+                  const int ks = (c == a.nchunks - 1) ? a.ksteps_last : (c == nct - 1 && second) ? a.ksteps2_last : KC / 16;
+                  const bool ctr = second && a.x2_center;                         // centre tap only
+                  // weight tile of (kx, c): tile0 + kx * tstride
+                  const uint32_t tile0 = (uint32_t)(second ? 3 * a.nchunks + (c - a.nchunks) : c);
+                  const uint32_t tstride = (uint32_t)(second ? (ctr ? 0 : a.nchunks2) : a.nchunks);
+                  for (int g = 0; g < ng; ++g) {
+                    const uint32_t d = tmem_base + (g == 0 ? gc0 : g == 1 ? gc1 : gc2);
+                    const uint32_t gb = w_lo + (g == 0 ? gb0 : g == 1 ? gb1 : gb2) + tile0 * wtile_lo;
+                    const uint32_t id = g == 0 ? gi0 : g == 1 ? gi1 : gi2;
 #pragma unroll
-                  for (int kx = 0; kx < 3; ++kx) {
-                    const uint32_t al = a_lo + (uint32_t)c * (CHUNK_BYTES >> 4) + (uint32_t)kx * (ROWB >> 4);
-                    const uint32_t bl = b_lo + (uint32_t)(kx * a.nchunks + c) * wtile_lo;
+                    for (int kx = 0; kx < 3; ++kx) {
+                      if (ctr && kx != 1) continue;
+                      const uint32_t al = a_lo + (uint32_t)kx * (ROWB >> 4);
+                      const uint32_t bl = (1u << 16) | (gb + (uint32_t)kx * tstride * wtile_lo);
+                      if (ks == KC / 16) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k)
-                      if (k < ks) umma_bf16_acc(d, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)((1u << 16) | (bl + 2u * k)), id);
+                        for (int k = 0; k < KC / 16; ++k)
+                          umma_bf16_acc(d, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)(bl + 2u * k), id);
+                      } else {
+#pragma unroll
+                        for (int k = 0; k < KC / 16 - 1; ++k)
+                          if (k < ks) umma_bf16_acc(d, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)(bl + 2u * k), id);
+                      }
+                    }
                   }
                 }
               }
+              umma_commit(&ch_empty[stage]);                                  // stage consumed when these MMAs retire
+              if (gi == ngrp - 1 && ri >= 2) umma_commit(&acc_full[s0]);      // output row ri-2 (slot s0) is final
             }
-            umma_commit(&row_empty[stage]);                       // input row consumed when these MMAs retire
-            if (ri >= 2) umma_commit(&acc_full[s0]);              // output row ri-2 (slot s0) is final
+            __syncwarp();
+            // probe the next stage's barrier now: its latency overlaps the MMAs just issued
+            ready = mbar_try_wait(&ch_full[nstage], nphase);
+            stage = nstage;
+            phase = nphase;
           }
-          __syncwarp();
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
           if (++s2 == S) { s2 = 0; ++r2; }
         }
         jbase += rows;
@@ -219,6 +271,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     __syncwarp();
     if (lane == 0)
       for (int sl = 0; sl < S; ++sl) mbar_arrive(&acc_empty[sl]);
+    // ReLU-mask prefetch: with NOUT <= 32 a thread owns ONE 16-channel chunk per row; its mask values for the
+    // next 4 rows of the item are kept in flight so the epilogue is not a chain of exposed HBM latencies.
+    const int cm = c_lo + part * 16;                       // absolute first channel of that chunk
+    // (PF kernels are only launched with a mask, no mask_sub and NOUT <= 32)
+    const bool pf = PF && part < nch && cm >= a.mask_c0 && cm + 16 <= a.Cout && !(a.dbg & 4);
+    uint4 mqa[4], mqb[4];            // [row slot]: channels cm..cm+7 and cm+8..cm+15
+#pragma unroll
+    for (int d = 0; d < 4; ++d) mqa[d] = mqb[d] = make_uint4(0, 0, 0, 0);
     int slot = 0;
     uint32_t par = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -228,30 +288,63 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
       const int x = strip * BM + row;
       const bool valid = x < a.W;
-      int64_t p = ((int64_t)n * a.H + y0) * a.W + x;
-      for (int oi = 0; oi < rows; ++oi, p += a.W) {
+      const int64_t p0 = ((int64_t)n * a.H + y0) * a.W + x;
+      const bool pfv = pf && valid;
+      if (pfv) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+          if (d < rows) {
+            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (p0 + (int64_t)d * a.W) * a.ldmask + cm);
+            mqa[d] = mp[0];
+            mqb[d] = mp[1];
+          }
+      }
+      for (int oi4 = 0; oi4 < rows; oi4 += 4) {
+#pragma unroll
+       for (int D = 0; D < 4; ++D) {             // static D after unrolling: the prefetch slots stay in registers
+        const int oi = oi4 + D;
+        if (oi >= rows) break;
+        const int64_t p = p0 + (int64_t)oi * a.W;
+        const uint4 cur0 = mqa[D], cur1 = mqb[D];
+        if (pfv && oi + 4 < rows) {
+          const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (p + 4 * (int64_t)a.W) * a.ldmask + cm);
+          mqa[D] = mp[0];
+          mqb[D] = mp[1];
+        }
         mbar_wait(&acc_full[slot], par);
         tc_fence_after();
         const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT);
         // column address such that (taddr + absolute channel) is the accumulator column of that channel
         const uint32_t taddr = tcol - (uint32_t)c_lo;
-        for (int c = part; c < nch_all; c += 4) {
-          EpiChunk<OutT> e0, e1;
-          const bool two = c + 2 < nch_all;
-          const bool live0 = c < nch && !(a.dbg & 4), live1 = two && c + 2 < nch && !(a.dbg & 4);
-          if (live0) e0.issue(a, taddr, c_lo + c * 16, valid, p);
-          if (live1) e1.issue(a, taddr, c_lo + (c + 2) * 16, valid, p);
-          tmem_ld_wait();
-          tmem_st16_zero(tcol + (uint32_t)(c * 16));            // re-arm the slot for its next output row
-          if (two) tmem_st16_zero(tcol + (uint32_t)((c + 2) * 16));
-          if (live0) e0.finish(a, c_lo + c * 16, valid, p);
-          if (live1) e1.finish(a, c_lo + (c + 2) * 16, valid, p);
+        if (PF) {                                                  // one chunk per thread (c = part), mask prefetched
+          if (part < nch_all) {
+            EpiChunk<OutT> e0;
+            const bool live0 = part < nch && !(a.dbg & 4);
+            if (live0) e0.issue(a, taddr, c_lo + part * 16, valid, p, pfv, cur0, cur1);
+            tmem_ld_wait();
+            tmem_st16_zero(tcol + (uint32_t)(part * 16));          // re-arm the slot for its next output row
+            if (live0) e0.finish(a, c_lo + part * 16, valid, p);
+          }
+        } else {
+          for (int c = part; c < nch_all; c += 4) {
+            EpiChunk<OutT> e0, e1;
+            const bool two = c + 2 < nch_all;
+            const bool live0 = c < nch && !(a.dbg & 4), live1 = two && c + 2 < nch && !(a.dbg & 4);
+            if (live0) e0.issue(a, taddr, c_lo + c * 16, valid, p);
+            if (live1) e1.issue(a, taddr, c_lo + (c + 2) * 16, valid, p);
+            tmem_ld_wait();
+            tmem_st16_zero(tcol + (uint32_t)(c * 16));            // re-arm the slot for its next output row
+            if (two) tmem_st16_zero(tcol + (uint32_t)((c + 2) * 16));
+            if (live0) e0.finish(a, c_lo + c * 16, valid, p);
+            if (live1) e1.finish(a, c_lo + (c + 2) * 16, valid, p);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
         if (++slot == S) { slot = 0; par ^= 1u; }
+       }
       }
     }
   }
@@ -264,7 +357,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 struct RowPlan {
-  int NOUT, nsplit, nchunks, ksteps_last, stages, slots, merged, strips, R, segs;
+  int NOUT, nsplit, nchunks, ksteps_last, nchunks2, ksteps2_last, cps, stages, slots, merged, strips, R, segs;
   size_t smem;
 };
 
@@ -272,20 +365,33 @@ struct RowPlan {
 bool plan_rows(const nervecl_conv_params& a, int sms, RowPlan& p) {
   p.nchunks = (a.Cin + KC - 1) / KC;
   p.ksteps_last = (a.Cin - (p.nchunks - 1) * KC + 15) / 16;
+  p.nchunks2 = a.x2 ? (a.Cin2 + KC - 1) / KC : 0;
+  p.ksteps2_last = a.x2 ? (a.Cin2 - (p.nchunks2 - 1) * KC + 15) / 16 : 0;
+  const int nct = p.nchunks + p.nchunks2;
+  const int ntiles = 3 * p.nchunks + ((a.x2 && a.x2_center) ? 1 : 3) * p.nchunks2;
   const int cout16 = (a.Cout + 15) / 16 * 16;
-  const size_t stage_bytes = (size_t)p.nchunks * CHUNK_BYTES;
   p.nsplit = 0;
-  for (int ns = 1; ns <= 16; ++ns) {
+  for (int ns = 1; ns <= 16 && !p.nsplit; ++ns) {
     const int nout = ((cout16 + ns - 1) / ns + 15) / 16 * 16;
     if (nout > 128) continue;
-    const size_t w_bytes = (size_t)9 * p.nchunks * nout * ROWB;
-    const size_t fixed = 1024 + w_bytes + (2 * 8 + 2 * kMaxSlots + 2) * sizeof(uint64_t) + 64;
-    if (fixed + 2 * stage_bytes > kSmemBudget) continue;
-    p.nsplit = ns;
-    p.NOUT = nout;
-    p.stages = (int)imin(8, (int64_t)((kSmemBudget - fixed) / stage_bytes));
-    p.smem = fixed + (size_t)p.stages * stage_bytes;
-    break;
+    const size_t w_bytes = (size_t)3 * ntiles * nout * ROWB;
+    const size_t fixed = 1024 + w_bytes + (2 * kMaxStages + 2 * kMaxSlots + 2) * sizeof(uint64_t) + 64;
+    if (fixed >= kSmemBudget) continue;
+    const int chunks_fit = (int)((kSmemBudget - fixed) / CHUNK_BYTES);
+    // a ring stage holds `cps` chunks (a divisor of the chunks per row): whole rows when two of them fit
+    // (one barrier round trip and one commit per row), else the largest group that still leaves >= 3 stages
+    for (int cps = nct; cps >= 1; --cps) {
+      if (nct % cps) continue;
+      const int st = chunks_fit / cps;
+      if (st >= (cps == nct ? 2 : 3)) {
+        p.nsplit = ns;
+        p.NOUT = nout;
+        p.cps = cps;
+        p.stages = (int)imin(kMaxStages, st);
+        p.smem = fixed + (size_t)p.stages * cps * CHUNK_BYTES;
+        break;
+      }
+    }
   }
   if (!p.nsplit) return false;
   p.slots = (int)imin(kMaxSlots, 512 / p.NOUT);
@@ -310,10 +416,16 @@ bool plan_rows(const nervecl_conv_params& a, int sms, RowPlan& p) {
 namespace nv {
 
 bool conv_rows_supported(const nervecl_conv_params& a) {
-  if (!conv_tc_fwd_supported(a)) return false;       // dtype / alignment / epilogue constraints are the same
+  nervecl_conv_params b = a;
+  b.x2 = nullptr;
+  if (!conv_tc_fwd_supported(b)) return false;       // dtype / alignment / epilogue constraints are the same
   if (a.K != 3) return false;
   if (a.Cin < 32 || a.Cin % 16 || a.Cin > 512) return false;
   if (a.W < 64 || a.H < 3) return false;
+  if (a.x2) {
+    if (a.Cin2 < 16 || a.Cin2 % 16 || a.Cin2 > 256 || a.ldx2 % 8 || !aligned(a.x2, 16)) return false;
+    if (a.w_ld < (a.Cin + KC - 1) / KC * KC + a.Cin2) return false;   // x2 weights start at the next 64-column boundary
+  }
   RowPlan p;
   return plan_rows(a, sm_count(), p);
 }
@@ -325,18 +437,25 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   RowPlan p;
   if (!plan_rows(a, sms, p)) return NERVECL_EUNSUPPORTED;
 
-  CUtensorMap tx, tw;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
-    cuuint64_t strides[3] = {(cuuint64_t)a.ldx * 2, (cuuint64_t)a.W * a.ldx * 2, (cuuint64_t)a.H * a.W * a.ldx * 2};
+  CUtensorMap tx, tx2, tw;
+  auto encode_act = [&](CUtensorMap* m, const void* base, int C, int64_t ld) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)a.W * ld * 2, (cuuint64_t)a.H * a.W * ld * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)PXB, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return NERVECL_EUNSUPPORTED;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!encode_act(&tx, a.x, a.Cin, a.ldx)) return NERVECL_EUNSUPPORTED;
+  if (a.x2) {
+    if (!encode_act(&tx2, a.x2, a.Cin2, a.ldx2)) return NERVECL_EUNSUPPORTED;
+  } else {
+    tx2 = tx;
   }
   {
+    // the x2 weight columns start at column nchunks*64 of the packed rows; TMA boxes address them as chunk
+    // (nchunks + c2), so one map over the whole row length serves both inputs
     cuuint64_t dims[3] = {(cuuint64_t)a.w_ld, (cuuint64_t)a.w_rows, 9};
     cuuint64_t strides[2] = {(cuuint64_t)a.w_ld * 2, (cuuint64_t)a.w_rows * a.w_ld * 2};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.NOUT, 1};
@@ -356,22 +475,36 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.out = a.out; t.ldo = a.ldo;
   t.N = a.N; t.H = a.H; t.W = a.W;
   t.NOUT = p.NOUT; t.nchunks = p.nchunks; t.ksteps_last = p.ksteps_last;
-  t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
+  t.nchunks2 = p.nchunks2; t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
+  t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
   { const char* d = getenv("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
 
   const int64_t items = (int64_t)a.N * p.strips * p.segs;
   dim3 grid((unsigned)imin(items, imax(1, sms / p.nsplit)), (unsigned)p.nsplit);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  const bool pf = a.mask && !a.mask_sub && p.NOUT <= 32;
+#define NV_LAUNCH_ROWS(OT, PFV)                                                                                       \
+  do {                                                                                                                \
+    e = cudaFuncSetAttribute(conv_rows_kernel<OT, PFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);     \
+    if (e != cudaSuccess) return (int)e;                                                                              \
+    conv_rows_kernel<OT, PFV><<<grid, kThreads, p.smem, s>>>(tx, tx2, tw, t);                                          \
+  } while (0)
   if (a.out_dtype == NERVECL_F32) {
-    e = cudaFuncSetAttribute(conv_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return (int)e;
-    conv_rows_kernel<float><<<grid, kThreads, p.smem, s>>>(tx, tw, t);
+    if (pf) NV_LAUNCH_ROWS(float, true); else NV_LAUNCH_ROWS(float, false);
   } else {
-    e = cudaFuncSetAttribute(conv_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return (int)e;
-    conv_rows_kernel<bf16><<<grid, kThreads, p.smem, s>>>(tx, tw, t);
+    if (pf) NV_LAUNCH_ROWS(bf16, true); else NV_LAUNCH_ROWS(bf16, false);
   }
-  return launch_status();
+#undef NV_LAUNCH_ROWS
+  int rc = launch_status();
+  if (rc == (int)cudaErrorLaunchOutOfResources) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, conv_rows_kernel<bf16, false>) == cudaSuccess)
+      fprintf(stderr, "nervecl conv_rows: launch out of resources: regs %d maxThreads %d static smem %zu maxDyn %d; requested "
+                      "dyn smem %zu, block %d, grid %u x %u\n",
+              fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, p.smem, kThreads, grid.x,
+              grid.y);
+  }
+  return rc;
 }
 
 }  // namespace nv

@@ -216,6 +216,20 @@ class Plan:
             if name != "feature_extractor.head.0":   # the input frames need no gradient
                 self.wb[name] = torch.empty((kk, c.cin_pad, _align(c.cout, 8)), device=device, dtype=adt)
 
+        # Fused dense-block data gradient (bf16 tcgen05 path): the gradient of buffer slice s is ONE conv over the
+        # already-final gradients of all later layers (adjacent channels of the gradient buffer) plus the LFF
+        # 1x1 branch as a centre-tap-only second input.  wslice[s][k]: packed [9, rows, cols] per block k with
+        # cols = [later layers' 32-ch groups, padded to 64 | 64 LFF channels]; s = 0 is the block input x.
+        self.fused_rdb_bwd = False
+        self.wslice: List[Tensor] = []
+        if adt == torch.bfloat16 and W >= 64 and H >= 3 and self.NB > 0:
+            self.fused_rdb_bwd = True
+            for s in range(RDB_LAYERS):                       # s = 0: x slice (F channels); s >= 1: layer s-1's output
+                rows = F if s == 0 else GROWTH
+                cmain = GROWTH * (RDB_LAYERS - s) if s > 0 else GROWTH * RDB_LAYERS
+                cols = _align(cmain, 64) + F
+                self.wslice.append(torch.zeros((9, self.NB * rows, cols), device=device, dtype=adt))
+
     # ---- activation-set pool ---------------------------------------------------------------
     def acquire(self) -> Activations:
         return self._free.pop() if self._free else Activations(self)
@@ -232,6 +246,26 @@ class Plan:
             nv.pack_conv_weight(w, self.wf[name], False)
             if need_bwd and name in self.wb:
                 nv.pack_conv_weight(w, self.wb[name], True)
+
+    def pack_rdb_slice_weights(self, P: Dict[str, Tensor]) -> None:
+        """Assemble (in fp32, batched over the blocks) and pack the slice-gradient operators described in
+        ``__init__``:  W_s[c, (i,o), tap] = W_i[o, c_lo+c, 8-tap] for the later layers i, and for the LFF columns
+        the centre tap 0.2 * W_lff[d, c_lo+c]."""
+        F, NB = self.F, self.NB
+        Wl = [torch.stack([P[f"residual_blocks.{k}.layers.{i}.0.weight"] for k in range(NB)]) for i in range(RDB_LAYERS)]
+        Wf = torch.stack([P[f"residual_blocks.{k}.lff.weight"] for k in range(NB)])[..., 0, 0]      # [NB, F, CT]
+        for s in range(RDB_LAYERS):
+            rows = F if s == 0 else GROWTH
+            c_lo = 0 if s == 0 else F + (s - 1) * GROWTH
+            first = 0 if s == 0 else s                      # first later layer
+            cmain = GROWTH * (RDB_LAYERS - first)
+            cols = _align(cmain, 64) + F
+            comb = torch.zeros((NB, rows, cols, 3, 3), device=self.device, dtype=torch.float32)
+            for j, i in enumerate(range(first, RDB_LAYERS)):
+                blk = Wl[i][:, :, c_lo:c_lo + rows]          # [NB, o, c, 3, 3]
+                comb[:, :, j * GROWTH:(j + 1) * GROWTH] = blk.permute(0, 2, 1, 3, 4).flip(3, 4)
+            comb[:, :, _align(cmain, 64):, 1, 1] = 0.2 * Wf[:, :, c_lo:c_lo + rows].permute(0, 2, 1)    # [NB, c, d]
+            nv.pack_conv_weight(comb.view(NB * rows, cols, 3, 3), self.wslice[s], False)
 
     # ---- helpers ---------------------------------------------------------------------------
     def _span(self, kind: str, x: Tensor, cin: int, cout: int, k: int):
@@ -382,6 +416,55 @@ class Plan:
             self._bwd_ws = ws
         return self._bwd_ws
 
+    def _rdb_backward_layers(self, k: int, buf: Tensor, g: Tensor, dblock: Tensor, G: Dict[str, Tensor]) -> None:
+        """Layer-by-layer dense-block backward (fp32 parity path and small shapes): each layer's data gradient is
+        accumulated into the shared gradient buffer by the conv epilogue."""
+        F = self.F
+        CT = F + RDB_LAYERS * GROWTH
+        name = f"residual_blocks.{k}.lff"
+        # g[:, :CT] = 0.2 * lff^T(dblock) (+ dblock on the first F channels: the block skip);
+        # slice 4 (channels >= F+4G) has no other consumer, so its ReLU mask is applied here.
+        self.dgrad(name, dblock, g, cout=CT, alpha=0.2, res=dblock, res_channels=F, mask=buf,
+                   mask_c0=F + (RDB_LAYERS - 1) * GROWTH)
+        for i in reversed(range(RDB_LAYERS)):
+            c0 = F + i * GROWTH
+            name = f"residual_blocks.{k}.layers.{i}.0"
+            dy = g[..., c0:c0 + GROWTH]
+            self.wgrad(name, buf[..., :c0], dy, G)
+            if i >= 1:
+                self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True, mask=buf, mask_c0=c0 - GROWTH)
+            else:
+                self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True)
+
+    def _rdb_backward_fused(self, k: int, buf: Tensor, g: Tensor, dblock: Tensor, G: Dict[str, Tensor]) -> None:
+        """Dense-block backward as 1 + 5 convolutions that each WRITE one slice of the gradient buffer once
+        (no read-modify-write accumulation) followed by one grouped weight-gradient GEMM."""
+        F = self.F
+        CT = F + RDB_LAYERS * GROWTH
+        lff = f"residual_blocks.{k}.lff"
+        # last slice: only the LFF reaches it.  dy_4 = relu'(o_4) * 0.2 * W_lff[:, slice]^T dblock
+        c4 = F + (RDB_LAYERS - 1) * GROWTH
+        with self._span("conv_dgrad", dblock, F, GROWTH, 1):
+            nv.conv2d_fwd(dblock, self.wb[lff][:, c4:CT, :], None, None, buf[..., c4:CT], None, g[..., c4:CT], GROWTH,
+                          False, False, 0, 0, 0.2, self.engine)
+        for s in range(RDB_LAYERS - 1, -1, -1):              # slices F+(s-1)G .. (s >= 1), then the x slice (s = 0)
+            rows = F if s == 0 else GROWTH
+            c_lo = 0 if s == 0 else F + (s - 1) * GROWTH
+            x_lo = F + (0 if s == 0 else s) * GROWTH          # first channel of the later layers' gradients
+            w = self.wslice[s][:, k * rows:(k + 1) * rows, :]
+            mask = buf[..., c_lo:c_lo + rows] if s > 0 else None
+            with self._span_flops("conv_dgrad|slice", buf, 2.0 * rows * (9 * (CT - x_lo) + F)):
+                # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
+                nv.conv2d_fwd(g[..., x_lo:CT], w, None, dblock if s == 0 else None, mask, None,
+                              g[..., c_lo:c_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,
+                              dblock, True)
+        names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
+        cx = F + (RDB_LAYERS - 1) * GROWTH
+        with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
+                                                                for i in range(RDB_LAYERS))):
+            nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names],
+                                     [G[n + ".bias"] for n in names], [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
+
     def backward(self, A: Activations, dout: Tensor, P: Dict[str, Tensor], G: Dict[str, Tensor],
                  on_grads_ready=None) -> None:
         """Accumulate parameter gradients into ``G`` (name -> fp32 tensor, same shapes as ``P``).
@@ -413,34 +496,17 @@ class Plan:
 
         # ---- residual dense blocks, last to first ----
         CT = F + RDB_LAYERS * GROWTH
+        fused = self.fused_rdb_bwd and self.engine != CONV_SIMT
+        if fused:
+            self.pack_rdb_slice_weights(P)
         for k in reversed(range(self.NB)):
             buf, g = A.rdb[k], ws["g"][k & 1]
             name = f"residual_blocks.{k}.lff"
             self.wgrad(name, buf, dblock, G, scale=0.2)
-            # g[:, :CT] = 0.2 * lff^T(dblock) (+ dblock on the first F channels: the block skip);
-            # slice 4 (channels >= F+4G) has no other consumer, so its ReLU mask is applied here.
-            self.dgrad(name, dblock, g, cout=CT, alpha=0.2, res=dblock, res_channels=F, mask=buf,
-                       mask_c0=F + (RDB_LAYERS - 1) * GROWTH)
-            grouped = self.adt == torch.bfloat16 and self.engine != CONV_SIMT and W >= 64
-            for i in reversed(range(RDB_LAYERS)):
-                c0 = F + i * GROWTH
-                name = f"residual_blocks.{k}.layers.{i}.0"
-                dy = g[..., c0:c0 + GROWTH]
-                if not grouped:
-                    self.wgrad(name, buf[..., :c0], dy, G)
-                if i >= 1:
-                    self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True, mask=buf, mask_c0=c0 - GROWTH)
-                else:
-                    self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True)
-            if grouped:
-                # all five layers' weight/bias gradients in one GEMM: X = the block buffer, dY = g[:, F:]
-                names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
-                cx = F + (RDB_LAYERS - 1) * GROWTH
-                with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
-                                                                        for i in range(RDB_LAYERS))):
-                    nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names],
-                                             [G[n + ".bias"] for n in names],
-                                             [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
+            if fused:
+                self._rdb_backward_fused(k, buf, g, dblock, G)
+            else:
+                self._rdb_backward_layers(k, buf, g, dblock, G)
             ready(f"residual_blocks.{k}.")
             dblock = g[..., :F]
         dagg = dblock

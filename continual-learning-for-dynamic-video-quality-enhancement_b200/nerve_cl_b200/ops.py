@@ -143,9 +143,9 @@ def _pack_conv_weight(w: Tensor, dst: Tensor, transpose_flip: bool) -> None:
 # --------------------------------------------------------------------------------------------
 @_op("conv2d_fwd(Tensor x, Tensor w, Tensor? bias, Tensor? res, Tensor? mask, Tensor? mask_sub, "
      "Tensor(a!) out, int cout, bool relu, bool accumulate, int res_channels, int mask_c0, float alpha, "
-     "int engine) -> ()")
+     "int engine, Tensor? x2=None, bool x2_center=False) -> ()")
 def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, res_channels, mask_c0, alpha,
-                engine) -> None:
+                engine, x2=None, x2_center=False) -> None:
     """Fused conv (see ``nervecl_conv2d_fwd``).  ``w`` is a packed [K*K, rows, cols] tensor; ``cout`` is the
     number of output channels actually computed (<= rows)."""
     xp, ldx, n, h, wd, cin = _nhwc(x, "x")
@@ -156,7 +156,11 @@ def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, re
     k = int(round(kk ** 0.5))
     p = ConvParams()
     p.N, p.H, p.W, p.Cin, p.Cout, p.K = n, h, wd, cin, cout, k
-    p.w_ld, p.w_rows = w.shape[2], w.shape[1]
+    # packed weight: [K*K, rows, cols]; a row-slice view of a larger packed tensor is fine (rows per tap and the
+    # row length come from the strides)
+    if w.stride(2) != 1 or w.stride(0) % max(w.stride(1), 1):
+        raise RuntimeError("nervecl.conv2d_fwd: packed weight must have unit column stride")
+    p.w_ld, p.w_rows = w.stride(1), (w.stride(0) // w.stride(1) if kk > 1 else w.shape[1])
     p.dtype, p.out_dtype = _dt(x), _dt(out)
     if w.dtype != x.dtype:
         raise RuntimeError("nervecl.conv2d_fwd: weight dtype must equal activation dtype")
@@ -174,6 +178,11 @@ def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, re
         sp, lds, *_ = _nhwc(mask_sub, "mask_sub")
         p.mask_sub, p.ldmask_sub = sp, lds
     p.out, p.ldo = op, ldo
+    if x2 is not None:
+        x2p, ldx2, n2, h2, w2, c2 = _nhwc(x2, "x2")
+        if (n2, h2, w2) != (n, h, wd) or x2.dtype != x.dtype:
+            raise RuntimeError("nervecl.conv2d_fwd: x2 must match x in batch, size and dtype")
+        p.x2, p.ldx2, p.Cin2, p.x2_center = x2p, ldx2, c2, int(x2_center)
     _lib.check(_lib.load().nervecl_conv2d_fwd(C.byref(p), _stream()), "conv2d_fwd")
 
 

@@ -90,7 +90,7 @@ int nervecl_pack_conv_weight(const float* w_oihw, void* dst, int dtype, int O, i
  * efficient_layers.py:50-56 (pointwise), :94-100 (upsampler conv), :196-197 (7x7) -- and, called
  * on dY with transpose_flip weights, ATen's convolution_backward input gradient.
  *
- *   v = sum_taps sum_ci x[p+tap, ci] * w[tap, co, ci]
+ *   v = sum_taps sum_ci x[p+tap, ci] * w[tap, co, ci]   (+ sum over the x2 channels when x2 != NULL)
  *   v += bias[co]                      (bias != NULL)
  *   v  = max(v, 0)                     (relu)
  *   v *= alpha
@@ -118,6 +118,12 @@ typedef struct nervecl_conv_params {
   const void* mask; int64_t ldmask;
   const void* mask_sub; int64_t ldmask_sub;
   void* out;       int64_t ldo;
+  /* ABI v2: optional second input, a virtual channel concat [x | x2] (no copy).  Its weights are columns
+   * [ceil(Cin/64)*64, +Cin2) of the packed weight rows.  With x2_center != 0 only the centre tap of those
+   * columns is used (a fused 1x1 branch).  Row-streaming tcgen05 engine only (3x3, bf16). */
+  const void* x2;  int64_t ldx2;
+  int32_t Cin2;
+  int32_t x2_center;
 } nervecl_conv_params;
 
 int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t stream);

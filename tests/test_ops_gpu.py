@@ -510,3 +510,34 @@ def test_conv3x3_wgrad_grouped_dense_block(shape):
         F.conv2d(buf[:, :cin], wt, b, 1, 1).backward(dy[:, 32 * i:32 * i + 32])
         assert relerr(dws[i], 0.5 * wt.grad) <= 1e-3, i
         assert relerr(dbs[i], 0.5 * b.grad) <= 1e-3, i
+
+
+@pytest.mark.parametrize("shape", [(1, 20, 130, 96, 32, 64), (2, 9, 200, 160, 64, 64), (1, 40, 128, 32, 32, 64),
+                                   (1, 12, 136, 64, 48, 32)])
+@pytest.mark.parametrize("center", [True, False])
+def test_conv_rows_second_input(shape, center):
+    """Virtual channel concat [x | x2] (row-streaming tcgen05 engine): 3x3 over x plus x2 through all taps or
+    through the centre tap only, with the ReLU-mask epilogue (prefetched mask path when Cout <= 32)."""
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout, cin2 = shape
+    g = torch.Generator().manual_seed(sum(shape) + 41)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    x2 = bf(torch.randn(n, cin2, h, w, generator=g))
+    w1 = bf(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    w2 = bf(torch.randn(cout, cin2, 3, 3, generator=g) / (cin2 * 9) ** 0.5)
+    if center:
+        keep = torch.zeros(3, 3)
+        keep[1, 1] = 1
+        w2 = w2 * keep
+    act = bf(torch.randn(n, cout, h, w, generator=g))
+    ref = (F.conv2d(x, w1, None, 1, 1) + F.conv2d(x2, w2, None, 1, 1)) * 0.5 * (act > 0)
+    cpad = (cin + 63) // 64 * 64
+    comb = torch.zeros(cout, cpad + cin2, 3, 3)
+    comb[:, :cin] = w1
+    comb[:, cpad:] = w2
+    out = torch.full((n, h, w, cout + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    nv().conv2d_fwd(nhwc(x, torch.bfloat16, pad_to=cin + 8), pack(comb, torch.bfloat16), None, None,
+                    nhwc(act, torch.bfloat16), None, out[..., :cout], cout, False, False, 0, 0, 0.5, ops.CONV_TC,
+                    nhwc(x2, torch.bfloat16), center)
+    assert relerr(nchw(out[..., :cout]), ref) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0

@@ -108,3 +108,52 @@ def test_module_contract():
         m(torch.rand(1, 5, 3, 16, 16, device="cuda"))       # wrong T, as in the reference
     with pytest.raises(RuntimeError):
         m(torch.rand(1, 3, 3, 16, 16))                       # CPU input: no fallback
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 2, 1, 2, 40, 160), (4, 64, 1, 2, 1, 24, 136)])
+def test_bf16_tcgen05_engine_gradients(cfg):
+    """The bf16 path at a size where every fast kernel engages (row-streaming tcgen05 convs, fused dense-block
+    backward, grouped weight gradient, tiled correlation / depthwise kernels: W >= 64).
+
+    * against the SAME bf16 storage run through the layer-by-layer CUDA-core convolution engine (fp32
+      accumulation, reference op order): the two differ only in summation order / fusion (the fused dense-block
+      backward rounds each gradient slice once instead of after every layer), so every parameter gradient
+      agrees to bf16 noise (relative L2 <= 6e-2);
+    * against the fp32 path (itself pinned to the oracle above): no further from it than the reference-order
+      bf16 run is (x1.1 + 1e-3), within bf16 storage noise overall (<= 0.25), output within 40 dB PSNR."""
+    from nerve_cl_b200 import ops
+    from nerve_cl_b200.models import SuperResolutionNet
+    scale, feats, blocks, tw, b, h, w = cfg
+    torch.manual_seed(11)
+    model = SuperResolutionNet(scale_factor=scale, num_features=feats, num_residual_blocks=blocks,
+                               temporal_window=tw).cuda().train()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    t = model.num_frames
+    g = torch.Generator().manual_seed(12)
+    base = torch.rand(b, 3, h, w, generator=g)
+    x = torch.stack([torch.roll(base, (i - t // 2, 2 * (i - t // 2)), (2, 3)) for i in range(t)], 1).cuda()
+    tgt = torch.rand(b, 3, h * scale, w * scale, generator=g).cuda()
+    grads, outs = {}, {}
+    for tag, dt, eng in (("fp32", torch.float32, ops.CONV_AUTO), ("tc", torch.bfloat16, ops.CONV_AUTO),
+                         ("simt", torch.bfloat16, ops.CONV_SIMT)):
+        model.load_state_dict(sd)
+        model.zero_grad()
+        model.compute_dtype, model.conv_engine = dt, eng
+        model._plans.clear()
+        out = model(x)
+        torch.nn.functional.mse_loss(out, tgt).backward()
+        grads[tag] = {n: p.grad.detach().double().clone() for n, p in model.named_parameters()}
+        outs[tag] = out.detach()
+    assert psnr(outs["tc"], outs["fp32"]) >= 40.0
+    checked = 0
+    for n, ref in grads["fp32"].items():
+        denom = float(ref.norm())
+        if denom < 1e-10:
+            continue
+        checked += 1
+        e_simt = float((grads["tc"][n] - grads["simt"][n]).norm()) / float(grads["simt"][n].norm())
+        e_fp32 = float((grads["tc"][n] - ref).norm()) / denom
+        e_ref = float((grads["simt"][n] - ref).norm()) / denom
+        assert e_simt <= 6e-2, (n, e_simt)
+        assert e_fp32 <= 0.25 and e_fp32 <= 1.1 * e_ref + 1e-3, (n, e_fp32, e_ref)
+    assert checked > 100
