@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Continual training (EWC or experience replay) on the B200 path -- the reference's
+`experiments/train_continual.py` flow (4 content-type tasks, Adam 1e-4, 5 epochs per task, EWC lambda 5000,
+online consolidation) with torchrun data parallelism.
+
+Deviation from the reference launcher, documented in SURVEY.md section 3.3: the reference registers a task by
+feeding raw 4-D batches to `EnhancementEngine`, which raises at the end of task 0; here the Fisher pass gets the
+same (B,T,C,H,W) windows the training loop uses and the bare SR network, i.e. what the reference intended.
+
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 experiments/train_continual.py --strategy ewc
+"""
+import argparse
+import random
+from pathlib import Path
+
+import _common  # noqa: F401
+import torch
+
+OFFSETS = {"sports": 0.2, "animation": -0.2, "movie": 0.0, "news": 0.1}
+
+
+def create_task_data(content_type: str, num_samples: int, size: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    off = OFFSETS.get(content_type, 0.0)
+    return (torch.randn(num_samples, 3, size, size, generator=g) + off,
+            torch.randn(num_samples, 3, 2 * size, 2 * size, generator=g) + off)
+
+
+class WindowLoader:
+    """Iterable of (lr_window[B,3,C,H,W], hr[B,C,2H,2W]) device batches over this rank's shard."""
+
+    def __init__(self, lr, hr, idx, batch, device, seed):
+        self.lr, self.hr, self.idx, self.batch, self.device, self.seed = lr, hr, list(idx), batch, device, seed
+        self.epoch = 0
+
+    def __len__(self):
+        return max(len(self.idx) // self.batch, 1)
+
+    def __iter__(self):
+        order = self.idx[:]
+        random.Random(self.seed + self.epoch).shuffle(order)
+        self.epoch += 1
+        for s in range(len(self)):
+            sel = order[s * self.batch:(s + 1) * self.batch]
+            lr = self.lr[sel].to(self.device, non_blocking=True)
+            yield lr.unsqueeze(1).expand(-1, 3, -1, -1, -1), self.hr[sel].to(self.device, non_blocking=True)
+
+
+class ReplayBuffer:
+    """Per-rank reservoir of CPU samples (the reference's EpisodicMemory is a host-side list; one per rank)."""
+
+    def __init__(self, capacity: int, seed: int):
+        self.capacity, self.items, self.seen, self.rng = capacity, [], 0, random.Random(seed)
+
+    def __len__(self):
+        return len(self.items)
+
+    def store(self, lr, hr):
+        self.seen += 1
+        if len(self.items) < self.capacity:
+            self.items.append((lr, hr))
+        else:
+            j = self.rng.randrange(self.seen)
+            if j < self.capacity:
+                self.items[j] = (lr, hr)
+
+    def sample(self, n, device):
+        pick = self.rng.sample(self.items, min(n, len(self.items)))
+        return torch.stack([p[0] for p in pick]).to(device), torch.stack([p[1] for p in pick]).to(device)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--strategy", choices=["ewc", "replay"], default="ewc")
+    ap.add_argument("--memory-size", type=int, default=200)
+    ap.add_argument("--ewc-lambda", type=float, default=5000.0)
+    ap.add_argument("--samples", type=int, default=200)
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--epochs", type=int, default=5)
+    ap.add_argument("--batch-size", type=int, default=16)
+    ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    args = ap.parse_args()
+
+    from nerve_cl_b200 import distributed as nd
+    from nerve_cl_b200.continual import EWC
+    from nerve_cl_b200.models import SuperResolutionNet
+    from nerve_cl_b200.optim import FlatAdamW
+    rank, local_rank, world, device = _common.setup_distributed()
+    torch.manual_seed(0)
+    model = SuperResolutionNet(scale_factor=2).to(device)          # the engine's SR branch (64 feat, 8 blocks)
+    model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    nd.data_parallel(model)
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=0.0)              # Adam(lr=1e-4)
+    tasks = [(ct, create_task_data(ct, args.samples, args.size, 100 + i)) for i, ct in enumerate(OFFSETS)]
+    ewc = EWC(model, ewc_lambda=args.ewc_lambda) if args.strategy == "ewc" else None
+    if ewc is not None and world > 1:
+        ewc.process_group = torch.distributed.group.WORLD      # Fisher: local sum of g^2, then one all-reduce
+    memory = ReplayBuffer(args.memory_size, 7 + rank) if args.strategy == "replay" else None
+
+    for task_id, (name, (lr, hr)) in enumerate(tasks):
+        _common.log(rank, f"\n=== Training on Task {task_id}: {name} ===")
+        loader = WindowLoader(lr, hr, _common.shard(len(lr), rank, world), args.batch_size, device, task_id)
+        for epoch in range(args.epochs):
+            model.train()
+            total = torch.zeros((), device=device)
+            steps = 0
+            for lr_w, hr_b in loader:
+                if memory is not None and len(memory) > 0:
+                    r_lr, r_hr = memory.sample(8, device)
+                    lr_w = torch.cat([lr_w, r_lr.unsqueeze(1).expand(-1, 3, -1, -1, -1)])
+                    hr_b = torch.cat([hr_b, r_hr])
+                opt.zero_grad()
+                loss = torch.nn.functional.mse_loss(model(lr_w), hr_b)
+                if ewc is not None:
+                    loss = loss + ewc.penalty()          # Python 0.0 before the first task, as in the reference
+                loss.backward()
+                opt.step()
+                total += loss.detach()
+                steps += 1
+                if memory is not None:
+                    break                                 # the reference's replay loop takes one step per epoch
+            _common.log(rank, f"  Epoch {epoch + 1}: Loss={float(total) / max(steps, 1):.4f}")
+        if ewc is not None:
+            ewc.register_task(task_id, loader)            # local sum of g^2 + ONE all-reduce of the flat Fisher
+            _common.log(rank, f"  Registered task {task_id} for EWC protection")
+        if memory is not None:
+            for i in list(_common.shard(len(lr), rank, world))[:50]:
+                memory.store(lr[i], hr[i])
+            _common.log(rank, f"  Memory size: {len(memory)}")
+    if rank == 0:
+        Path("checkpoints").mkdir(exist_ok=True)
+        torch.save(model.state_dict(), "checkpoints/continual_model.pt")
+    _common.log(rank, "\nTraining complete!")
+
+
+if __name__ == "__main__":
+    main()

@@ -15,4 +15,11 @@ echo "ncu list rc=$?"
 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-conv_tc}" -s ${NCU_SKIP:-400} -c ${NCU_COUNT:-6} -f -o gpurun_out/${tag}_prof $CMD > gpurun_out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
+if [ -n "${NCU_STEP_SKIP:-}" ]; then
+  # light counters for every launch of one whole step (no source, few sections)
+  $CMD > gpurun_out/${tag}_plain3.log 2>&1 &&
+  ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --clock-control none \
+      -s ${NCU_STEP_SKIP} -c ${NCU_STEP_COUNT:-400} -f -o gpurun_out/${tag}_step $CMD > gpurun_out/${tag}_ncu_step.log 2>&1
+  echo "ncu step rc=$?"
+fi
 ls -la gpurun_out | tail -20
