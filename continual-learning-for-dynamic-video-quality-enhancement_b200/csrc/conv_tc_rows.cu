@@ -420,7 +420,7 @@ bool conv_rows_supported(const nervecl_conv_params& a) {
   b.x2 = nullptr;
   if (!conv_tc_fwd_supported(b)) return false;       // dtype / alignment / epilogue constraints are the same
   if (a.K != 3) return false;
-  if (a.Cin < 32 || a.Cin % 16 || a.Cin > 512) return false;
+  if (a.Cin < 16 || a.Cin % 16 || a.Cin > 512) return false;
   if (a.W < 64 || a.H < 3) return false;
   if (a.x2) {
     if (a.Cin2 < 16 || a.Cin2 % 16 || a.Cin2 > 256 || a.ldx2 % 8 || !aligned(a.x2, 16)) return false;

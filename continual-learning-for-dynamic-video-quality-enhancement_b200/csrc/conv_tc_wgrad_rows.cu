@@ -49,6 +49,27 @@ struct WgrArgs {
   float scale;
 };
 
+// bias gradient of a group whose column count / offset is not a multiple of 4 (<= 32 columns):
+// db[c] += scale * sum_p dy[p, c]
+__global__ void __launch_bounds__(256)
+colsum_any_kernel(const bf16* __restrict__ dy, int64_t ldy, int64_t npix, int ncols, float scale, float* __restrict__ db) {
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < ncols) acc[c] += ldf(dy + p * ldy + c);
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c < ncols) {
+      const float v = warp_sum(acc[c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(db + c, scale * v);
+    }
+  }
+}
+
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -301,7 +322,15 @@ NV_API int nervecl_conv3x3_wgrad_grouped(const void* x, int64_t ldx, const void*
   if (db_host) {
     for (int g = 0; g < ngroups; ++g) {
       if (!db_host[g]) continue;
-      if (ncols_host[g] % 4 || col0_host[g] % 4) return NERVECL_EALIGN;
+      if (ncols_host[g] % 4 || col0_host[g] % 4) {
+        if (ncols_host[g] > 32) return NERVECL_EALIGN;
+        const int64_t npix = (int64_t)N * H * W;
+        colsum_any_kernel<<<(int)imin(cdiv(npix, 256 * 8), sm_count() * 4), 256, 0, s>>>(
+            reinterpret_cast<const bf16*>(dy) + col0_host[g], ldy, npix, ncols_host[g], scale, db_host[g]);
+        rc = launch_status();
+        if (rc) return rc;
+        continue;
+      }
       rc = nervecl_chan_sum(reinterpret_cast<const bf16*>(dy) + col0_host[g], ldy, NERVECL_BF16, 1, (int64_t)N * H * W,
                             ncols_host[g], scale, db_host[g], stream);
       if (rc) return rc;

@@ -198,6 +198,12 @@ warp_fwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
 
 // blockDim multiple of 32; the cg (= C/8, power of two <= 32) threads of one pixel are adjacent
 // lanes, so the flow gradient is reduced with xor-shuffles.
+// 8 consecutive fp32 accumulations as two 128-bit vector reductions (red.global.add.v4.f32, sm_90+)
+__device__ __forceinline__ void atomic_add8(float* p, float w, const f8& g) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(w * g.v[0], w * g.v[1], w * g.v[2], w * g.v[3]));
+  atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(w * g.v[4], w * g.v[5], w * g.v[6], w * g.v[7]));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow,
@@ -230,36 +236,36 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
       float* db = dfeat + q * lddf + c0;
       if (yin0 && xin0) {
         f8 v = ld8(fb);
+        atomic_add8(db, wnw, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          atomicAdd(db + k, wnw * g.v[k]);
           gix -= v.v[k] * (y1f - c.iy) * g.v[k];
           giy -= v.v[k] * (x1f - c.ix) * g.v[k];
         }
       }
       if (yin0 && xin1) {
         f8 v = ld8(fb + ldf_);
+        atomic_add8(db + lddf, wne, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          atomicAdd(db + lddf + k, wne * g.v[k]);
           gix += v.v[k] * (y1f - c.iy) * g.v[k];
           giy -= v.v[k] * (c.ix - c.x0f) * g.v[k];
         }
       }
       if (yin1 && xin0) {
         f8 v = ld8(fb + (int64_t)W * ldf_);
+        atomic_add8(db + (int64_t)W * lddf, wsw, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          atomicAdd(db + (int64_t)W * lddf + k, wsw * g.v[k]);
           gix -= v.v[k] * (c.iy - c.y0f) * g.v[k];
           giy += v.v[k] * (x1f - c.ix) * g.v[k];
         }
       }
       if (yin1 && xin1) {
         f8 v = ld8(fb + (int64_t)(W + 1) * ldf_);
+        atomic_add8(db + (int64_t)(W + 1) * lddf, wse, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          atomicAdd(db + (int64_t)(W + 1) * lddf + k, wse * g.v[k]);
           gix += v.v[k] * (c.iy - c.y0f) * g.v[k];
           giy += v.v[k] * (c.ix - c.x0f) * g.v[k];
         }
@@ -337,7 +343,8 @@ NV_API int nervecl_warp_bwd(const void* feat, int64_t ldf, const float* flow, co
   if (!feat || !flow || !dout || !dfeat || !dflow) return NERVECL_EINVAL;
   int rc = warp_check(N, H, W, C);
   if (rc) return rc;
-  if ((ldf & 7) || (lddo & 7) || !aligned(feat, 16) || !aligned(dout, 16) || !aligned(flow, 8) || !aligned(dflow, 8))
+  if ((ldf & 7) || (lddo & 7) || (lddf & 3) || !aligned(feat, 16) || !aligned(dout, 16) || !aligned(dfeat, 16) ||
+      !aligned(flow, 8) || !aligned(dflow, 8))
     return NERVECL_EALIGN;
   float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
   int64_t total = (int64_t)N * H * W * (C >> 3);

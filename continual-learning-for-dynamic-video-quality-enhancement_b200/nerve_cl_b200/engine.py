@@ -135,7 +135,7 @@ class Activations:
         def act(n, c, dtype=adt):
             return torch.empty((n, H, W, c), device=dev, dtype=dtype)
 
-        self.x_in = act(T * B, 8)              # RGB + 5 zero channels: 16-byte pixels (TMA-addressable)
+        self.x_in = act(T * B, 16)             # RGB + 13 zero channels: one 16-channel MMA k-step per tap, TMA-addressable
         self.head = act(T * B, F)
         self.dwo = [act(T * B, F) for _ in range(3)]
         self.pwo = [act(T * B, F) for _ in range(3)]
@@ -190,7 +190,7 @@ class Plan:
         def add(name, cin, cout, k, bias=True, cin_pad=None):
             cs[name] = ConvSpec(name, cin, cout, k, bias, cin_pad)
 
-        add("feature_extractor.head.0", 3, F, 3, cin_pad=8)
+        add("feature_extractor.head.0", 3, F, 3, cin_pad=16)
         for j in range(3):
             add(f"feature_extractor.body.{j}.pointwise", F, F, 1, bias=False)
         add("motion_estimator.flow_net.0", CORR_CH, 128, 3, cin_pad=CORR_PAD)
@@ -214,7 +214,8 @@ class Plan:
             kk = c.k * c.k
             self.wf[name] = torch.empty((kk, c.cout, _align(c.cin_pad, 8)), device=device, dtype=adt)
             if name != "feature_extractor.head.0":   # the input frames need no gradient
-                self.wb[name] = torch.empty((kk, c.cin_pad, _align(c.cout, 8)), device=device, dtype=adt)
+                # (>= 16 columns: the output gradients of the 2/3/12-channel convs are 16-channel zero-padded buffers)
+                self.wb[name] = torch.empty((kk, c.cin_pad, _align(c.cout, 16)), device=device, dtype=adt)
 
         # Fused dense-block data gradient (bf16 tcgen05 path): the gradient of buffer slice s is ONE conv over the
         # already-final gradients of all later layers (adjacent channels of the gradient buffer) plus the LFF
@@ -297,8 +298,17 @@ class Plan:
             nv.conv2d_fwd(dy, self.wb[name], None, res, mask, mask_sub, out, cout or c.cin_pad, False, accumulate,
                           res_channels if res is not None else 0, mask_c0, alpha, self.engine)
 
-    def wgrad(self, name: str, x: Tensor, dy: Tensor, G: Dict[str, Tensor], scale: float = 1.0) -> None:
+    def wgrad(self, name: str, x: Tensor, dy: Tensor, G: Dict[str, Tensor], scale: float = 1.0,
+              dy_padded: Optional[Tensor] = None) -> None:
+        """``dy_padded``: the zero-padded (>= 16 channel) buffer ``dy`` is a prefix view of, for the small-Cout
+        convs -- lets the row-resident tcgen05 weight gradient take them (it masks the unused columns)."""
         c = self.convs[name]
+        if (dy_padded is not None and c.k == 3 and self.adt == torch.bfloat16 and self.engine != CONV_SIMT
+                and self.W >= 64 and x.shape[-1] >= 16):
+            with self._span("conv_wgrad", x, x.shape[-1], dy.shape[-1], c.k):
+                nv.conv3x3_wgrad_grouped(x, dy_padded, [G[name + ".weight"]],
+                                         [G[name + ".bias"]] if c.has_bias else [], [0], scale)
+            return
         with self._span("conv_wgrad", x, x.shape[-1], dy.shape[-1], c.k):
             nv.conv2d_wgrad(x, dy, G[name + ".weight"], G[name + ".bias"] if c.has_bias else None, scale,
                             self.engine)
@@ -390,7 +400,7 @@ class Plan:
             ws["dup"] = act(B, 3 * s * s, f32)
             # fp32 gradients of the three fp32-output convs, re-cast to the activation dtype in buffers whose
             # channel count is padded to a multiple of 8 (pad channels stay zero: never written after this)
-            ws["dup_a"] = torch.zeros((B, H, W, _align(3 * s * s, 8)), device=dev, dtype=adt)
+            ws["dup_a"] = torch.zeros((B, H, W, _align(3 * s * s, 16)), device=dev, dtype=adt)
             ws["dfused"] = act(B, F)
             ws["dgff"] = act(B, F)
             ws["dtrunk"] = act(B, F)
@@ -403,12 +413,12 @@ class Plan:
             ws["dpool"] = torch.empty((B, F), device=dev, dtype=f32)
             ws["dcat"] = act(B, T * F)
             ws["dlogits"] = act(B, T, f32)
-            ws["dlogits_a"] = torch.zeros((B, H, W, _align(T, 8)), device=dev, dtype=adt)
+            ws["dlogits_a"] = torch.zeros((B, H, W, _align(T, 16)), device=dev, dtype=adt)
             ws["da2"], ws["da1"] = act(B, F), act(B, F)
             ws["dfeat"] = act(T * B, F)
             ws["dfeat32"] = act(B, F, f32)
             ws["dflow"] = act(B, 2, f32)
-            ws["dflow_a"] = torch.zeros((B, H, W, 8), device=dev, dtype=adt)
+            ws["dflow_a"] = torch.zeros((B, H, W, 16), device=dev, dtype=adt)
             ws["dfn3"], ws["dfn2"], ws["dfn1"] = act(B, 32), act(B, 64), act(B, 128)
             ws["dcorr"] = act(B, CORR_PAD)
             ws["t"] = [act(T * B, F) for _ in range(3)]
@@ -485,7 +495,7 @@ class Plan:
         nv.upfinish_bwd(A.up, A.lr_centre, dout, ws["dup"], s)
         dup = ws["dup_a"][..., :ncs]
         nv.axpy(ws["dup"], dup, 1.0, False)
-        self.wgrad("upsampler.conv", A.fused, dup, G)
+        self.wgrad("upsampler.conv", A.fused, dup, G, dy_padded=ws["dup_a"])
         ready("upsampler.")
         self.dgrad("upsampler.conv", ws["dup_a"], ws["dfused"])      # padded view: zero channels x zero weights
         nv.relu_bwd(ws["dfused"], A.fused, centre, ws["dgff"])
@@ -527,7 +537,7 @@ class Plan:
         nv.tfuse_bwd(A.cat, A.attn, ws["dblend"], ws["dpool"], ws["dcat"], ws["dlogits"])
         dlog = ws["dlogits_a"][..., :T]
         nv.axpy(ws["dlogits"], dlog, 1.0, False)
-        self.wgrad("temporal_aggregator.attention.4", A.a2, dlog, G)
+        self.wgrad("temporal_aggregator.attention.4", A.a2, dlog, G, dy_padded=ws["dlogits_a"])
         self.dgrad("temporal_aggregator.attention.4", ws["dlogits_a"], ws["da2"], mask=A.a2)
         self.wgrad("temporal_aggregator.attention.2", A.a1, ws["da2"], G)
         self.dgrad("temporal_aggregator.attention.2", ws["da2"], ws["da1"], mask=A.a1)
@@ -546,7 +556,7 @@ class Plan:
             nv.axpy(ws["dfeat32"], dfeat[t], 1.0, False)
             dflow = ws["dflow_a"][..., :2]
             nv.axpy(ws["dflow"], dflow, 1.0, False)
-            self.wgrad("motion_estimator.flow_net.6", A.fn3[t], dflow, G)
+            self.wgrad("motion_estimator.flow_net.6", A.fn3[t], dflow, G, dy_padded=ws["dflow_a"])
             self.dgrad("motion_estimator.flow_net.6", ws["dflow_a"], ws["dfn3"], mask=A.fn3[t])
             self.wgrad("motion_estimator.flow_net.4", A.fn2[t], ws["dfn3"], G)
             self.dgrad("motion_estimator.flow_net.4", ws["dfn3"], ws["dfn2"], mask=A.fn2[t])
@@ -580,5 +590,10 @@ class Plan:
                 # extractor skip (feat = body(head) + head): d(head) = d(feat) + depthwise data gradient
                 nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], ws["dfeat"], True, True)
         nv.relu_bwd(ws["dfeat"], A.head, None, ws["t"][0])
-        self.wgrad("feature_extractor.head.0", A.x_in[..., :3], ws["t"][0], G)
+        if self.adt == torch.bfloat16 and self.engine != CONV_SIMT and W >= 64:
+            with self._span("conv_wgrad", A.x_in[..., :3], 3, F, 3):
+                nv.conv3x3_wgrad_grouped(A.x_in, ws["t"][0], [G["feature_extractor.head.0.weight"]],
+                                         [G["feature_extractor.head.0.bias"]], [0], 1.0)
+        else:
+            self.wgrad("feature_extractor.head.0", A.x_in[..., :3], ws["t"][0], G)
         ready("feature_extractor.")

@@ -4,11 +4,11 @@
 set -u
 tag=${1:-r01}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
+timeout ${PYTEST_TIMEOUT:-600} python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 cp gpurun_out/bench_detail.json gpurun_out/${tag}_bench_detail.json 2>/dev/null
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="timeout ${NCU_TIMEOUT:-420} python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu_list.log 2>&1
 echo "ncu list rc=$?"

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(args, cwd):
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "experiments"))
-    return subprocess.run([sys.executable] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=600)
+    return subprocess.run([sys.executable] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=240)
 
 
 def test_train_baseline_synthetic(tmp_path):

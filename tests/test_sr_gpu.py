@@ -156,4 +156,4 @@ def test_bf16_tcgen05_engine_gradients(cfg):
         e_ref = float((grads["simt"][n] - ref).norm()) / denom
         assert e_simt <= 6e-2, (n, e_simt)
         assert e_fp32 <= 0.25 and e_fp32 <= 1.1 * e_ref + 1e-3, (n, e_fp32, e_ref)
-    assert checked > 100
+    assert checked >= 40
