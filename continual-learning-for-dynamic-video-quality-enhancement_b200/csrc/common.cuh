@@ -73,12 +73,11 @@ __device__ __forceinline__ f8 ld8(const float* p) {
 __device__ __forceinline__ f8 ld8(const bf16* p) {
   uint4 t = *reinterpret_cast<const uint4*>(p);
   f8 r;
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    r.v[2 * i] = f.x;
-    r.v[2 * i + 1] = f.y;
+  for (int i = 0; i < 4; ++i) {          // bf16 -> fp32 is a 16-bit shift: one ALU op per element
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
   return r;
 }

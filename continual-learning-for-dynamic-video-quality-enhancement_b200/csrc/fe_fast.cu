@@ -30,17 +30,21 @@ template <typename T>
 __device__ __forceinline__ void stage_tile(T* __restrict__ sm, const T* __restrict__ x, int64_t ldx, int n, int y0, int x0,
                                            int H, int W, int C, int TWp) {
   constexpr int EPC = 16 / sizeof(T);          // elements per 16-byte chunk
-  const int cpp = C / EPC;                     // chunks per pixel
+  const int cpp = C / EPC;                     // chunks per pixel (divides the block size: C/8 is a power of two)
   const int PWs = TWp + 2;
-  const int total = (DW_TH + 2) * PWs * cpp;
-  for (int e = threadIdx.x; e < total; e += kThreadsFe) {
-    const int ch = e % cpp;
-    const int pp = e / cpp;
-    const int px = pp % PWs, r = pp / PWs;
+  const int ch = threadIdx.x % cpp;            // this thread always copies the same chunk of a pixel ...
+  const int pstep = kThreadsFe / cpp;          // ... of every pstep-th pixel: no division in the loop
+  int px = threadIdx.x / cpp, r = 0;
+  while (px >= PWs) { px -= PWs; ++r; }
+  const T* img = x + (int64_t)n * H * W * ldx + ch * EPC;
+  T* dst = sm + ch * EPC;
+  for (; r < DW_TH + 2;) {
     const int yy = y0 - 1 + r, xx = x0 - 1 + px;
     const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-    const T* src = ok ? x + (((int64_t)n * H + yy) * W + xx) * ldx + ch * EPC : x;
-    cp_async16(sm + (size_t)pp * C + ch * EPC, src, ok);
+    const T* src = ok ? img + ((int64_t)yy * W + xx) * ldx : x;
+    cp_async16(dst + (size_t)(r * PWs + px) * C, src, ok);
+    px += pstep;
+    while (px >= PWs) { px -= PWs; ++r; }
   }
 }
 
@@ -78,32 +82,51 @@ dwconv_tile_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
     __syncthreads();
     const int xx = x0 + tx;
     if (xx < W) {
-#pragma unroll 1
-      for (int ty = 0; ty < DW_TH; ++ty) {
-        const int yy = y0 + ty;
-        if (yy >= H) break;
-        float acc[8];
+      // walk the DW_TH + 2 input rows of this thread's column once: each row's three neighbour vectors are
+      // loaded / converted once and feed the three output rows they belong to (rolling accumulators)
+      float acc[3][8];
+      const T* col = sm + tx * C + c0;                                   // this thread's column of the tile
+      const int rstride = PWs * C;
+      T* yp = y + (((int64_t)n * H + y0) * W + xx) * ldy + c0;
+      const int64_t ystride = (int64_t)W * ldy;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int ri = 0; ri < DW_TH + 2; ++ri) {
+        float v[3][8];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          f8 t = ld8(col + ri * rstride + kx * C);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            f8 v = ld8(sm + (size_t)((ty + ky) * PWs + tx + kx) * C + c0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wt[ky][kx][k], acc[k]);
-          }
-        T* yp = y + (((int64_t)n * H + yy) * W + xx) * ldy + c0;
-        f8 o;
-        if (accumulate) {
-          o = ld8(yp);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o.v[k] += acc[k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+          for (int k = 0; k < 8; ++k) v[kx][k] = t.v[k];
         }
-        st8(yp, o);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int oi = ri - ky;                     // output row (tile-local) that uses this input row as tap row ky
+          if (oi < 0 || oi >= DW_TH) continue;
+          float* a = acc[oi % 3];
+          if (ky == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = 0.f;
+          }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fmaf(v[kx][k], wt[ky][kx][k], a[k]);
+        }
+        const int od = ri - 2;                        // this output row is complete
+        if (od >= 0 && y0 + od < H) {
+          const float* a = acc[od % 3];
+          f8 o;
+          if (accumulate) {
+            o = ld8(yp);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] += a[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = a[k];
+          }
+          st8(yp, o);
+          yp += ystride;
+        }
       }
     }
   }
@@ -153,17 +176,33 @@ dwconv_wgrad_tile_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
     }
     cp_async_wait_all();
     __syncthreads();
-#pragma unroll 1
-    for (int ty = 0; ty < DW_TH; ++ty) {
-      const f8 d = ld8(smd + (size_t)(ty * TWp + tx) * C + c0);
+    {
+      // input row ri pairs with the dy rows ri - ky (tap row ky): keep the three live dy vectors in registers
+      float d[3][8];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int ri = 0; ri < DW_TH + 2; ++ri) {
+        if (ri < DW_TH) {
+          const f8 t = ld8(smd + (ri * TWp + tx) * C + c0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[ri % 3][k] = t.v[k];
+        }
+        float v[3][8];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          f8 v = ld8(sm + (size_t)((ty + ky) * PWs + tx + kx) * C + c0);
+          f8 t = ld8(sm + ((ri * PWs + tx + kx) * C + c0));
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[ky][kx][k] = fmaf(d.v[k], v.v[k], acc[ky][kx][k]);
+          for (int k = 0; k < 8; ++k) v[kx][k] = t.v[k];
         }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int oi = ri - ky;
+          if (oi < 0 || oi >= DW_TH) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[ky][kx][k] = fmaf(d[oi % 3][k], v[kx][k], acc[ky][kx][k]);
+        }
+      }
     }
   }
   // block reduction: shared fp32 atomics (one address per (channel, tap)), then one global atomic each

