@@ -38,7 +38,7 @@ constexpr int kMaxClasses = 12;
 struct WgGroup { int col0, ncols, cin; float* dw; };
 
 struct WgrArgs {
-  int N, H, W, strips;
+  int N, H, W, Cx, strips;
   int ngroups;
   WgGroup grp[kMaxGroups];
   int nclasses;
@@ -122,7 +122,10 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = 2u * (PXB * ROWB) + (uint32_t)nby * YCHUNK;
+      // channel chunks of this M tile that exist (the second one may lie entirely beyond Cx: not loaded; its
+      // accumulator rows are never drained)
+      const int nxc = (mt * 128 + KC < a.Cx) ? 2 : 1;
+      const uint32_t bytes = (uint32_t)nxc * (PXB * ROWB) + (uint32_t)nby * YCHUNK;
       for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
         const int strip = (int)(rt % a.strips);
         const int64_t r = rt / a.strips;
@@ -132,7 +135,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         mbar_expect_tx(&full_bar[stage], bytes);
         uint8_t* sx = smem + (size_t)stage * stage_bytes;
         uint8_t* sy = sx + 2 * XCHUNK;
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < nxc; ++c)
           tma_load_4d(sx + (size_t)c * XCHUNK, &tmap_x, &full_bar[stage], mt * 128 + c * KC, x0 - 1, y + ky - 1, n);
         for (int c = 0; c < nby; ++c)
           tma_load_4d(sy + (size_t)c * YCHUNK, &tmap_dy, &full_bar[stage], col0 + c * KC, x0, y, n);
@@ -233,7 +236,7 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
   if (!enc) return NERVECL_EUNSUPPORTED;
   if (ngroups < 1 || ngroups > kMaxGroups) return NERVECL_EINVAL;
   WgrArgs a;
-  a.N = N; a.H = H; a.W = W; a.strips = (W + BM - 1) / BM;
+  a.N = N; a.H = H; a.W = W; a.Cx = Cx; a.strips = (W + BM - 1) / BM;
   a.ngroups = ngroups;
   a.scale = scale;
   for (int g = 0; g < ngroups; ++g) {

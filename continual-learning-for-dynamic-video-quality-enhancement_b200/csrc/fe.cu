@@ -10,6 +10,8 @@ int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ld
                  int flip, int accumulate, cudaStream_t s);
 int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy, int dtype, float* dw, int N, int H, int W,
                        int C, cudaStream_t s);
+int bn_sums_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
+                 const float* beta, int dtype, int C, int64_t npix, int groups, double* sums, cudaStream_t s);
 int bn_relu_fwd_fast(const void* x, int64_t ldx, const float* stat, const float* gamma, const float* beta, const void* res,
                      int64_t ldres, void* y, int64_t ldy, int dtype, int C, int64_t npix, int groups, cudaStream_t s);
 int bn_bwd_apply_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
@@ -371,6 +373,9 @@ NV_API int nervecl_bn_stats(const void* x, int64_t ldx, int dtype, int C, int64_
                             double* sums, nervecl_stream_t stream) {
   if (!x || !sums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || C > 1024) return NERVECL_EALIGN;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (fe_fast_supported(C, ldx, ldx, x, x))
+    return bn_sums_fast(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, dtype, C, npix, groups, sums, as_stream(stream));
   int lanes = 256 / (C >> 2);
   int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups + 1));
   dim3 grid(chunks, groups);
@@ -409,6 +414,9 @@ NV_API int nervecl_bn_relu_bwd_reduce(const void* x, int64_t ldx, const void* dy
                                       int C, int64_t npix, int groups, double* bsums, nervecl_stream_t stream) {
   if (!x || !dy || !stat || !gamma || !beta || !bsums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (lddy & 3) || C > 1024) return NERVECL_EALIGN;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (fe_fast_supported(C, ldx, lddy, x, dy))
+    return bn_sums_fast(x, ldx, dy, lddy, stat, gamma, beta, dtype, C, npix, groups, bsums, as_stream(stream));
   int lanes = 256 / (C >> 2);
   int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups + 1));
   dim3 grid(chunks, groups);

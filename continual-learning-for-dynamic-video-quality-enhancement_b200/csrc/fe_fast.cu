@@ -311,6 +311,73 @@ bn_bwd_apply_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
   }
 }
 
+// per-(group, channel) sums in float64: sums[g][c][0..1] += (sum a, sum b) where (a, b) = (x, x^2) for the
+// statistics pass and (g, g*xhat) with g = dy * [bn(x) > 0] for the backward reduction.  grid = (chunks, groups);
+// a thread owns 8 channels of every (256/cg)-th pixel; fp32 partials are flushed to fp64 every 32 pixels.
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kThreadsFe)
+bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                    const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, int C,
+                    int64_t npix, double* __restrict__ sums) {
+  const int cg = C >> 3;
+  const int g = threadIdx.x % cg, c0 = g << 3;
+  const int grp = blockIdx.y;
+  const int64_t base = (int64_t)grp * npix;
+  float mean[8], is[8], ga[8], be[8];
+  if (BWD) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      mean[k] = stat[((int64_t)grp * C + c) * 2];
+      is[k] = stat[((int64_t)grp * C + c) * 2 + 1];
+      ga[k] = gamma[c];
+      be[k] = beta[c];
+    }
+  }
+  double sa[8], sb[8];
+  float fa[8], fb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sa[k] = sb[k] = 0.0; fa[k] = fb[k] = 0.f; }
+  int cnt = 0;
+  const int64_t stride = (int64_t)gridDim.x * kThreadsFe / cg;
+  for (int64_t p = ((int64_t)blockIdx.x * kThreadsFe + threadIdx.x) / cg; p < npix; p += stride) {
+    const f8 v = ld8(x + (base + p) * ldx + c0);
+    if (BWD) {
+      const f8 d = ld8(dy + (base + p) * lddy + c0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (v.v[k] - mean[k]) * is[k];
+        const float gk = fmaf(xh, ga[k], be[k]) > 0.f ? d.v[k] : 0.f;
+        fa[k] += gk;
+        fb[k] = fmaf(gk, xh, fb[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        fa[k] += v.v[k];
+        fb[k] = fmaf(v.v[k], v.v[k], fb[k]);
+      }
+    }
+    if (++cnt == 32) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; fa[k] = fb[k] = 0.f; }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; }
+  extern __shared__ double dred[];  // [C][2]
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) dred[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(&dred[(c0 + k) * 2 + 0], sa[k]);
+    atomicAdd(&dred[(c0 + k) * 2 + 1], sb[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(sums + (int64_t)grp * C * 2 + i, dred[i]);
+}
+
 inline bool cg_ok(int C) {
   if (C & 7) return false;
   const int cg = C >> 3;
@@ -360,6 +427,21 @@ int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy,
                                                               tiles_x, tiles_y)
   if (dtype == NERVECL_F32) { NV_DW_LAUNCH(float); } else { NV_DW_LAUNCH(bf16); }
 #undef NV_DW_LAUNCH
+  return launch_status();
+}
+
+int bn_sums_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
+                 const float* beta, int dtype, int C, int64_t npix, int groups, double* sums, cudaStream_t s) {
+  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 16), (kSMs * 6) / groups + 1));
+  dim3 grid(chunks, groups);
+  const size_t smem = (size_t)C * 2 * sizeof(double);
+  if (dy) {
+    NV_DISPATCH_DTYPE(dtype, E, (bn_sums_fast_kernel<E, true><<<grid, kThreadsFe, smem, s>>>(
+                                    (const E*)x, ldx, (const E*)dy, lddy, stat, gamma, beta, C, npix, sums)));
+  } else {
+    NV_DISPATCH_DTYPE(dtype, E, (bn_sums_fast_kernel<E, false><<<grid, kThreadsFe, smem, s>>>(
+                                    (const E*)x, ldx, nullptr, 0, nullptr, nullptr, nullptr, C, npix, sums)));
+  }
   return launch_status();
 }
 

@@ -154,6 +154,60 @@ NV_API int nervecl_pack_conv_weight(const float* w_oihw, void* dst, int dtype, i
   return launch_status();
 }
 
+// Batched form: up to kPackBatch weights per launch (descriptor table in the kernel parameters), block
+// (blockIdx.y = entry).  Replaces ~130 tiny launches per training step by 3-4.
+constexpr int kPackBatch = 48;
+struct PackEntry { const float* w; void* dst; int O, I, KK, rows, cols_pad, flip; };
+struct PackTable { PackEntry e[kPackBatch]; };
+
+template <typename T>
+__global__ void pack_weight_batched_kernel(const __grid_constant__ PackTable tab) {
+  const PackEntry& q = tab.e[blockIdx.y];
+  const int nrows = q.flip ? q.I : q.O, cols = q.flip ? q.O : q.I;
+  const int64_t total = (int64_t)q.KK * q.rows * q.cols_pad;
+  T* dst = reinterpret_cast<T*>(q.dst);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % q.cols_pad);
+    const int64_t r2 = i / q.cols_pad;
+    const int r = (int)(r2 % q.rows), tap = (int)(r2 / q.rows);
+    float v = 0.f;
+    if (c < cols && r < nrows)
+      v = q.flip ? __ldg(q.w + ((int64_t)c * q.I + r) * q.KK + (q.KK - 1 - tap)) : __ldg(q.w + ((int64_t)r * q.I + c) * q.KK + tap);
+    stf(dst + i, v);
+  }
+}
+
+NV_API int nervecl_pack_conv_weights_batched(int n, const float* const* w_host, void* const* dst_host, const int32_t* O_host,
+                                             const int32_t* I_host, const int32_t* K_host, const int32_t* rows_pad_host,
+                                             const int32_t* cols_pad_host, const int32_t* flip_host, int dtype,
+                                             nervecl_stream_t stream) {
+  if (n < 0 || (n && (!w_host || !dst_host || !O_host || !I_host || !K_host || !rows_pad_host || !cols_pad_host || !flip_host)))
+    return NERVECL_EINVAL;
+  if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  for (int base = 0; base < n; base += kPackBatch) {
+    const int m = (int)imin(kPackBatch, n - base);
+    PackTable tab;
+    int64_t biggest = 0;
+    for (int j = 0; j < m; ++j) {
+      const int i = base + j;
+      const int nrows = flip_host[i] ? I_host[i] : O_host[i], cols = flip_host[i] ? O_host[i] : I_host[i];
+      if (!w_host[i] || !dst_host[i] || O_host[i] <= 0 || I_host[i] <= 0 || K_host[i] <= 0 || cols_pad_host[i] < cols ||
+          rows_pad_host[i] < nrows)
+        return NERVECL_EINVAL;
+      tab.e[j] = PackEntry{w_host[i], dst_host[i], O_host[i], I_host[i], K_host[i] * K_host[i], rows_pad_host[i],
+                           cols_pad_host[i], flip_host[i]};
+      biggest = imax(biggest, (int64_t)tab.e[j].KK * rows_pad_host[i] * cols_pad_host[i]);
+    }
+    for (int j = m; j < kPackBatch; ++j) tab.e[j] = tab.e[0];
+    dim3 grid((unsigned)imax(1, imin(cdiv(biggest, 256 * 4), 64)), (unsigned)m);
+    if (dtype == NERVECL_F32) pack_weight_batched_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(tab);
+    else pack_weight_batched_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(tab);
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return NERVECL_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // out = (acc ? out : 0) + alpha * x
 // ---------------------------------------------------------------------------------------

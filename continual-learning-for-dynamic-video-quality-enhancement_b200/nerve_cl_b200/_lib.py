@@ -46,6 +46,9 @@ _SIGNATURES = {
     "nervecl_nhwc_to_nchw": [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_nchw_to_nhwc": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_pack_conv_weight": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "nervecl_pack_conv_weights_batched": [c_i32, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_i32), C.POINTER(c_i32),
+                                          C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), c_i32,
+                                          c_vp],
     "nervecl_conv2d_fwd": [C.POINTER(ConvParams), c_vp],
     "nervecl_conv2d_wgrad": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                              c_i32, c_f32, c_i32, c_vp],

@@ -242,11 +242,13 @@ class Plan:
 
     # ---- weights ---------------------------------------------------------------------------
     def pack_weights(self, P: Dict[str, Tensor], need_bwd: bool) -> None:
+        ws, ds, fl = [], [], []
         for name in self.convs:
             w = P[name + ".weight"]
-            nv.pack_conv_weight(w, self.wf[name], False)
+            ws.append(w); ds.append(self.wf[name]); fl.append(False)
             if need_bwd and name in self.wb:
-                nv.pack_conv_weight(w, self.wb[name], True)
+                ws.append(w); ds.append(self.wb[name]); fl.append(True)
+        nv.pack_conv_weights_batched(ws, ds, fl)
 
     def pack_rdb_slice_weights(self, P: Dict[str, Tensor]) -> None:
         """Assemble (in fp32, batched over the blocks) and pack the slice-gradient operators described in
@@ -463,7 +465,7 @@ class Plan:
             x_lo = F + (0 if s == 0 else s) * GROWTH          # first channel of the later layers' gradients
             w = self.wslice[s][:, k * rows:(k + 1) * rows, :]
             mask = buf[..., c_lo:c_lo + rows] if s > 0 else None
-            with self._span_flops("conv_dgrad|slice", buf, 2.0 * rows * (9 * (CT - x_lo) + F)):
+            with self._span_flops(f"conv_dgrad|slice{s}", buf, 2.0 * rows * (9 * (CT - x_lo) + F)):
                 # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
                 nv.conv2d_fwd(g[..., x_lo:CT], w, None, dblock if s == 0 else None, mask, None,
                               g[..., c_lo:c_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,

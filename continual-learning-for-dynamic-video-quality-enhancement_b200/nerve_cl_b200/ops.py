@@ -138,6 +138,25 @@ def _pack_conv_weight(w: Tensor, dst: Tensor, transpose_flip: bool) -> None:
                "pack_conv_weight")
 
 
+@_op("pack_conv_weights_batched(Tensor[] w, Tensor(a!)[] dst, bool[] transpose_flip) -> ()")
+def _pack_conv_weights_batched(w, dst, transpose_flip) -> None:
+    """``pack_conv_weight`` for a list of weights in a handful of launches (all ``dst`` share one dtype)."""
+    n = len(w)
+    if len(dst) != n or len(transpose_flip) != n:
+        raise RuntimeError("nervecl.pack_conv_weights_batched: list lengths differ")
+    if n == 0:
+        return
+    for wi, di in zip(w, dst):
+        if di.dim() != 3 or di.shape[0] != wi.shape[2] * wi.shape[3] or not di.is_contiguous() or di.dtype != dst[0].dtype:
+            raise RuntimeError("nervecl.pack_conv_weights_batched: dst must be contiguous [K*K, rows, cols] of one dtype")
+    vps, i32 = C.c_void_p * n, C.c_int32 * n
+    _lib.check(_lib.load().nervecl_pack_conv_weights_batched(
+        n, vps(*[_flat(t, "w") for t in w]), vps(*[t.data_ptr() for t in dst]), i32(*[t.shape[0] for t in w]),
+        i32(*[t.shape[1] for t in w]), i32(*[t.shape[2] for t in w]), i32(*[t.shape[1] for t in dst]),
+        i32(*[t.shape[2] for t in dst]), i32(*[int(f) for f in transpose_flip]), _dt(dst[0]), _stream()),
+        "pack_conv_weights_batched")
+
+
 # --------------------------------------------------------------------------------------------
 # dense convolution
 # --------------------------------------------------------------------------------------------

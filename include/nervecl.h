@@ -84,6 +84,13 @@ int nervecl_pack_conv_weight(const float* w_oihw, void* dst, int dtype, int O, i
                              int KW, int rows_pad, int cols_pad, int transpose_flip,
                              nervecl_stream_t stream);
 
+/* The same for n weights in (n + 47) / 48 launches: host arrays of length n (dst_host[i] is [K*K][rows_pad][cols_pad]
+ * in `dtype`).  Used once per step for all forward and data-gradient operators. */
+int nervecl_pack_conv_weights_batched(int n, const float* const* w_host, void* const* dst_host,
+                                      const int32_t* O_host, const int32_t* I_host, const int32_t* K_host,
+                                      const int32_t* rows_pad_host, const int32_t* cols_pad_host,
+                                      const int32_t* flip_host, int dtype, nervecl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense convolution (stride 1, "same" zero padding, odd square kernel) with fused epilogue.
  * Replaces every nn.Conv2d on the path: super_resolution.py:40-43,74-82,167-174,234-242,308-311;
