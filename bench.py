@@ -298,6 +298,17 @@ def run_native(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- inference (the metric's second half): eval-mode forward of the same windows, device resident ----
+    model.eval()
+
+    def infer_step():
+        with torch.no_grad():
+            model(lr_dev)
+
+    infer_step()
+    ms_infer = timed(infer_step, args.steps)
+    model.train()
+
     if rank != 0:
         return
     pk = peaks()
@@ -328,6 +339,8 @@ def run_native(args):
                             "tflops": d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0}
                         for k, d in ksum.items() if k.startswith("conv")},
         },
+        "infer": {"metric": "sr_x2_infer_frames_per_sec", "value": frames / (ms_infer / 1e3), "unit": UNIT,
+                  "ms_per_batch": ms_infer / args.steps, "note": "eval-mode forward only, same windows, inputs in HBM"},
         "loss_last": losses[-1] if losses else None,
         "other_kernels_ms_per_step": {k: round(d["ms"] / args.steps, 3) for k, d in
                                       sorted(ksum.items(), key=lambda kv: -kv[1]["ms"]) if not k.startswith("conv")},

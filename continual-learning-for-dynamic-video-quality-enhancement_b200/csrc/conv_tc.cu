@@ -103,7 +103,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (keeps descriptors in uniform registers; see
+    // conv_tc_rows.cu)
+    {
       const uint32_t idesc = make_idesc_bf16((uint32_t)a.BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -124,18 +126,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           int nstage = stage + 1;
           uint32_t nphase = phase;
           if (nstage == a.stages) { nstage = 0; nphase ^= 1; }
-          // probe the next stage now: its latency overlaps the MMA issue below
-          ready = mbar_try_wait(&full_bar[nstage], nphase);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (>>4) address field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < KC / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (>>4) address field
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+            if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);   // accumulator ready for the epilogue
           }
-          umma_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+          __syncwarp();
+          // probe the next stage now: its latency overlaps the MMAs just issued
+          ready = mbar_try_wait(&full_bar[nstage], nphase);
           stage = nstage;
           phase = nphase;
         }
-        umma_commit(&tfull_bar[acc]);                      // accumulator ready for the epilogue
       }
     }
   } else {

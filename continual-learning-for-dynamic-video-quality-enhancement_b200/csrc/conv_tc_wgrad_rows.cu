@@ -70,6 +70,44 @@ colsum_any_kernel(const bf16* __restrict__ dy, int64_t ldy, int64_t npix, int nc
   }
 }
 
+// All bias gradients of a grouped call in ONE pass over dy (Cy % 8 == 0): db_g[o] += scale * sum_p dy[p, col0_g + o].
+// A thread owns 8 channels of every (256 / (Cy/8))-th pixel; block partials go through shared memory.
+struct BiasTable { int ngroups; int col0[kMaxGroups], ncols[kMaxGroups]; float* db[kMaxGroups]; };
+
+__global__ void __launch_bounds__(256)
+colsum_scatter_kernel(const bf16* __restrict__ dy, int64_t ldy, int64_t npix, int Cy, float scale, const BiasTable tab) {
+  extern __shared__ float red[];          // [Cy]
+  const int cg = Cy >> 3;
+  const int lanes = 256 / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (lane < lanes) {
+    for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < npix; p += (int64_t)gridDim.x * lanes) {
+      const f8 v = ld8(dy + p * ldy + 8 * g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+    }
+  }
+  for (int i = threadIdx.x; i < Cy; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&red[8 * g + k], acc[k]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cy; c += blockDim.x) {
+    for (int q = 0; q < tab.ngroups; ++q) {
+      const int o = c - tab.col0[q];
+      if (o >= 0 && o < tab.ncols[q]) {
+        if (tab.db[q]) atomicAdd(tab.db[q] + o, scale * red[c]);
+        break;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -322,6 +360,21 @@ NV_API int nervecl_conv3x3_wgrad_grouped(const void* x, int64_t ldx, const void*
   cudaStream_t s = as_stream(stream);
   int rc = wgrad_rows(x, ldx, dy, ldy, N, H, W, Cx, Cy, ngroups, col0_host, ncols_host, cin_host, dw_host, scale, s);
   if (rc) return rc;
+  if (db_host && ngroups > 1 && Cy % 8 == 0 && Cy <= 256 && aligned(dy, 16) && ldy % 8 == 0) {
+    BiasTable tab;
+    tab.ngroups = ngroups;
+    bool any = false;
+    for (int g = 0; g < ngroups; ++g) {
+      tab.col0[g] = col0_host[g]; tab.ncols[g] = ncols_host[g]; tab.db[g] = db_host[g];
+      any = any || db_host[g];
+    }
+    if (!any) return NERVECL_OK;
+    const int64_t npix = (int64_t)N * H * W;
+    const int lanes = 256 / (Cy / 8);
+    const int blocks = (int)imax(1, imin(cdiv(npix, (int64_t)lanes * 32), sm_count() * 6));
+    colsum_scatter_kernel<<<blocks, 256, Cy * sizeof(float), s>>>(reinterpret_cast<const bf16*>(dy), ldy, npix, Cy, scale, tab);
+    return launch_status();
+  }
   if (db_host) {
     for (int g = 0; g < ngroups; ++g) {
       if (!db_host[g]) continue;

@@ -242,6 +242,7 @@ bn_relu_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __res
     be[k] = beta[c];
   }
   const int64_t stride = (int64_t)gridDim.x * kThreadsFe / cg;
+#pragma unroll 4
   for (int64_t p = ((int64_t)blockIdx.x * kThreadsFe + threadIdx.x) / cg; p < npix; p += stride) {
     f8 v = ld8(x + (base + p) * ldx + c0);
     f8 o;
@@ -340,25 +341,39 @@ bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   for (int k = 0; k < 8; ++k) { sa[k] = sb[k] = 0.0; fa[k] = fb[k] = 0.f; }
   int cnt = 0;
   const int64_t stride = (int64_t)gridDim.x * kThreadsFe / cg;
-  for (int64_t p = ((int64_t)blockIdx.x * kThreadsFe + threadIdx.x) / cg; p < npix; p += stride) {
-    const f8 v = ld8(x + (base + p) * ldx + c0);
-    if (BWD) {
-      const f8 d = ld8(dy + (base + p) * lddy + c0);
+  constexpr int U = 4;                       // pixels in flight per thread
+  for (int64_t p0 = ((int64_t)blockIdx.x * kThreadsFe + threadIdx.x) / cg; p0 < npix; p0 += U * stride) {
+    f8 v[U], d[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xh = (v.v[k] - mean[k]) * is[k];
-        const float gk = fmaf(xh, ga[k], be[k]) > 0.f ? d.v[k] : 0.f;
-        fa[k] += gk;
-        fb[k] = fmaf(gk, xh, fb[k]);
-      }
-    } else {
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < npix) {
+        v[u] = ld8(x + (base + p) * ldx + c0);
+        if (BWD) d[u] = ld8(dy + (base + p) * lddy + c0);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        fa[k] += v.v[k];
-        fb[k] = fmaf(v.v[k], v.v[k], fb[k]);
+        for (int k = 0; k < 8; ++k) { v[u].v[k] = BWD ? mean[k] : 0.f; if (BWD) d[u].v[k] = 0.f; }
       }
     }
-    if (++cnt == 32) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (BWD) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (v[u].v[k] - mean[k]) * is[k];
+          const float gk = fmaf(xh, ga[k], be[k]) > 0.f ? d[u].v[k] : 0.f;
+          fa[k] += gk;
+          fb[k] = fmaf(gk, xh, fb[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          fa[k] += v[u].v[k];
+          fb[k] = fmaf(v[u].v[k], v[u].v[k], fb[k]);
+        }
+      }
+    }
+    if (++cnt == 8) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; fa[k] = fb[k] = 0.f; }
       cnt = 0;
