@@ -170,12 +170,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       uint32_t phase = 0;
       int jbase = 0;                      // output rows issued so far by this CTA (running index -> TMEM slot)
       bool ready = false;                 // early, non-blocking probe of the next chunk's barrier succeeded
+      bool acc_ready = false;             // same for the accumulator slot the next input row starts
       mbar_wait(w_bar, 0);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int seg = item % a.segs;
         const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
         int s2 = jbase % S;               // slot of output row oi = ri (the row this input row starts)
         uint32_t r2 = (uint32_t)(jbase / S);   // how many times that slot has been used before
+        acc_ready = false;                     // (the probe at the end of the previous item was for another slot)
         for (int ri = 0; ri < rows + 2; ++ri) {
           // input row ri feeds output rows oi = ri - ky (0 <= oi < rows); weight block b = 2 - ky <-> oi = ri - 2 + b
           const int blo = max(0, 2 - ri), bhi = min(2, rows + 1 - ri);
@@ -183,7 +185,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           // group adjacent blocks whose accumulator slots are adjacent columns into one MMA (merged mode)
           uint32_t gb0, gb1 = 0, gb2 = 0, gc0, gc1 = 0, gc2 = 0, gi0, gi1 = 0, gi2 = 0;
           int ng;
-          {
+          if (a.merged && blo == 0 && bhi == 2 && s2 >= 2) {     // interior row, no ring wrap: one N = 3*NOUT MMA
+            gb0 = 0; gc0 = (uint32_t)(s0 * a.NOUT); gi0 = id3; ng = 1;
+          } else {
             const bool m01 = a.merged && blo == 0 && bhi >= 1 && s1 == s0 + 1;
             const bool m12 = a.merged && blo <= 1 && bhi == 2 && s2 == s1 + 1;
             auto sbf = [&](int b) { return b == 0 ? s0 : b == 1 ? s1 : s2; };
@@ -201,7 +205,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               if (b <= bhi) { gb2 = (uint32_t)b * blk_lo; gc2 = (uint32_t)(sbf(b) * a.NOUT); gi2 = id1; ng = 3; }
             }
           }
-          if (bhi == 2) mbar_wait(&acc_empty[s2], r2 & 1u);     // slot of the new output row is drained + zeroed
+          if (bhi == 2 && !acc_ready) mbar_wait(&acc_empty[s2], r2 & 1u);   // slot of the new output row is drained + zeroed
+          acc_ready = false;
           for (int gi = 0; gi < ngrp; ++gi) {
             if (!ready) mbar_wait(&ch_full[stage], phase);
             tc_fence_after();
@@ -244,9 +249,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               umma_commit(&ch_empty[stage]);                                  // stage consumed when these MMAs retire
               if (gi == ngrp - 1 && ri >= 2) umma_commit(&acc_full[s0]);      // output row ri-2 (slot s0) is final
             }
-            __syncwarp();
-            // probe the next stage's barrier now: its latency overlaps the MMAs just issued
+            // probe the next stage's barrier (and, after the row's last stage, the accumulator slot of the next
+            // row) now: the latencies overlap each other and the MMAs just issued
             ready = mbar_try_wait(&ch_full[nstage], nphase);
+            if (gi == ngrp - 1) {
+              const int ns2 = s2 + 1 == S ? 0 : s2 + 1;
+              const uint32_t nr2 = s2 + 1 == S ? r2 + 1 : r2;
+              acc_ready = mbar_try_wait(&acc_empty[ns2], nr2 & 1u);
+            }
             stage = nstage;
             phase = nphase;
           }

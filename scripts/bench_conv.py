@@ -69,6 +69,13 @@ if __name__ == "__main__":
         fwd_case(192, 64, 3, 192, 64, engines)
         fwd_case(64, 64, 3, 64, 64, engines)
         fwd_case(224, 64, 1, 224, 64, engines)
+    if which == "layout":
+        # same conv, input/output pixel pitch 64/32 (contiguous pixels) vs 256 (channel slices of a wide buffer)
+        for cin in (64, 128, 192):
+            fwd_case(cin, 32, 3, cin, 32, [ops.CONV_TC])
+            fwd_case(cin, 32, 3, cin, 256, [ops.CONV_TC])
+            fwd_case(cin, 32, 3, 256, 32, [ops.CONV_TC])
+            fwd_case(cin, 32, 3, 256, 256, [ops.CONV_TC])
     if which == "rows":
         fwd_case(64, 32, 3, 224, 224, [ops.CONV_TC])
         fwd_case(64, 32, 3, 256, 256, [ops.CONV_TC])
