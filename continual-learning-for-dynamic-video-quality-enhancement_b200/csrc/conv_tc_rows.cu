@@ -57,6 +57,7 @@ struct RowArgs : EpiArgs {
   int stages;       // ring depth in stages
   int slots;        // TMEM accumulator ring depth
   int merged;       // vertical taps merged into N
+  int fast;         // 1: epilogue is relu?(acc + bias?) -> bf16; 2: alpha * acc gated by the ReLU mask -> bf16 (lean paths)
   int dbg;          // NERVECL_ROWS_DBG bits (profiling only): 1 no MMAs, 2 no row loads, 4 no epilogue work
 };
 
@@ -291,6 +292,100 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     for (int d = 0; d < 4; ++d) mqa[d] = mqb[d] = make_uint4(0, 0, 0, 0);
     int slot = 0;
     uint32_t par = 0;
+    if (a.fast && sizeof(OutT) == 2) {
+      // ---- lean epilogues (the generic one below is ~300 dependent instructions per warp and row, which made
+      //      the epilogue the bottleneck of every small-K launch): whole 16-channel chunks, bf16 output, bias
+      //      kept in registers, row pointers advanced instead of recomputed.  A thread owns chunk `part` and,
+      //      for NOUT = 64, chunk part + 2.
+      const bool has0 = part < nch_all, two = part + 2 < nch_all;
+      const int ch0 = c_lo + part * 16, ch1 = ch0 + 32;
+      float bz0[16], bz1[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        bz0[j] = (a.fast == 1 && a.bias && has0) ? __ldg(a.bias + ch0 + j) : 0.f;
+        bz1[j] = (a.fast == 1 && a.bias && two) ? __ldg(a.bias + ch1 + j) : 0.f;
+      }
+      const bool relu = a.relu != 0;
+      const float alpha = a.alpha;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int seg = item % a.segs;
+        const int t = item / a.segs;
+        const int strip = t % a.strips, n = t / a.strips;
+        const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
+        const int x = strip * BM + row;
+        const bool valid = x < a.W;
+        const int64_t p0 = ((int64_t)n * a.H + y0) * a.W + x;
+        bf16* op = reinterpret_cast<bf16*>(a.out) + p0 * a.ldo + ch0;
+        const int64_t ostride = (int64_t)a.W * a.ldo;
+        const bf16* mp = a.mask + p0 * a.ldmask + ch0;
+        const int64_t mstride = (int64_t)a.W * a.ldmask;
+        if (PF && valid && has0) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            if (d < rows) {
+              const uint4* m4 = reinterpret_cast<const uint4*>(mp + d * mstride);
+              mqa[d] = m4[0];
+              mqb[d] = m4[1];
+            }
+        }
+        for (int oi4 = 0; oi4 < rows; oi4 += 4) {
+#pragma unroll
+          for (int D = 0; D < 4; ++D) {
+            const int oi = oi4 + D;
+            if (oi >= rows) break;
+            uint4 m0 = mqa[D], m1 = mqb[D];
+            if (PF && valid && has0 && oi + 4 < rows) {
+              const uint4* m4 = reinterpret_cast<const uint4*>(mp + (int64_t)(oi + 4) * mstride);
+              mqa[D] = m4[0];
+              mqb[D] = m4[1];
+            }
+            mbar_wait(&acc_full[slot], par);
+            tc_fence_after();
+            const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT + part * 16);
+            uint32_t v0[16], v1[16];
+            if (has0) tmem_ld16(tcol, v0);
+            if (two) tmem_ld16(tcol + 32u, v1);
+            tmem_ld_wait();
+            if (has0) tmem_st16_zero(tcol);                          // re-arm the slot for its next output row
+            if (two) tmem_st16_zero(tcol + 32u);
+            if (valid && has0 && !(a.dbg & 4)) {
+              float f[16];
+              if (a.fast == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  f[j] = __uint_as_float(v0[j]) + bz0[j];
+                  if (relu) f[j] = fmaxf(f[j], 0.f);
+                }
+                store16(op, f);
+                if (two) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    f[j] = __uint_as_float(v1[j]) + bz1[j];
+                    if (relu) f[j] = fmaxf(f[j], 0.f);
+                  }
+                  store16(op + 32, f);
+                }
+              } else {                                               // fast == 2 (PF): alpha * acc where mask > 0
+                const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float ml = __uint_as_float(mw[j] << 16), mh = __uint_as_float(mw[j] & 0xFFFF0000u);
+                  f[2 * j] = ml > 0.f ? alpha * __uint_as_float(v0[2 * j]) : 0.f;
+                  f[2 * j + 1] = mh > 0.f ? alpha * __uint_as_float(v0[2 * j + 1]) : 0.f;
+                }
+                store16(op, f);
+              }
+            }
+            op += ostride;
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            if (++slot == S) { slot = 0; par ^= 1u; }
+          }
+        }
+      }
+    } else
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int seg = item % a.segs;
       const int t = item / a.segs;
@@ -488,6 +583,11 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.nchunks2 = p.nchunks2; t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
   t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
   { const char* d = getenv("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
+  const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.res && !a.accumulate &&
+                     !a.mask_sub && !(t.dbg & 64);
+  t.fast = 0;
+  if (whole && !a.mask && a.alpha == 1.0f && p.NOUT <= 64) t.fast = 1;
+  if (whole && a.mask && !a.bias && !a.relu && a.mask_c0 == 0 && p.NOUT <= 32) t.fast = 2;
 
   const int64_t items = (int64_t)a.N * p.strips * p.segs;
   dim3 grid((unsigned)imin(items, imax(1, sms / p.nsplit)), (unsigned)p.nsplit);
