@@ -312,6 +312,61 @@ def run_native(args):
     if rank != 0:
         return
     pk = peaks()
+    hbm_peak = pk.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
+
+    # ---- bandwidth-bound kernels against the measured HBM copy bandwidth --------------------------------
+    # (a) from the per-launch CUDA-event spans of the timed steps: algorithmic bytes per LR pixel (SURVEY.md 8d,
+    #     DESIGN.md 3; e = 2 B bf16, C = 64) x pixels per launch / launch time
+    e = 2 if args.dtype == "bf16" else 4
+    C = args.features
+    px, pxT = B * H * W, B * T * H * W
+    byte_model = {                       # kernel -> (bytes per launch, launches counted per span)
+        "warp_fwd": (2 * C * e + 8) * px, "warp_bwd": (3 * C * e + 16) * px,
+        "corr_fwd": (2 * C * e + 96 * e) * px, "corr_bwd": (96 * e + 4 * C * e) * px,
+        "dwconv3x3_fwd": 2 * C * e * pxT, "dwconv3x3_wgrad": 2 * C * e * pxT,
+        "bn_stats": C * e * pxT, "bn_relu_fwd": 2 * C * e * pxT, "bn_relu_bwd_reduce": 2 * C * e * pxT,
+        "bn_relu_bwd_apply": 3 * C * e * pxT, "tfuse_fwd": ((T + 1) * C * e + 2 * T * 4) * px,
+    }
+    hbm_kernels = {}
+    for k, nbytes in byte_model.items():
+        d = ksum.get(k)
+        if d and d["ms"] > 0:
+            gbs = nbytes * d["launches"] / (d["ms"] / 1e3) / 1e9
+            hbm_kernels[k] = {"GBs": round(gbs, 1), "frac": round(gbs / hbm_peak, 3),
+                              "ms_per_launch": round(d["ms"] / d["launches"], 4)}
+    # (b) the flat-buffer kernels are launch-bound at the model's 2 M parameters (24 MB: L2 resident), so their
+    #     bandwidth is measured on a 2^26-element buffer as well
+    n_big = 1 << 26
+    th = torch.randn(n_big, device=dev)
+    fi = torch.rand(n_big, device=dev)
+    st = torch.randn(n_big, device=dev)
+    gr = torch.randn(n_big, device=dev)
+    acc = torch.zeros(1, device=dev)
+    ea, eq = torch.zeros(n_big, device=dev), torch.zeros(n_big, device=dev)
+
+    def dev_ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    flat = {
+        "ewc_penalty_fwd": (12, lambda: ops.nv.ewc_penalty_fwd([th], fi, st, 2500.0, acc)),
+        "ewc_penalty_bwd": (20, lambda: ops.nv.ewc_penalty_bwd([th], [gr], fi, st, 5000.0, None)),
+        "ewc_fisher_accum": (12, lambda: ops.nv.ewc_fisher_accum(fi, [gr], [n_big], 1.0)),
+        "adamw_step": (28, lambda: ops.nv.adamw_step(th, gr, ea, eq, 1e-3, 0.9, 0.999, 1e-8, 1e-5, 1, 1.0)),
+    }
+    for k, (bpe, fn) in flat.items():
+        ms_k = dev_ms(fn)
+        gbs = bpe * n_big / (ms_k / 1e3) / 1e9
+        hbm_kernels[k] = {"GBs": round(gbs, 1), "frac": round(gbs / hbm_peak, 3), "ms_per_launch": round(ms_k, 4),
+                          "elements": n_big}
+    del th, fi, st, gr, ea, eq
     frames = B * world * args.steps
     value = frames / (ms / 1e3)
     conv_ms = sum(d["ms"] for k, d in ksum.items() if k.startswith("conv"))
@@ -341,6 +396,8 @@ def run_native(args):
         },
         "infer": {"metric": "sr_x2_infer_frames_per_sec", "value": frames / (ms_infer / 1e3), "unit": UNIT,
                   "ms_per_batch": ms_infer / args.steps, "note": "eval-mode forward only, same windows, inputs in HBM"},
+        "hbm_kernels": {"peak_GBs": hbm_peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk['_source']})",
+                        "kernels": hbm_kernels},
         "loss_last": losses[-1] if losses else None,
         "other_kernels_ms_per_step": {k: round(d["ms"] / args.steps, 3) for k, d in
                                       sorted(ksum.items(), key=lambda kv: -kv[1]["ms"]) if not k.startswith("conv")},

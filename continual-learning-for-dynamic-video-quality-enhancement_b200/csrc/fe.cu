@@ -375,7 +375,8 @@ NV_API int nervecl_bn_stats(const void* x, int64_t ldx, int dtype, int C, int64_
   if (!x || !sums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || C > 1024) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  // (bn_sums_fast measured slower than the 4-channel kernel below on B200: 0.72 vs 0.52 ms per launch at cfg 2)
+  // (the 8-channel / 4-loads-in-flight bn_sums_fast kernel measured slower on B200 than the plain kernel below:
+  //  0.99 vs 0.52 ms per launch at cfg 2 -- kept selectable for profiling)
   if (getenv("NERVECL_BN_SUMS_FAST") && fe_fast_supported(C, ldx, ldx, x, x))
     return bn_sums_fast(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, dtype, C, npix, groups, sums, as_stream(stream));
   int lanes = 256 / (C >> 2);

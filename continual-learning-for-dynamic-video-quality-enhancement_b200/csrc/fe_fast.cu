@@ -316,7 +316,7 @@ bn_bwd_apply_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
 // statistics pass and (g, g*xhat) with g = dy * [bn(x) > 0] for the backward reduction.  grid = (chunks, groups);
 // a thread owns 8 channels of every (256/cg)-th pixel; fp32 partials are flushed to fp64 every 32 pixels.
 template <typename T, bool BWD>
-__global__ void __launch_bounds__(kThreadsFe)
+__global__ void __launch_bounds__(kThreadsFe, 2)
 bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                     const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, int C,
                     int64_t npix, double* __restrict__ sums) {
@@ -341,22 +341,22 @@ bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
   for (int k = 0; k < 8; ++k) { sa[k] = sb[k] = 0.0; fa[k] = fb[k] = 0.f; }
   int cnt = 0;
   const int64_t stride = (int64_t)gridDim.x * kThreadsFe / cg;
-  constexpr int U = 4;                       // pixels in flight per thread
+  constexpr int U = 4;                       // independent 16-byte loads in flight per thread and operand
   for (int64_t p0 = ((int64_t)blockIdx.x * kThreadsFe + threadIdx.x) / cg; p0 < npix; p0 += U * stride) {
     f8 v[U], d[U];
+    bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t p = p0 + u * stride;
-      if (p < npix) {
+      ok[u] = p < npix;
+      if (ok[u]) {
         v[u] = ld8(x + (base + p) * ldx + c0);
         if (BWD) d[u] = ld8(dy + (base + p) * lddy + c0);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { v[u].v[k] = BWD ? mean[k] : 0.f; if (BWD) d[u].v[k] = 0.f; }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
       if (BWD) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -373,7 +373,7 @@ bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
         }
       }
     }
-    if (++cnt == 8) {
+    if (++cnt == 16) {                       // 64 pixels: flush the fp32 partials to fp64 before they lose bits
 #pragma unroll
       for (int k = 0; k < 8; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; fa[k] = fb[k] = 0.f; }
       cnt = 0;
@@ -447,7 +447,7 @@ int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy,
 
 int bn_sums_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
                  const float* beta, int dtype, int C, int64_t npix, int groups, double* sums, cudaStream_t s) {
-  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 16), (kSMs * 6) / groups + 1));
+  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 16), (kSMs * 2 * 2) / groups + 1));
   dim3 grid(chunks, groups);
   const size_t smem = (size_t)C * 2 * sizeof(double);
   if (dy) {

@@ -167,14 +167,17 @@ __global__ void __launch_bounds__(256)
 warp_fwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow, T* __restrict__ out,
                 int64_t ldo, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode,
                 int32_t* __restrict__ idx_out) {
+  // grid = (N*H rows, pixel groups of a row); the C/8 threads of a pixel are adjacent lanes (cg is a power of two):
+  // no 64-bit division per element
   const int cg = C >> 3;
-  const int64_t total = (int64_t)N * H * W * cg;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int c0 = (int)(t % cg) << 3;
-    int64_t p = t / cg;
-    int x = (int)(p % W), y = (int)((p / W) % H);
-    int64_t img = p - (int64_t)y * W - x;  // n*H*W
+  const int ppb = blockDim.x / cg;                       // pixels per block
+  const int x = blockIdx.y * ppb + (int)threadIdx.x / cg;
+  const int c0 = ((int)threadIdx.x % cg) << 3;
+  const int64_t rowi = blockIdx.x;                       // n*H + y
+  const int y = (int)(rowi % H);
+  if (x < W) {
+    const int64_t p = rowi * W + x;
+    const int64_t img = (rowi - y) * W;                  // n*H*W
     float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
     WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
     if (idx_out && c0 == 0) {
@@ -216,18 +219,19 @@ __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow,
                 const T* __restrict__ dout, int64_t lddo, float* __restrict__ dfeat, int64_t lddf,
                 float* __restrict__ dflow, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode) {
+  // grid = (N*H rows, pixel groups of a row); the C/8 threads of a pixel are adjacent lanes
   const int cg = C >> 3;
-  const int64_t total = (int64_t)N * H * W * cg;
-  const int64_t total_pad = cdiv(total, 32) * 32;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_pad;
-       t += (int64_t)gridDim.x * blockDim.x) {
+  const int ppb = blockDim.x / cg;
+  const int x = blockIdx.y * ppb + (int)threadIdx.x / cg;
+  const int64_t rowi = blockIdx.x;                       // n*H + y
+  const int y = (int)(rowi % H);
+  {
     float gix = 0.f, giy = 0.f;
-    int64_t p = t / cg;
-    const bool active = t < total;
+    const int64_t p = rowi * W + x;
+    const bool active = x < W;
     if (active) {
-      int c0 = (int)(t % cg) << 3;
-      int x = (int)(p % W), y = (int)((p / W) % H);
-      int64_t img = p - (int64_t)y * W - x;
+      const int c0 = ((int)threadIdx.x % cg) << 3;
+      const int64_t img = (rowi - y) * W;
       float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
       WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
       float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
@@ -282,7 +286,7 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
       gix += __shfl_xor_sync(0xffffffffu, gix, o);
       giy += __shfl_xor_sync(0xffffffffu, giy, o);
     }
-    if (active && (t % cg) == 0) {
+    if (active && ((int)threadIdx.x % cg) == 0) {
       // d ix / d flow_x = ((W-1)/2) * (2 * 1/(W-1)), evaluated in the reference's order
       float mx = ((float)(W - 1) * 0.5f) * (2.0f * inv_w);
       float my = ((float)(H - 1) * 0.5f) * (2.0f * inv_h);
@@ -339,8 +343,9 @@ NV_API int nervecl_warp_fwd(const void* feat, int64_t ldf, const float* flow, vo
   if (rc) return rc;
   if ((ldf & 7) || (ldo & 7) || !aligned(feat, 16) || !aligned(out, 16) || !aligned(flow, 8)) return NERVECL_EALIGN;
   float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
-  int64_t total = (int64_t)N * H * W * (C >> 3);
-  int blocks = (int)imax(1, imin(cdiv(total, 256), kSMs * 16));
+  const int ppb = 256 / (C >> 3);
+  if (cdiv(W, ppb) > 65535 || (int64_t)N * H > 0x7fffffff) return NERVECL_EUNSUPPORTED;
+  dim3 blocks((unsigned)((int64_t)N * H), (unsigned)cdiv(W, ppb));
   NV_DISPATCH_DTYPE(dtype, E, (warp_fwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
                                   (const E*)feat, ldf, flow, (E*)out, ldo, N, H, W, C, inv_w, inv_h, div_mode, idx_out)));
   return launch_status();
@@ -356,8 +361,9 @@ NV_API int nervecl_warp_bwd(const void* feat, int64_t ldf, const float* flow, co
       !aligned(flow, 8) || !aligned(dflow, 8))
     return NERVECL_EALIGN;
   float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
-  int64_t total = (int64_t)N * H * W * (C >> 3);
-  int blocks = (int)imax(1, imin(cdiv(total, 256), kSMs * 16));
+  const int ppb = 256 / (C >> 3);
+  if (cdiv(W, ppb) > 65535 || (int64_t)N * H > 0x7fffffff) return NERVECL_EUNSUPPORTED;
+  dim3 blocks((unsigned)((int64_t)N * H), (unsigned)cdiv(W, ppb));
   NV_DISPATCH_DTYPE(dtype, E, (warp_bwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
                                   (const E*)feat, ldf, flow, (const E*)dout, lddo, dfeat, lddf, dflow, N, H, W, C,
                                   inv_w, inv_h, div_mode)));
