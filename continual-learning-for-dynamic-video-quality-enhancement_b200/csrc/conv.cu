@@ -1,6 +1,7 @@
 // ABI entry points for dense convolution: argument validation + engine dispatch.
 #include "common.cuh"
 #include "conv_internal.cuh"
+#include <cstdlib>
 
 using namespace nv;
 
@@ -30,7 +31,10 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
   }
   if (engine == NERVECL_CONV_AUTO) engine = conv_tc_fwd_supported(*p) ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
   if (engine == NERVECL_CONV_TC) {               // best tcgen05 kernel for the shape
-    if (conv_rows_supported(*p)) return conv_rows_fwd(*p, s);
+    // (1x1: the row kernel wins while the per-row MMA count stays small; wide inputs are at the HBM roofline
+    //  with the per-tap kernel already)
+    static const int k1_max_cin = getenv("NERVECL_ROWS_K1_MAXCIN") ? atoi(getenv("NERVECL_ROWS_K1_MAXCIN")) : 128;
+    if ((p->K == 3 || p->Cin <= k1_max_cin) && conv_rows_supported(*p)) return conv_rows_fwd(*p, s);
     if (!conv_tc_fwd_supported(*p)) return NERVECL_EUNSUPPORTED;
     return conv_tc_fwd(*p, s);
   }

@@ -52,6 +52,7 @@ struct RowArgs : EpiArgs {
   int nchunks2;     // 64-channel chunks of x2 (0: no second input)
   int ksteps2_last;
   int x2_center;    // x2 channels only have a centre tap
+  int x_center;     // 1x1 convolution: x only has a centre tap (its ky = 0 / 2 weight blocks are zero-filled)
   int strips, R, segs;
   int cps;          // chunks per ring stage (a stage is filled / released as a unit)
   int stages;       // ring depth in stages
@@ -63,9 +64,9 @@ struct RowArgs : EpiArgs {
 
 // weight tile index of (kx, chunk): x chunks first, then x2 chunks (one tile per chunk when centre-only)
 __device__ __forceinline__ int wtile_index(const RowArgs& a, int kx, int c) {
-  if (c < a.nchunks) return kx * a.nchunks + c;
+  if (c < a.nchunks) return a.x_center ? c : kx * a.nchunks + c;
   const int c2 = c - a.nchunks;
-  return 3 * a.nchunks + (a.x2_center ? c2 : kx * a.nchunks2 + c2);
+  return (a.x_center ? 1 : 3) * a.nchunks + (a.x2_center ? c2 : kx * a.nchunks2 + c2);
 }
 
 template <typename OutT, bool PF>
@@ -77,7 +78,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const uint32_t blk_bytes = (uint32_t)a.NOUT * ROWB;          // one ky block of one (kx, chunk) weight tile
   const uint32_t wtile_bytes = 3u * blk_bytes;
   const int nct = a.nchunks + a.nchunks2;
-  const int ntiles = 3 * a.nchunks + (a.x2_center ? 1 : 3) * a.nchunks2;
+  const int ntiles = (a.x_center ? 1 : 3) * a.nchunks + (a.x2_center ? 1 : 3) * a.nchunks2;
   const uint32_t w_bytes = (uint32_t)ntiles * wtile_bytes;
   uint8_t* w_smem = smem;
   uint8_t* ring = smem + w_bytes;
@@ -123,10 +124,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_expect_tx(w_bar, w_bytes);
       for (int c = 0; c < nct; ++c)
         for (int kx = 0; kx < 3; ++kx) {
-          if (c >= a.nchunks && a.x2_center && kx != 1) continue;
-          for (int b = 0; b < 3; ++b)     // block b holds ky = 2 - b
+          if ((c >= a.nchunks ? a.x2_center : a.x_center) && kx != 1) continue;
+          for (int b = 0; b < 3; ++b) {   // block b holds ky = 2 - b; a 1x1 filter is tap 0, its other blocks are
+            const int tap = a.x_center ? (b == 1 ? 0 : 1) : (2 - b) * 3 + kx;    // out of range = zero fill
             tma_load_3d(w_smem + (size_t)wtile_index(a, kx, c) * wtile_bytes + (size_t)b * blk_bytes, &tmap_w, w_bar,
-                        c * KC, grp * a.NOUT, (2 - b) * 3 + kx);
+                        c * KC, grp * a.NOUT, tap);
+          }
         }
       int stage = 0;
       uint32_t phase = 0;
@@ -221,10 +224,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   const uint32_t a_lo = ring_lo + (uint32_t)stage * (stage_bytes >> 4) + (uint32_t)cc * (CHUNK_BYTES >> 4);
                   const bool second = c >= a.nchunks;
                   const int ks = (c == a.nchunks - 1) ? a.ksteps_last : (c == nct - 1 && second) ? a.ksteps2_last : KC / 16;
-                  const bool ctr = second && a.x2_center;                         // centre tap only
+                  const bool ctr = second ? a.x2_center != 0 : a.x_center != 0;   // centre tap only
                   // weight tile of (kx, c): tile0 + kx * tstride
-                  const uint32_t tile0 = (uint32_t)(second ? 3 * a.nchunks + (c - a.nchunks) : c);
-                  const uint32_t tstride = (uint32_t)(second ? (ctr ? 0 : a.nchunks2) : a.nchunks);
+                  const uint32_t tile0 = (uint32_t)(second ? (a.x_center ? 1 : 3) * a.nchunks + (c - a.nchunks) : c);
+                  const uint32_t tstride = (uint32_t)(ctr ? 0 : second ? a.nchunks2 : a.nchunks);
                   for (int g = 0; g < ng; ++g) {
                     const uint32_t d = tmem_base + (g == 0 ? gc0 : g == 1 ? gc1 : gc2);
                     const uint32_t gb = w_lo + (g == 0 ? gb0 : g == 1 ? gb1 : gb2) + tile0 * wtile_lo;
@@ -473,7 +476,7 @@ bool plan_rows(const nervecl_conv_params& a, int sms, RowPlan& p) {
   p.nchunks2 = a.x2 ? (a.Cin2 + KC - 1) / KC : 0;
   p.ksteps2_last = a.x2 ? (a.Cin2 - (p.nchunks2 - 1) * KC + 15) / 16 : 0;
   const int nct = p.nchunks + p.nchunks2;
-  const int ntiles = 3 * p.nchunks + ((a.x2 && a.x2_center) ? 1 : 3) * p.nchunks2;
+  const int ntiles = (a.K == 1 ? 1 : 3) * p.nchunks + ((a.x2 && a.x2_center) ? 1 : 3) * p.nchunks2;
   const int cout16 = (a.Cout + 15) / 16 * 16;
   p.nsplit = 0;
   for (int ns = 1; ns <= 16 && !p.nsplit; ++ns) {
@@ -524,7 +527,8 @@ bool conv_rows_supported(const nervecl_conv_params& a) {
   nervecl_conv_params b = a;
   b.x2 = nullptr;
   if (!conv_tc_fwd_supported(b)) return false;       // dtype / alignment / epilogue constraints are the same
-  if (a.K != 3) return false;
+  if (a.K != 3 && a.K != 1) return false;
+  if (a.K == 1 && a.x2) return false;
   if (a.Cin < 16 || a.Cin % 16 || a.Cin > 512) return false;
   if (a.W < 64 || a.H < 3) return false;
   if (a.x2) {
@@ -561,7 +565,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   {
     // the x2 weight columns start at column nchunks*64 of the packed rows; TMA boxes address them as chunk
     // (nchunks + c2), so one map over the whole row length serves both inputs
-    cuuint64_t dims[3] = {(cuuint64_t)a.w_ld, (cuuint64_t)a.w_rows, 9};
+    cuuint64_t dims[3] = {(cuuint64_t)a.w_ld, (cuuint64_t)a.w_rows, (cuuint64_t)(a.K * a.K)};
     cuuint64_t strides[2] = {(cuuint64_t)a.w_ld * 2, (cuuint64_t)a.w_rows * a.w_ld * 2};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)p.NOUT, 1};
     cuuint32_t es[3] = {1, 1, 1};
@@ -581,6 +585,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.N = a.N; t.H = a.H; t.W = a.W;
   t.NOUT = p.NOUT; t.nchunks = p.nchunks; t.ksteps_last = p.ksteps_last;
   t.nchunks2 = p.nchunks2; t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
+  t.x_center = a.K == 1;
   t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
   { const char* d = getenv("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
   const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.res && !a.accumulate &&

@@ -7,10 +7,12 @@ using namespace nv;
 
 namespace nv {   // fe_fast.cu
 bool fe_fast_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b);
+bool dw_tiled_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b);
 int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int dtype, int N, int H, int W, int C,
                  int flip, int accumulate, cudaStream_t s);
 int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy, int dtype, float* dw, int N, int H, int W,
                        int C, cudaStream_t s);
+bool bn_sums_fast_supported(int C, int64_t lda, int64_t ldb);
 int bn_sums_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
                  const float* beta, int dtype, int C, int64_t npix, int groups, double* sums, cudaStream_t s);
 int bn_relu_fwd_fast(const void* x, int64_t ldx, const float* stat, const float* gamma, const float* beta, const void* res,
@@ -345,7 +347,7 @@ NV_API int nervecl_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, voi
   if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if ((C & 7) || (ldx & 7) || (ldy & 7) || !aligned(x, 16) || !aligned(y, 16)) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  if (fe_fast_supported(C, ldx, ldy, x, y))
+  if (dw_tiled_supported(C, ldx, ldy, x, y))
     return dwconv_slide(x, ldx, w, y, ldy, dtype, N, H, W, C, flip, accumulate, as_stream(stream));
   int64_t total = (int64_t)N * H * W * (C >> 3);
   NV_DISPATCH_DTYPE(dtype, E, (dwconv_kernel<E><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
@@ -358,7 +360,7 @@ NV_API int nervecl_dwconv3x3_wgrad(const void* x, int64_t ldx, const void* dy, i
   if (!x || !dy || !dw || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (ldy & 3) || C > 1024) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  if (fe_fast_supported(C, ldx, ldy, x, dy))
+  if (dw_tiled_supported(C, ldx, ldy, x, dy))
     return dwconv_wgrad_slide(x, ldx, dy, ldy, dtype, dw, N, H, W, C, as_stream(stream));
   int64_t npix = (int64_t)N * H * W;
   int lanes = 256 / (C >> 2);
@@ -375,12 +377,10 @@ NV_API int nervecl_bn_stats(const void* x, int64_t ldx, int dtype, int C, int64_
   if (!x || !sums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || C > 1024) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  // (the 8-channel / 4-loads-in-flight bn_sums_fast kernel measured slower on B200 than the plain kernel below:
-  //  0.99 vs 0.52 ms per launch at cfg 2 -- kept selectable for profiling)
-  if (getenv("NERVECL_BN_SUMS_FAST") && fe_fast_supported(C, ldx, ldx, x, x))
+  if (!getenv("NERVECL_BN_SUMS_PLAIN") && bn_sums_fast_supported(C, ldx, ldx))
     return bn_sums_fast(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, dtype, C, npix, groups, sums, as_stream(stream));
   int lanes = 256 / (C >> 2);
-  int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups + 1));
+  int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups));
   dim3 grid(chunks, groups);
   size_t smem = (size_t)C * 2 * sizeof(double);
   NV_DISPATCH_DTYPE(dtype, E, (bn_stats_kernel<E><<<grid, 256, smem, as_stream(stream)>>>(
@@ -418,10 +418,10 @@ NV_API int nervecl_bn_relu_bwd_reduce(const void* x, int64_t ldx, const void* dy
   if (!x || !dy || !stat || !gamma || !beta || !bsums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (lddy & 3) || C > 1024) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  if (getenv("NERVECL_BN_SUMS_FAST") && fe_fast_supported(C, ldx, lddy, x, dy))
+  if (!getenv("NERVECL_BN_SUMS_PLAIN") && bn_sums_fast_supported(C, ldx, lddy))
     return bn_sums_fast(x, ldx, dy, lddy, stat, gamma, beta, dtype, C, npix, groups, bsums, as_stream(stream));
   int lanes = 256 / (C >> 2);
-  int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups + 1));
+  int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups));
   dim3 grid(chunks, groups);
   size_t smem = (size_t)C * 2 * sizeof(double);
   NV_DISPATCH_DTYPE(dtype, E, (bn_bwd_reduce_kernel<E><<<grid, 256, smem, as_stream(stream)>>>(

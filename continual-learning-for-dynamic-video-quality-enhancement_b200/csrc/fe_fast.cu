@@ -6,6 +6,7 @@
 //     LSU-issue-bound at ~7x the HBM time);
 //   * BatchNorm+ReLU forward and backward-apply with every per-channel coefficient hoisted into registers.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 using namespace nv;
 
@@ -14,47 +15,69 @@ namespace {
 constexpr int kThreadsFe = 256;
 constexpr int DW_TH = 8;         // output rows per tile
 
-// 16-byte async copy global -> shared (zero-fills when !valid: src-size 0)
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+// Depthwise tiles are brought in by TMA: one 4-D box {C, TWp + 2, TH + 2, 1} per tile with out-of-image pixels
+// zero-filled (= the conv padding), landing in shared memory as [(TH+2)][(TWp+2)][C].  The per-thread cp.async
+// staging this replaces cost ~400 of the kernel's 2100 instructions per thread and tile, and the kernel was
+// instruction-issue bound (72 % SM throughput at 49 % of the HBM roofline, profiles/r01z_summary.md).
+struct TileXY { int n, y0, x0; };
+__device__ __forceinline__ TileXY tile_xy(int64_t tile, int tiles_x, int tiles_y, int TWp, int TH) {
+  const int txi = (int)(tile % tiles_x);
+  const int64_t r = tile / tiles_x;
+  return TileXY{(int)(r / tiles_y), (int)(r % tiles_y) * TH, txi * TWp};
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename T> struct Vec8Bytes { static constexpr int value = 8 * sizeof(T); };
-
-// Stage the halo'd tile rows [y0-1, y0+TH], pixels [x0-1, x0+TWp] of image n into shared memory as
-// [(TH+2)][(TWp+2)][C] (zero outside the image) with 16-byte cp.async copies.
-template <typename T>
-__device__ __forceinline__ void stage_tile(T* __restrict__ sm, const T* __restrict__ x, int64_t ldx, int n, int y0, int x0,
-                                           int H, int W, int C, int TWp) {
-  constexpr int EPC = 16 / sizeof(T);          // elements per 16-byte chunk
-  const int cpp = C / EPC;                     // chunks per pixel (divides the block size: C/8 is a power of two)
-  const int PWs = TWp + 2;
-  const int ch = threadIdx.x % cpp;            // this thread always copies the same chunk of a pixel ...
-  const int pstep = kThreadsFe / cpp;          // ... of every pstep-th pixel: no division in the loop
-  int px = threadIdx.x / cpp, r = 0;
-  while (px >= PWs) { px -= PWs; ++r; }
-  const T* img = x + (int64_t)n * H * W * ldx + ch * EPC;
-  T* dst = sm + ch * EPC;
-  for (; r < DW_TH + 2;) {
-    const int yy = y0 - 1 + r, xx = x0 - 1 + px;
-    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-    const T* src = ok ? img + ((int64_t)yy * W + xx) * ldx : x;
-    cp_async16(dst + (size_t)(r * PWs + px) * C, src, ok);
-    px += pstep;
-    while (px >= PWs) { px -= PWs; ++r; }
+// One output column of DW_TH rows: each input row's three neighbour vectors are loaded / converted once and feed
+// the three output rows they belong to (rolling accumulators).  FULL: all DW_TH rows are inside the image.
+template <typename T, bool ACC, bool FULL>
+__device__ __forceinline__ void dw_column(const T* __restrict__ col, int rstride, int C, const float (&wt)[3][3][8],
+                                          T* __restrict__ yp, int64_t ystride, int nrows) {
+  float acc[3][8];
+#pragma unroll
+  for (int ri = 0; ri < DW_TH + 2; ++ri) {
+    float v[3][8];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const f8 t = ld8(col + ri * rstride + kx * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[kx][k] = t.v[k];
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int oi = ri - ky;                     // output row (tile-local) that uses this input row as tap row ky
+      if (oi < 0 || oi >= DW_TH) continue;
+      float* a = acc[oi % 3];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (ky == 0 && kx == 0) ? v[kx][k] * wt[ky][kx][k] : fmaf(v[kx][k], wt[ky][kx][k], a[k]);
+    }
+    const int od = ri - 2;                        // this output row is complete
+    if (od >= 0 && (FULL || od < nrows)) {
+      const float* a = acc[od % 3];
+      f8 o;
+      if (ACC) {
+        o = ld8(yp);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += a[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = a[k];
+      }
+      st8(yp, o);
+      yp += ystride;
+    }
   }
 }
 
 // y[p,c] (+)= sum_taps x[p+tap,c] * w[c][tap]   (flip: 180-degree rotated filter = data gradient)
-// block = 256 threads = (C/8 channel groups) x TWp pixel columns; tile = DW_TH rows x TWp columns.
-template <typename T>
+// block = 256 threads = (C/8 channel groups) x TWp pixel columns; tile = DW_TH rows x TWp columns; two tile
+// buffers so the next tile's TMA load is in flight while this one is computed.
+template <typename T, bool ACC>
 __global__ void __launch_bounds__(kThreadsFe, 2)
-dwconv_tile_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, T* __restrict__ y, int64_t ldy,
-                   int N, int H, int W, int C, int flip, int accumulate, int tiles_x, int tiles_y) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+dwconv_tile_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ w, T* __restrict__ y, int64_t ldy,
+                   int N, int H, int W, int C, int flip, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int cg = C >> 3;
   const int TWp = kThreadsFe / cg;
@@ -71,73 +94,56 @@ dwconv_tile_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
       }
   const int PWs = TWp + 2;
   const int64_t ntiles = (int64_t)N * tiles_y * tiles_x;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int txi = (int)(tile % tiles_x);
-    const int64_t r = tile / tiles_x;
-    const int tyi = (int)(r % tiles_y), n = (int)(r / tiles_y);
-    const int x0 = txi * TWp, y0 = tyi * DW_TH;
-    __syncthreads();                       // previous tile's reads are done
-    stage_tile(sm, x, ldx, n, y0, x0, H, W, C, TWp);
-    cp_async_wait_all();
-    __syncthreads();
-    const int xx = x0 + tx;
-    if (xx < W) {
-      // walk the DW_TH + 2 input rows of this thread's column once: each row's three neighbour vectors are
-      // loaded / converted once and feed the three output rows they belong to (rolling accumulators)
-      float acc[3][8];
-      const T* col = sm + tx * C + c0;                                   // this thread's column of the tile
-      const int rstride = PWs * C;
-      T* yp = y + (((int64_t)n * H + y0) * W + xx) * ldy + c0;
-      const int64_t ystride = (int64_t)W * ldy;
-#pragma unroll
-      for (int ri = 0; ri < DW_TH + 2; ++ri) {
-        float v[3][8];
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          f8 t = ld8(col + ri * rstride + kx * C);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[kx][k] = t.v[k];
-        }
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int oi = ri - ky;                     // output row (tile-local) that uses this input row as tap row ky
-          if (oi < 0 || oi >= DW_TH) continue;
-          float* a = acc[oi % 3];
-          if (ky == 0) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = 0.f;
-          }
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = fmaf(v[kx][k], wt[ky][kx][k], a[k]);
-        }
-        const int od = ri - 2;                        // this output row is complete
-        if (od >= 0 && y0 + od < H) {
-          const float* a = acc[od % 3];
-          f8 o;
-          if (accumulate) {
-            o = ld8(yp);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o.v[k] += a[k];
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o.v[k] = a[k];
-          }
-          st8(yp, o);
-          yp += ystride;
-        }
-      }
+  const size_t tile_elems = (size_t)(DW_TH + 2) * PWs * C;
+  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(T));
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmx);
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) {
+    const TileXY t0 = tile_xy(blockIdx.x, tiles_x, tiles_y, TWp, DW_TH);
+    tc::mbar_expect_tx(&bars[0], tile_bytes);
+    tc::tma_load_4d(sm, &tmx, &bars[0], 0, t0.x0 - 1, t0.y0 - 1, t0.n);
+  }
+  int buf = 0;
+  uint32_t par = 0;                        // phase parity bit of each buffer's barrier
+  const int rstride = PWs * C;
+  const int64_t ystride = (int64_t)W * ldy;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const TileXY t = tile_xy(tile, tiles_x, tiles_y, TWp, DW_TH);
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) {   // (every read of that buffer ended before the last barrier)
+      const TileXY tn = tile_xy(tile + gridDim.x, tiles_x, tiles_y, TWp, DW_TH);
+      tc::mbar_expect_tx(&bars[buf ^ 1], tile_bytes);
+      tc::tma_load_4d(sm + (buf ^ 1) * tile_elems, &tmx, &bars[buf ^ 1], 0, tn.x0 - 1, tn.y0 - 1, tn.n);
     }
+    tc::mbar_wait(&bars[buf], (par >> buf) & 1u);
+    par ^= 1u << buf;
+    const int xx = t.x0 + tx;
+    if (xx < W) {
+      const T* col = sm + buf * tile_elems + tx * C + c0;                // this thread's column of the tile
+      T* yp = y + (((int64_t)t.n * H + t.y0) * W + xx) * ldy + c0;
+      const int nrows = H - t.y0;
+      if (nrows >= DW_TH) dw_column<T, ACC, true>(col, rstride, C, wt, yp, ystride, DW_TH);
+      else dw_column<T, ACC, false>(col, rstride, C, wt, yp, ystride, nrows);
+    }
+    __syncthreads();                       // every read of this buffer is done before the next round refills it
   }
 }
 
 // dw[c][tap] += sum_p dy[p,c] * x[p+tap,c]
+// Same tiling with WG_TH-row tiles and two (x, dy) tile buffers; the 72 partial sums of the thread's 8 channels
+// stay in registers across all of the block's tiles.  Out-of-image dy pixels are zero-filled by TMA.
+constexpr int WG_TH = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(kThreadsFe, 2)
-dwconv_wgrad_tile_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+dwconv_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmd,
                          float* __restrict__ dw, int N, int H, int W, int C, int tiles_x, int tiles_y) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int cg = C >> 3;
   const int TWp = kThreadsFe / cg;
@@ -150,53 +156,56 @@ dwconv_wgrad_tile_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[ky][kx][k] = 0.f;
   const int PWs = TWp + 2;
-  T* smd = sm + (size_t)(DW_TH + 2) * PWs * C;
+  const size_t x_elems = (size_t)(WG_TH + 2) * PWs * C;
+  const size_t d_elems = (size_t)WG_TH * TWp * C;
+  const size_t buf_elems = x_elems + d_elems;                      // [x tile | dy tile]
+  const uint32_t buf_bytes = (uint32_t)(buf_elems * sizeof(T));
   const int64_t ntiles = (int64_t)N * tiles_y * tiles_x;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int txi = (int)(tile % tiles_x);
-    const int64_t r = tile / tiles_x;
-    const int tyi = (int)(r % tiles_y), n = (int)(r / tiles_y);
-    const int x0 = txi * TWp, y0 = tyi * DW_TH;
-    __syncthreads();
-    stage_tile(sm, x, ldx, n, y0, x0, H, W, C, TWp);
-    // dy tile [DW_TH][TWp][C] behind the x tile
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmx);
+    tc::prefetch_tmap(&tmd);
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  auto load = [&](int b, int64_t tile) {
+    const TileXY t = tile_xy(tile, tiles_x, tiles_y, TWp, WG_TH);
+    T* dst = sm + b * buf_elems;
+    tc::mbar_expect_tx(&bars[b], buf_bytes);
+    tc::tma_load_4d(dst, &tmx, &bars[b], 0, t.x0 - 1, t.y0 - 1, t.n);
+    tc::tma_load_4d(dst + x_elems, &tmd, &bars[b], 0, t.x0, t.y0, t.n);
+  };
+  if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) load(0, blockIdx.x);
+  int buf = 0;
+  uint32_t par = 0;                        // phase parity bit of each buffer's barrier
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) load(buf ^ 1, tile + gridDim.x);
+    tc::mbar_wait(&bars[buf], (par >> buf) & 1u);
+    par ^= 1u << buf;
     {
-      constexpr int EPC = 16 / sizeof(T);
-      const int cpp = C / EPC;
-      const int total = DW_TH * TWp * cpp;
-      for (int e = threadIdx.x; e < total; e += kThreadsFe) {
-        const int ch = e % cpp;
-        const int pp = e / cpp;
-        const int px = pp % TWp, rr = pp / TWp;
-        const int yy = y0 + rr, xq = x0 + px;
-        const bool ok = yy < H && xq < W;
-        const T* src = ok ? dy + (((int64_t)n * H + yy) * W + xq) * lddy + ch * EPC : dy;
-        cp_async16(smd + (size_t)pp * C + ch * EPC, src, ok);
-      }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    {
+      const T* smx = sm + buf * buf_elems + tx * C + c0;
+      const T* smd = sm + buf * buf_elems + x_elems + tx * C + c0;
       // input row ri pairs with the dy rows ri - ky (tap row ky): keep the three live dy vectors in registers
       float d[3][8];
 #pragma unroll
-      for (int ri = 0; ri < DW_TH + 2; ++ri) {
-        if (ri < DW_TH) {
-          const f8 t = ld8(smd + (ri * TWp + tx) * C + c0);
+      for (int ri = 0; ri < WG_TH + 2; ++ri) {
+        if (ri < WG_TH) {
+          const f8 t = ld8(smd + ri * TWp * C);
 #pragma unroll
           for (int k = 0; k < 8; ++k) d[ri % 3][k] = t.v[k];
         }
         float v[3][8];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          f8 t = ld8(sm + ((ri * PWs + tx + kx) * C + c0));
+          const f8 t = ld8(smx + (ri * PWs + kx) * C);
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[kx][k] = t.v[k];
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const int oi = ri - ky;
-          if (oi < 0 || oi >= DW_TH) continue;
+          if (oi < 0 || oi >= WG_TH) continue;
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -204,9 +213,9 @@ dwconv_wgrad_tile_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
         }
       }
     }
+    __syncthreads();
   }
   // block reduction: shared fp32 atomics (one address per (channel, tap)), then one global atomic each
-  __syncthreads();
   float* red = reinterpret_cast<float*>(smem_raw);   // [C*9]
   for (int i = threadIdx.x; i < C * 9; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
@@ -224,7 +233,7 @@ dwconv_wgrad_tile_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
 // BatchNorm + ReLU, 8 channels per thread, coefficients in registers.  grid = (chunks, groups).
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreadsFe)
+__global__ void __launch_bounds__(kThreadsFe, 3)
 bn_relu_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ stat, const float* __restrict__ gamma,
                         const float* __restrict__ beta, const T* __restrict__ res, int64_t ldres, T* __restrict__ y,
                         int64_t ldy, int C, int64_t npix) {
@@ -258,7 +267,7 @@ bn_relu_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __res
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreadsFe)
+__global__ void __launch_bounds__(kThreadsFe, 3)
 bn_bwd_apply_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                          const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta,
                          const double* __restrict__ bsums, T* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
@@ -313,21 +322,27 @@ bn_bwd_apply_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restri
 }
 
 // per-(group, channel) sums in float64: sums[g][c][0..1] += (sum a, sum b) where (a, b) = (x, x^2) for the
-// statistics pass and (g, g*xhat) with g = dy * [bn(x) > 0] for the backward reduction.  grid = (chunks, groups);
-// a thread owns 8 channels of every (256/cg)-th pixel; fp32 partials are flushed to fp64 every 32 pixels.
-template <typename T, bool BWD>
-__global__ void __launch_bounds__(kThreadsFe, 2)
+// statistics pass and (g, g*xhat) with g = dy * [bn(x) > 0] for the backward reduction.
+// One wave of kSMs*4 (backward: kSMs*3) blocks, flattened over (group, slab): a block streams one contiguous slab of pixels of one
+// group; a thread owns 4 channels of every (256/cg)-th pixel and keeps U independent vector loads per operand in
+// flight (64 KB per SM, enough to cover the HBM latency); fp32 partials go to fp64 every 16 rounds.
+template <typename T, bool BWD, int U>
+__global__ void __launch_bounds__(kThreadsFe, BWD ? 3 : 4)
 bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                     const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ beta, int C,
-                    int64_t npix, double* __restrict__ sums) {
-  const int cg = C >> 3;
-  const int g = threadIdx.x % cg, c0 = g << 3;
-  const int grp = blockIdx.y;
-  const int64_t base = (int64_t)grp * npix;
-  float mean[8], is[8], ga[8], be[8];
+                    int64_t npix, int bpg, double* __restrict__ sums) {
+  const int cg = C >> 2;                     // threads per pixel: a power of two <= 256
+  const int lanes = kThreadsFe / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg, c0 = g << 2;
+  const int grp = blockIdx.x / bpg, slab = blockIdx.x % bpg;
+  const int64_t per = cdiv(npix, bpg);
+  const int64_t p_lo = (int64_t)slab * per, p_hi = p_lo + per < npix ? p_lo + per : npix;
+  const T* xb = x + (int64_t)grp * npix * ldx + c0;
+  const T* db = BWD ? dy + (int64_t)grp * npix * lddy + c0 : nullptr;
+  float mean[4], is[4], ga[4], be[4];
   if (BWD) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const int c = c0 + k;
       mean[k] = stat[((int64_t)grp * C + c) * 2];
       is[k] = stat[((int64_t)grp * C + c) * 2 + 1];
@@ -335,59 +350,64 @@ bn_sums_fast_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ 
       be[k] = beta[c];
     }
   }
-  double sa[8], sb[8];
-  float fa[8], fb[8];
+  double sa[4], sb[4];
+  float fa[4], fb[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { sa[k] = sb[k] = 0.0; fa[k] = fb[k] = 0.f; }
-  int cnt = 0;
-  const int64_t stride = (int64_t)gridDim.x * kThreadsFe / cg;
-  constexpr int U = 4;                       // independent 16-byte loads in flight per thread and operand
-  for (int64_t p0 = ((int64_t)blockIdx.x * kThreadsFe + threadIdx.x) / cg; p0 < npix; p0 += U * stride) {
-    f8 v[U], d[U];
-    bool ok[U];
+  for (int k = 0; k < 4; ++k) { sa[k] = sb[k] = 0.0; fa[k] = fb[k] = 0.f; }
+  auto add = [&](const f4& v, const f4& d) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + u * stride;
-      ok[u] = p < npix;
-      if (ok[u]) {
-        v[u] = ld8(x + (base + p) * ldx + c0);
-        if (BWD) d[u] = ld8(dy + (base + p) * lddy + c0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!ok[u]) continue;
+    for (int k = 0; k < 4; ++k) {
       if (BWD) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float xh = (v[u].v[k] - mean[k]) * is[k];
-          const float gk = fmaf(xh, ga[k], be[k]) > 0.f ? d[u].v[k] : 0.f;
-          fa[k] += gk;
-          fb[k] = fmaf(gk, xh, fb[k]);
-        }
+        const float xh = (v.v[k] - mean[k]) * is[k];
+        const float gk = fmaf(xh, ga[k], be[k]) > 0.f ? d.v[k] : 0.f;   // == bn_value(...) > 0
+        fa[k] += gk;
+        fb[k] = fmaf(gk, xh, fb[k]);
       } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          fa[k] += v[u].v[k];
-          fb[k] = fmaf(v[u].v[k], v[u].v[k], fb[k]);
-        }
+        fa[k] += v.v[k];
+        fb[k] = fmaf(v.v[k], v.v[k], fb[k]);
       }
     }
-    if (++cnt == 16) {                       // 64 pixels: flush the fp32 partials to fp64 before they lose bits
+  };
+  int64_t p = p_lo + lane;
+  int cnt = 0;
+  for (; p + (int64_t)(U - 1) * lanes < p_hi; p += (int64_t)U * lanes) {
+    f4 v[U], d[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; fa[k] = fb[k] = 0.f; }
+    for (int u = 0; u < U; ++u) {
+      v[u] = ld4(xb + (p + (int64_t)u * lanes) * ldx);
+      if (BWD) d[u] = ld4(db + (p + (int64_t)u * lanes) * lddy);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) add(v[u], BWD ? d[u] : v[u]);
+    if (++cnt == 64 / U) {                   // 64 pixels: flush the fp32 partials to fp64 before they lose bits
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; fa[k] = fb[k] = 0.f; }
       cnt = 0;
     }
   }
+  for (; p < p_hi; p += lanes) {
+    const f4 v = ld4(xb + p * ldx);
+    add(v, BWD ? ld4(db + p * lddy) : v);
+  }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; }
+  for (int k = 0; k < 4; ++k) { sa[k] += fa[k]; sb[k] += fb[k]; }
+  // lanes of one warp that own the same channels, then the warps of the block, then one global atomic per value
+  for (int o = cg; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sa[k] += __shfl_xor_sync(0xffffffffu, sa[k], o);
+      sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], o);
+    }
+  }
   extern __shared__ double dred[];  // [C][2]
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) dred[i] = 0.0;
   __syncthreads();
+  if ((threadIdx.x & 31) < cg) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&dred[(c0 + k) * 2 + 0], sa[k]);
-    atomicAdd(&dred[(c0 + k) * 2 + 1], sb[k]);
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&dred[(c0 + k) * 2 + 0], sa[k]);
+      atomicAdd(&dred[(c0 + k) * 2 + 1], sb[k]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(sums + (int64_t)grp * C * 2 + i, dred[i]);
@@ -406,6 +426,24 @@ namespace nv {
 bool fe_fast_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b) {
   return cg_ok(C) && !(lda & 7) && !(ldb & 7) && aligned(a, 16) && aligned(b, 16);
 }
+// TMA-tiled depthwise kernels: a box holds at most 256 pixels per row and 256 channels
+bool dw_tiled_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b) {
+  return fe_fast_supported(C, lda, ldb, a, b) && C >= 16 && C <= 256 && tc::encode_fn() != nullptr;
+}
+
+// 4-D tensor map over an NHWC activation with a {C, bw, bh, 1} box (no swizzle: the tile lands as [bh][bw][C])
+static bool encode_tile_map(CUtensorMap* m, const void* base, int64_t ld, int dtype, int N, int H, int W, int C, int bw, int bh) {
+  tc::EncodeTiledFn enc = tc::encode_fn();
+  if (!enc) return false;
+  const cuuint64_t esz = dtype == NERVECL_F32 ? 4 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)W * ld * esz, (cuuint64_t)H * W * ld * esz};
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, dtype == NERVECL_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+             const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int dtype, int N, int H, int W, int C,
                  int flip, int accumulate, cudaStream_t s) {
@@ -414,14 +452,19 @@ int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ld
   const int64_t ntiles = (int64_t)N * tiles_x * tiles_y;
   const int blocks = (int)imax(1, imin(ntiles, kSMs * 2));
   const size_t esz = dtype == NERVECL_F32 ? 4 : 2;
-  const size_t smem = (size_t)(DW_TH + 2) * (TWp + 2) * C * esz;
+  const size_t smem = 2 * (size_t)(DW_TH + 2) * (TWp + 2) * C * esz;          // two tile buffers
+  CUtensorMap tmx;
+  if (!encode_tile_map(&tmx, x, ldx, dtype, N, H, W, C, TWp + 2, DW_TH + 2)) return NERVECL_EUNSUPPORTED;
   cudaError_t e;
-#define NV_DW_LAUNCH(E)                                                                                              \
-  e = cudaFuncSetAttribute(dwconv_tile_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+#define NV_DW_LAUNCH(E, A)                                                                                           \
+  e = cudaFuncSetAttribute(dwconv_tile_kernel<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
   if (e != cudaSuccess) return (int)e;                                                                              \
-  dwconv_tile_kernel<E><<<blocks, kThreadsFe, smem, s>>>((const E*)x, ldx, w, (E*)y, ldy, N, H, W, C, flip,         \
-                                                        accumulate, tiles_x, tiles_y)
-  if (dtype == NERVECL_F32) { NV_DW_LAUNCH(float); } else { NV_DW_LAUNCH(bf16); }
+  dwconv_tile_kernel<E, A><<<blocks, kThreadsFe, smem, s>>>(tmx, w, (E*)y, ldy, N, H, W, C, flip, tiles_x, tiles_y)
+  if (dtype == NERVECL_F32) {
+    if (accumulate) { NV_DW_LAUNCH(float, true); } else { NV_DW_LAUNCH(float, false); }
+  } else {
+    if (accumulate) { NV_DW_LAUNCH(bf16, true); } else { NV_DW_LAUNCH(bf16, false); }
+  }
 #undef NV_DW_LAUNCH
   return launch_status();
 }
@@ -429,40 +472,50 @@ int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ld
 int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy, int dtype, float* dw, int N, int H, int W,
                        int C, cudaStream_t s) {
   const int TWp = kThreadsFe / (C >> 3);
-  const int tiles_x = (W + TWp - 1) / TWp, tiles_y = (H + DW_TH - 1) / DW_TH;
+  const int tiles_x = (W + TWp - 1) / TWp, tiles_y = (H + WG_TH - 1) / WG_TH;
   const int64_t ntiles = (int64_t)N * tiles_x * tiles_y;
   const int blocks = (int)imax(1, imin(ntiles, kSMs * 2));
   const size_t esz = dtype == NERVECL_F32 ? 4 : 2;
-  const size_t smem = imax((int64_t)(((size_t)(DW_TH + 2) * (TWp + 2) + (size_t)DW_TH * TWp) * C * esz), (int64_t)C * 9 * 4);
+  const size_t smem = imax((int64_t)(2 * ((size_t)(WG_TH + 2) * (TWp + 2) + (size_t)WG_TH * TWp) * C * esz), (int64_t)C * 9 * 4);
+  CUtensorMap tmx, tmd;
+  if (!encode_tile_map(&tmx, x, ldx, dtype, N, H, W, C, TWp + 2, WG_TH + 2) ||
+      !encode_tile_map(&tmd, dy, lddy, dtype, N, H, W, C, TWp, WG_TH))
+    return NERVECL_EUNSUPPORTED;
   cudaError_t e;
 #define NV_DW_LAUNCH(E)                                                                                              \
   e = cudaFuncSetAttribute(dwconv_wgrad_tile_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
   if (e != cudaSuccess) return (int)e;                                                                              \
-  dwconv_wgrad_tile_kernel<E><<<blocks, kThreadsFe, smem, s>>>((const E*)x, ldx, (const E*)dy, lddy, dw, N, H, W, C, \
-                                                              tiles_x, tiles_y)
+  dwconv_wgrad_tile_kernel<E><<<blocks, kThreadsFe, smem, s>>>(tmx, tmd, dw, N, H, W, C, tiles_x, tiles_y)
   if (dtype == NERVECL_F32) { NV_DW_LAUNCH(float); } else { NV_DW_LAUNCH(bf16); }
 #undef NV_DW_LAUNCH
   return launch_status();
 }
 
+bool bn_sums_fast_supported(int C, int64_t lda, int64_t ldb) {
+  const int cg = C >> 2;
+  return !(C & 3) && cg <= kThreadsFe && (cg & (cg - 1)) == 0 && !(lda & 3) && !(ldb & 3);
+}
+
 int bn_sums_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
                  const float* beta, int dtype, int C, int64_t npix, int groups, double* sums, cudaStream_t s) {
-  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 16), (kSMs * 2 * 2) / groups + 1));
-  dim3 grid(chunks, groups);
+  const int lanes = kThreadsFe / (C >> 2);
+  // one resident wave shared evenly by the groups; never more slabs than 64-pixel rounds
+  const int bpg = (int)imax(1, imin((kSMs * (dy ? 3 : 4)) / groups, cdiv(npix, (int64_t)lanes * 64)));
+  const int blocks = bpg * groups;
   const size_t smem = (size_t)C * 2 * sizeof(double);
   if (dy) {
-    NV_DISPATCH_DTYPE(dtype, E, (bn_sums_fast_kernel<E, true><<<grid, kThreadsFe, smem, s>>>(
-                                    (const E*)x, ldx, (const E*)dy, lddy, stat, gamma, beta, C, npix, sums)));
+    NV_DISPATCH_DTYPE(dtype, E, (bn_sums_fast_kernel<E, true, 4><<<blocks, kThreadsFe, smem, s>>>(
+                                    (const E*)x, ldx, (const E*)dy, lddy, stat, gamma, beta, C, npix, bpg, sums)));
   } else {
-    NV_DISPATCH_DTYPE(dtype, E, (bn_sums_fast_kernel<E, false><<<grid, kThreadsFe, smem, s>>>(
-                                    (const E*)x, ldx, nullptr, 0, nullptr, nullptr, nullptr, C, npix, sums)));
+    NV_DISPATCH_DTYPE(dtype, E, (bn_sums_fast_kernel<E, false, 8><<<blocks, kThreadsFe, smem, s>>>(
+                                    (const E*)x, ldx, nullptr, 0, nullptr, nullptr, nullptr, C, npix, bpg, sums)));
   }
   return launch_status();
 }
 
 int bn_relu_fwd_fast(const void* x, int64_t ldx, const float* stat, const float* gamma, const float* beta, const void* res,
                      int64_t ldres, void* y, int64_t ldy, int dtype, int C, int64_t npix, int groups, cudaStream_t s) {
-  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 4), (kSMs * 8) / groups + 1));
+  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 4), (kSMs * 3) / groups));
   dim3 grid(chunks, groups);
   NV_DISPATCH_DTYPE(dtype, E, (bn_relu_fwd_fast_kernel<E><<<grid, kThreadsFe, 0, s>>>((const E*)x, ldx, stat, gamma, beta,
                                                                                       (const E*)res, ldres, (E*)y, ldy, C,
@@ -473,7 +526,7 @@ int bn_relu_fwd_fast(const void* x, int64_t ldx, const float* stat, const float*
 int bn_bwd_apply_fast(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* stat, const float* gamma,
                       const float* beta, const double* bsums, void* dx, int64_t lddx, float* dgamma, float* dbeta, int dtype,
                       int C, int64_t npix, int groups, int training, cudaStream_t s) {
-  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 4), (kSMs * 8) / groups + 1));
+  const int chunks = (int)imax(1, imin(cdiv(npix * (C >> 3), kThreadsFe * 4), (kSMs * 3) / groups));
   dim3 grid(chunks, groups);
   NV_DISPATCH_DTYPE(dtype, E, (bn_bwd_apply_fast_kernel<E><<<grid, kThreadsFe, 0, s>>>(
                                   (const E*)x, ldx, (const E*)dy, lddy, stat, gamma, beta, bsums, (E*)dx, lddx, dgamma, dbeta,

@@ -38,9 +38,10 @@ def fwd_case(cin, cout, k, ld_in, ld_out, engines, accumulate=False, mask=False)
     res = []
     for eng in engines:
         try:
-            ms = bench(lambda: nv.conv2d_fwd(x[..., :cin], w, None if accumulate else bias, None,
+            plain = not accumulate and not mask
+            ms = bench(lambda: nv.conv2d_fwd(x[..., :cin], w, bias if plain else None, None,
                                              m[..., :cout] if mask else None, None, out[..., :cout], cout,
-                                             not accumulate, accumulate, 0, 0, 1.0, eng))
+                                             plain, accumulate, 0, 0, 1.0, eng))
             res.append(f"{ms:7.3f} ms {flops / ms / 1e9:7.1f} TF")
         except RuntimeError as e:
             res.append(f"unsupported ({str(e)[-30:]})")
@@ -81,6 +82,16 @@ if __name__ == "__main__":
         fwd_case(64, 32, 3, 256, 256, [ops.CONV_TC])
         fwd_case(192, 32, 3, 224, 224, [ops.CONV_TC])
         fwd_case(192, 32, 3, 256, 256, [ops.CONV_TC])
+    if which == "k1":
+        # 1x1 shapes of the step: LFF data gradient of the last dense layer (B images), extractor pointwise (T*B),
+        # LFF forward
+        print("engines: rows/auto | per-tap")
+        fwd_case(64, 32, 1, 64, 256, engines, accumulate=False, mask=True)
+        fwd_case(224, 64, 1, 256, 64, engines)
+        B_save = B
+        globals()["B"] = 3 * B_save
+        fwd_case(64, 64, 1, 64, 64, engines)
+        globals()["B"] = B_save
     if which in ("dgrad", "all"):
         for cout in (64, 96, 128, 160, 192):
             fwd_case(32, cout, 3, 224, 224, engines, accumulate=True, mask=True)

@@ -385,7 +385,10 @@ TC_SHAPES = [  # (N, H, W, Cin, Cout, K)
     # row-streaming kernel: merged N=192, two chunks, per-ky N=96 with a 5-slot ring, channel-group split,
     # 1/2-row tail segments, TMEM ring wrap (> 16 rows per item)
     (1, 20, 130, 64, 64, 3), (2, 7, 300, 128, 64, 3), (1, 5, 64, 32, 96, 3), (1, 40, 128, 192, 64, 3),
-    (1, 19, 140, 96, 128, 3), (1, 64, 128, 64, 32, 3), (1, 3, 640, 64, 48, 3), (1, 360, 640, 64, 32, 3),
+    (1, 19, 140, 96, 128, 3), (1, 64, 128, 64, 32, 3), (1, 3, 640, 64, 48, 3),
+    # 1x1 through the row-streaming kernel (centre tap only, zero-filled ky = 0 / 2 weight blocks)
+    (1, 20, 130, 64, 64, 1), (2, 9, 200, 64, 32, 1), (1, 16, 128, 128, 64, 1), (1, 12, 640, 32, 48, 1),
+    (1, 360, 640, 64, 32, 3),
 ]
 BF16_TOL = 6e-3
 
@@ -430,6 +433,28 @@ def test_conv_dgrad_tcgen05_accumulate_mask(shape):
     nv().conv2d_fwd(nhwc(dy, torch.bfloat16), pack(wt, torch.bfloat16, flip=True), None, None,
                     nhwc(act, torch.bfloat16), None, out, cin, False, True, 0, c0, 0.5, ops.CONV_TC)
     assert relerr(nchw(out), ref) <= BF16_TOL
+
+
+@pytest.mark.parametrize("k", [1, 3])
+@pytest.mark.parametrize("cout", [32, 64])
+def test_conv_rows_lean_epilogues(k, cout):
+    """The row kernel's lean epilogues (bias + ReLU -> bf16; alpha * acc gated by the ReLU mask) for 3x3 and 1x1."""
+    from nerve_cl_b200 import ops
+    n, h, w, cin = 2, 21, 200, 64
+    g = torch.Generator().manual_seed(5 * k + cout)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    act = bf(torch.randn(n, cout, h, w, generator=g))
+    xo, wp = nhwc(x, torch.bfloat16), pack(wt, torch.bfloat16)
+    out = torch.full((n, h, w, cout + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    nv().conv2d_fwd(xo, wp, b.cuda(), None, None, None, out[..., :cout], cout, True, False, 0, 0, 1.0, ops.CONV_TC)
+    assert relerr(nchw(out[..., :cout]), F.relu(F.conv2d(x, wt, b, 1, k // 2))) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
+    nv().conv2d_fwd(xo, wp, None, None, nhwc(act, torch.bfloat16), None, out[..., :cout], cout, False, False, 0, 0,
+                    0.25, ops.CONV_TC)
+    assert relerr(nchw(out[..., :cout]), 0.25 * F.conv2d(x, wt, None, 1, k // 2) * (act > 0)) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
 
 
 def test_conv_tc_matches_simt_bitwise_inputs():
