@@ -58,7 +58,7 @@ struct RowArgs : EpiArgs {
   int stages;       // ring depth in stages
   int slots;        // TMEM accumulator ring depth
   int merged;       // vertical taps merged into N
-  int fast;         // 1: epilogue is relu?(acc + bias?) -> bf16; 2: alpha * acc gated by the ReLU mask -> bf16 (lean paths)
+  int fast;         // lean epilogues -> bf16: 1: relu?(acc + bias?); 2: alpha * acc gated by the ReLU mask; 3: alpha * acc + res
   int dbg;          // NERVECL_ROWS_DBG bits (profiling only): 1 no MMAs, 2 no row loads, 4 no epilogue work
 };
 
@@ -300,7 +300,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       //      the epilogue the bottleneck of every small-K launch): whole 16-channel chunks, bf16 output, bias
       //      kept in registers, row pointers advanced instead of recomputed.  A thread owns chunk `part` and,
       //      for NOUT = 64, chunk part + 2.
-      const bool has0 = part < nch_all, two = part + 2 < nch_all;
+      const bool has0 = part < nch_all, two = !PF && part + 2 < nch_all;     // (PF kernels: NOUT <= 32)
       const int ch0 = c_lo + part * 16, ch1 = ch0 + 32;
       float bz0[16], bz1[16];
 #pragma unroll
@@ -322,6 +322,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int64_t ostride = (int64_t)a.W * a.ldo;
         const bf16* mp = a.mask + p0 * a.ldmask + ch0;
         const int64_t mstride = (int64_t)a.W * a.ldmask;
+        // second epilogue operand when it is not prefetched: the mask (fast 2, NOUT = 64) or the residual (fast 3)
+        const bf16* ep = a.fast == 3 ? a.res + p0 * a.ldres + ch0 : mp;
+        const int64_t estride = a.fast == 3 ? (int64_t)a.W * a.ldres : mstride;
         if (PF && valid && has0) {
 #pragma unroll
           for (int d = 0; d < 4; ++d)
@@ -342,6 +345,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               mqa[D] = m4[0];
               mqb[D] = m4[1];
             }
+            uint4 e0 = m0, e1 = m1, e2 = m0, e3 = m1;
+            if (!PF && a.fast >= 2 && valid && has0) {                 // issued before the wait: latency overlaps it
+              const uint4* e4 = reinterpret_cast<const uint4*>(ep);
+              e0 = e4[0];
+              e1 = e4[1];
+              if (two) { e2 = e4[4]; e3 = e4[5]; }
+            }
+            ep += estride;
             mbar_wait(&acc_full[slot], par);
             tc_fence_after();
             const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT + part * 16);
@@ -368,8 +379,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   }
                   store16(op + 32, f);
                 }
-              } else {                                               // fast == 2 (PF): alpha * acc where mask > 0
-                const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+              } else if (a.fast == 2) {                              // alpha * acc where mask > 0
+                const uint32_t mw[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float ml = __uint_as_float(mw[j] << 16), mh = __uint_as_float(mw[j] & 0xFFFF0000u);
@@ -377,6 +388,33 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   f[2 * j + 1] = mh > 0.f ? alpha * __uint_as_float(v0[2 * j + 1]) : 0.f;
                 }
                 store16(op, f);
+                if (two) {
+                  const uint32_t nw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float ml = __uint_as_float(nw[j] << 16), mh = __uint_as_float(nw[j] & 0xFFFF0000u);
+                    f[2 * j] = ml > 0.f ? alpha * __uint_as_float(v1[2 * j]) : 0.f;
+                    f[2 * j + 1] = mh > 0.f ? alpha * __uint_as_float(v1[2 * j + 1]) : 0.f;
+                  }
+                  store16(op + 32, f);
+                }
+              } else {                                               // fast == 3: alpha * acc + residual
+                const uint32_t rw[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[2 * j] = fmaf(alpha, __uint_as_float(v0[2 * j]), __uint_as_float(rw[j] << 16));
+                  f[2 * j + 1] = fmaf(alpha, __uint_as_float(v0[2 * j + 1]), __uint_as_float(rw[j] & 0xFFFF0000u));
+                }
+                store16(op, f);
+                if (two) {
+                  const uint32_t sw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    f[2 * j] = fmaf(alpha, __uint_as_float(v1[2 * j]), __uint_as_float(sw[j] << 16));
+                    f[2 * j + 1] = fmaf(alpha, __uint_as_float(v1[2 * j + 1]), __uint_as_float(sw[j] & 0xFFFF0000u));
+                  }
+                  store16(op + 32, f);
+                }
               }
             }
             op += ostride;
@@ -588,11 +626,12 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.x_center = a.K == 1;
   t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
   { const char* d = getenv("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
-  const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.res && !a.accumulate &&
-                     !a.mask_sub && !(t.dbg & 64);
+  const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.accumulate &&
+                     !a.mask_sub && p.NOUT <= 64 && !(t.dbg & 64);
   t.fast = 0;
-  if (whole && !a.mask && a.alpha == 1.0f && p.NOUT <= 64) t.fast = 1;
-  if (whole && a.mask && !a.bias && !a.relu && a.mask_c0 == 0 && p.NOUT <= 32) t.fast = 2;
+  if (whole && !a.res && !a.mask && a.alpha == 1.0f) t.fast = 1;
+  if (whole && !a.res && a.mask && !a.bias && !a.relu && a.mask_c0 == 0) t.fast = 2;
+  if (whole && a.res && a.res_channels >= a.Cout && !a.mask && !a.bias && !a.relu) t.fast = 3;
 
   const int64_t items = (int64_t)a.N * p.strips * p.segs;
   dim3 grid((unsigned)imin(items, imax(1, sms / p.nsplit)), (unsigned)p.nsplit);

@@ -455,6 +455,10 @@ def test_conv_rows_lean_epilogues(k, cout):
                     0.25, ops.CONV_TC)
     assert relerr(nchw(out[..., :cout]), 0.25 * F.conv2d(x, wt, None, 1, k // 2) * (act > 0)) <= BF16_TOL
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
+    nv().conv2d_fwd(xo, wp, None, nhwc(act, torch.bfloat16), None, None, out[..., :cout], cout, False, False, cout, 0,
+                    0.5, ops.CONV_TC)
+    assert relerr(nchw(out[..., :cout]), 0.5 * F.conv2d(x, wt, None, 1, k // 2) + act) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
 
 
 def test_conv_tc_matches_simt_bitwise_inputs():
