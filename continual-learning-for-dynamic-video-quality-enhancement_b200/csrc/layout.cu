@@ -64,6 +64,47 @@ NV_API int nervecl_pack_frames(const float* src, int64_t sB, int64_t sT, int64_t
   return launch_status();
 }
 
+// (B,T,C,H,W) strided fp32 -> [T][B][H][W][c*9 + tap] (3x3 unfold, zero padding); ldd % 8 == 0
+template <typename T>
+__global__ void pack_frames_unfold3_kernel(const float* __restrict__ src, int64_t sB, int64_t sT, int64_t sC,
+                                           int64_t sH, T* __restrict__ dst, int64_t ldd, int B, int Tn, int C,
+                                           int H, int W) {
+  int64_t total = (int64_t)Tn * B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    int64_t r = i / W;
+    int y = (int)(r % H);
+    r /= H;
+    int b = (int)(r % B);
+    int t = (int)(r / B);
+    const float* s = src + b * sB + t * sT;
+    T* d = dst + i * ldd;
+    for (int c8 = 0; c8 < (int)ldd; c8 += 8) {
+      f8 v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int col = c8 + k, c = col / 9, tap = col - c * 9;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        v.v[k] = (c < C && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(s + c * sC + yy * sH + xx) : 0.f;
+      }
+      st8(d + c8, v);
+    }
+  }
+}
+
+NV_API int nervecl_pack_frames_unfold3(const float* src, int64_t sB, int64_t sT, int64_t sC, int64_t sH,
+                                       void* dst, int64_t ldd, int dtype, int B, int T, int C, int H, int W,
+                                       nervecl_stream_t stream) {
+  if (!src || !dst || B <= 0 || T <= 0 || C <= 0 || H <= 0 || W <= 0 || ldd < 9 * C) return NERVECL_EINVAL;
+  if ((ldd & 7) || !aligned(dst, 16)) return NERVECL_EALIGN;
+  int64_t total = (int64_t)T * B * H * W;
+  int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
+  NV_DISPATCH_DTYPE(dtype, E, (pack_frames_unfold3_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  src, sB, sT, sC, sH, (E*)dst, ldd, B, T, C, H, W)));
+  return launch_status();
+}
+
 // ---------------------------------------------------------------------------------------
 // NHWC slice <-> NCHW fp32 via a 32x32 shared-memory transpose over (pixel, channel)
 // ---------------------------------------------------------------------------------------

@@ -224,6 +224,45 @@ __device__ __forceinline__ void stage_G(bf16* __restrict__ G, const bf16* __rest
   } else {
     // source-pixel major: pixel (y+i-4, sx) holds, in its 9 consecutive channels (8-i)*9 + u, the entries
     // G[px = sp - 8 + u][i*9 + 8 - u] of 9 neighbouring output pixels (sp = sx - x0 + 4)
+    if (vec_g) {
+      // one source pixel per loader thread, all nine vertical displacements: the 18 bytes of displacement row i
+      // start (8-i)*18 bytes into the pixel, i.e. inside two aligned 16-byte chunks -- two vector loads and
+      // compile-time half-word picks instead of nine 2-byte loads
+      const int sp = lt, sx = x0 - RAD + sp;
+#pragma unroll
+      for (int ib = 0; ib < ND; ib += 5) {
+        uint4 q0[5], q1[5];
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+          const int i = ib + ii;
+          q0[ii] = q1[ii] = make_uint4(0, 0, 0, 0);
+          if (i < ND) {
+            const int sy = y + i - RAD;
+            if (sp < PWU && sy >= 0 && sy < H && sx >= 0 && sx < W) {
+              const uint4* src = reinterpret_cast<const uint4*>(g + (((int64_t)n * H + sy) * W + sx) * ldg) + (((8 - i) * 18) >> 4);
+              q0[ii] = __ldg(src);
+              q1[ii] = __ldg(src + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+          const int i = ib + ii;
+          if (i < ND && sp < PWU) {
+            const uint32_t w[8] = {q0[ii].x, q0[ii].y, q0[ii].z, q0[ii].w, q1[ii].x, q1[ii].y, q1[ii].z, q1[ii].w};
+            const int sh = (((8 - i) * 18) & 15) >> 1;          // first half-word inside the two chunks
+#pragma unroll
+            for (int u = 0; u < ND; ++u) {
+              const int h = sh + u;
+              const uint16_t val = (uint16_t)((h & 1) ? (w[h >> 1] >> 16) : (w[h >> 1] & 0xFFFFu));
+              const int px = sp - 8 + u;
+              if (px >= 0 && px < TW) G[px * GPITCH + i * ND + 8 - u] = __ushort_as_bfloat16(val);
+            }
+          }
+        }
+      }
+      return;
+    }
     uint16_t v[GQ][ND];
 #pragma unroll
     for (int k = 0; k < GQ; ++k) {

@@ -60,6 +60,7 @@ nv = _OpsProxy()
 GROWTH = 32      # ResidualDenseBlock growth rate  (super_resolution.py:215)
 RDB_LAYERS = 5   # (super_resolution.py:216)
 CORR_CH = 81     # (2*4+1)^2 displacements          (super_resolution.py:73)
+HEAD_UNFOLD = 32 # unfolded 3x3 RGB neighbourhood: 27 live channels padded to two 16-channel MMA k-steps
 CORR_PAD = 96    # correlation volume is stored with 96 channels (zeros beyond 81): 16-byte aligned rows
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
@@ -135,7 +136,7 @@ class Activations:
         def act(n, c, dtype=adt):
             return torch.empty((n, H, W, c), device=dev, dtype=dtype)
 
-        self.x_in = act(T * B, 16)             # RGB + 13 zero channels: one 16-channel MMA k-step per tap, TMA-addressable
+        self.x_in = act(T * B, HEAD_UNFOLD)    # RGB 3x3 neighbourhoods unfolded into 27 (+5 zero) channels: the head conv is 1x1
         self.head = act(T * B, F)
         self.dwo = [act(T * B, F) for _ in range(3)]
         self.pwo = [act(T * B, F) for _ in range(3)]
@@ -190,7 +191,8 @@ class Plan:
         def add(name, cin, cout, k, bias=True, cin_pad=None):
             cs[name] = ConvSpec(name, cin, cout, k, bias, cin_pad)
 
-        add("feature_extractor.head.0", 3, F, 3, cin_pad=16)
+        # the 3-channel 3x3 head runs as a 1x1 conv over the unfolded frames (nervecl_pack_frames_unfold3)
+        add("feature_extractor.head.0", 27, F, 1, cin_pad=HEAD_UNFOLD)
         for j in range(3):
             add(f"feature_extractor.body.{j}.pointwise", F, F, 1, bias=False)
         add("motion_estimator.flow_net.0", CORR_CH, 128, 3, cin_pad=CORR_PAD)
@@ -245,6 +247,8 @@ class Plan:
         ws, ds, fl = [], [], []
         for name in self.convs:
             w = P[name + ".weight"]
+            if name == "feature_extractor.head.0":
+                w = w.view(w.shape[0], -1, 1, 1)           # OIHW flattening == unfolded channel order c*9 + tap
             ws.append(w); ds.append(self.wf[name]); fl.append(False)
             if need_bwd and name in self.wb:
                 ws.append(w); ds.append(self.wb[name]); fl.append(True)
@@ -327,7 +331,7 @@ class Plan:
         self.pack_weights(P, need_bwd)
 
         # ---- feature extractor over all T*B frames (super_resolution.py:346-349) ----
-        nv.pack_frames(lr_frames, A.x_in)
+        nv.pack_frames_unfold3(lr_frames, A.x_in)
         self.conv("feature_extractor.head.0", A.x_in, A.head, P, relu=True)
         x = A.head
         for j in range(3):
@@ -592,10 +596,8 @@ class Plan:
                 # extractor skip (feat = body(head) + head): d(head) = d(feat) + depthwise data gradient
                 nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], ws["dfeat"], True, True)
         nv.relu_bwd(ws["dfeat"], A.head, None, ws["t"][0])
-        if self.adt == torch.bfloat16 and self.engine != CONV_SIMT and W >= 64:
-            with self._span("conv_wgrad", A.x_in[..., :3], 3, F, 3):
-                nv.conv3x3_wgrad_grouped(A.x_in, ws["t"][0], [G["feature_extractor.head.0.weight"]],
-                                         [G["feature_extractor.head.0.bias"]], [0], 1.0)
-        else:
-            self.wgrad("feature_extractor.head.0", A.x_in[..., :3], ws["t"][0], G)
+        gw = G["feature_extractor.head.0.weight"]
+        with self._span("conv_wgrad", A.x_in, 27, F, 1):
+            nv.conv2d_wgrad(A.x_in[..., :27], ws["t"][0], gw.view(gw.shape[0], -1, 1, 1),
+                            G["feature_extractor.head.0.bias"], 1.0, self.engine)
         ready("feature_extractor.")

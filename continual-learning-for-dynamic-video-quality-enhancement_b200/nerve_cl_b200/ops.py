@@ -109,6 +109,24 @@ def _pack_frames(src: Tensor, dst: Tensor) -> None:
                "pack_frames")
 
 
+@_op("pack_frames_unfold3(Tensor src, Tensor(a!) dst) -> ()")
+def _pack_frames_unfold3(src: Tensor, dst: Tensor) -> None:
+    """src (B,T,C,H,W) fp32 -> dst [T*B,H,W,Cpad>=9C]: the 3x3 neighbourhood of every pixel unfolded into
+    channels c*9 + ky*3 + kx (zero outside the frame), padding zeroed (see ``nervecl_pack_frames_unfold3``)."""
+    _cuda(src, "src")
+    if src.dim() != 5 or src.dtype != torch.float32:
+        raise RuntimeError("nervecl.pack_frames_unfold3: src must be (B,T,C,H,W) float32")
+    if src.stride(4) != 1:
+        src = src.contiguous()
+    b, t, c, h, w = src.shape
+    dp, ld, n, dh, dw, dc = _nhwc(dst, "dst")
+    if (n, dh, dw) != (t * b, h, w) or dc < 9 * c or ld != dc:
+        raise RuntimeError("nervecl.pack_frames_unfold3: dst must be contiguous [T*B,H,W,Cpad] with Cpad >= 9*C")
+    _lib.check(_lib.load().nervecl_pack_frames_unfold3(src.data_ptr(), src.stride(0), src.stride(1), src.stride(2),
+                                                      src.stride(3), dp, ld, _dt(dst), b, t, c, h, w, _stream()),
+               "pack_frames_unfold3")
+
+
 @_op("nhwc_to_nchw(Tensor src, Tensor(a!) dst) -> ()")
 def _nhwc_to_nchw(src: Tensor, dst: Tensor) -> None:
     sp, ld, n, h, w, c = _nhwc(src, "src")

@@ -69,6 +69,15 @@ int nervecl_pack_frames(const float* src, int64_t sB, int64_t sT, int64_t sC, in
                         void* dst, int64_t ldd, int dtype, int B, int T, int C, int H, int W,
                         nervecl_stream_t stream);
 
+/* Same frames, unfolded for the 3x3 head convolution (feature_extractor.head.0, super_resolution.py:40):
+ *   dst[t][b][y][x][c*9 + ky*3 + kx] = src[b][t][c][y+ky-1][x+kx-1]   (zero outside the frame),
+ * channels 9C..ldd-1 zero.  The column order is the OIHW flattening of the filter, so the head conv is a
+ * 1x1 convolution with weight.view(Cout, 9C) over this buffer and its weight gradient a 1x1 weight gradient
+ * (a 3-channel 3x3 filter wastes > 80 % of every 16-channel MMA k-step; 27 of 32 unfolded channels are live). */
+int nervecl_pack_frames_unfold3(const float* src, int64_t sB, int64_t sT, int64_t sC, int64_t sH,
+                                void* dst, int64_t ldd, int dtype, int B, int T, int C, int H, int W,
+                                nervecl_stream_t stream);
+
 /* NHWC (dtype) channel slice -> NCHW fp32 contiguous.  Used only to hand intermediates back to
  * Python for return_intermediate=True (super_resolution.py:384-389) and by tests. */
 int nervecl_nhwc_to_nchw(const void* src, int64_t ld, int dtype, float* dst,

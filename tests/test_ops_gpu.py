@@ -378,6 +378,23 @@ def test_ops_reject_cpu_tensors():
 # tcgen05 implicit-GEMM engine (bf16): same contract as the SIMT engine, checked against fp32 ATen on
 # bf16-rounded operands (error budget: fp32 accumulation order + one bf16 rounding of the output)
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pack_frames_unfold3(dtype):
+    """3x3 unfold of strided (B,T,C,H,W) frames into channels c*9 + tap (== the OIHW filter flattening)."""
+    g = torch.Generator().manual_seed(3)
+    b, t, c, h, w = 2, 3, 3, 13, 37
+    big = torch.randn(b, t, c, h + 2, w + 5, generator=g).cuda()
+    src = big[:, :, :, 1:h + 1, 2:w + 2]                       # non-contiguous rows / frames
+    dst = torch.full((t * b, h, w, 32), 9.0, device="cuda", dtype=dtype)
+    nv().pack_frames_unfold3(src, dst)
+    ref = F.unfold(src.permute(1, 0, 2, 3, 4).reshape(t * b, c, h, w), 3, padding=1)      # [TB, c*9, h*w]
+    ref = ref.view(t * b, 27, h, w).permute(0, 2, 3, 1)
+    if dtype == torch.bfloat16:
+        ref = ref.bfloat16()
+    assert torch.equal(dst[..., :27].float(), ref.float())
+    assert float(dst[..., 27:].float().abs().max()) == 0.0
+
+
 TC_SHAPES = [  # (N, H, W, Cin, Cout, K)
     (1, 16, 128, 64, 32, 3), (2, 20, 72, 96, 32, 3), (1, 9, 200, 192, 32, 3), (1, 24, 40, 64, 64, 3),
     (1, 16, 64, 224, 64, 1), (1, 12, 136, 32, 192, 3), (2, 8, 16, 128, 64, 3), (1, 33, 65, 96, 128, 3),
