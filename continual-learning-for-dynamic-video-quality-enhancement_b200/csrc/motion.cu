@@ -214,10 +214,23 @@ __device__ __forceinline__ void atomic_add8(float* p, float w, const f8& g) {
   atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(w * g.v[4], w * g.v[5], w * g.v[6], w * g.v[7]));
 }
 
-template <typename T>
+// 8 consecutive bf16 accumulations as ONE 128-bit packed reduction (red.global.add.noftz.v4.bf16x2): half the
+// L2 reduction operations of the fp32 form, which is what bounds the scatter (one 16-byte RED per L2 slice clock)
+__device__ __forceinline__ void atomic_add8(bf16* p, float w, const f8& g) {
+  uint32_t r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(w * g.v[2 * i], w * g.v[2 * i + 1]);
+    r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
+template <typename T, typename AT>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow,
-                const T* __restrict__ dout, int64_t lddo, float* __restrict__ dfeat, int64_t lddf,
+                const T* __restrict__ dout, int64_t lddo, AT* __restrict__ dfeat, int64_t lddf,
                 float* __restrict__ dflow, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode) {
   // grid = (N*H rows, pixel groups of a row); the C/8 threads of a pixel are adjacent lanes
   const int cg = C >> 3;
@@ -244,7 +257,7 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
       f8 g = ld8(dout + p * lddo + c0);
       int64_t q = img + (int64_t)c.y0 * W + c.x0;
       const T* fb = feat + q * ldf_ + c0;
-      float* db = dfeat + q * lddf + c0;
+      AT* db = dfeat + q * lddf + c0;
       if (yin0 && xin0) {
         f8 v = ld8(fb);
         atomic_add8(db, wnw, g);
@@ -351,21 +364,40 @@ NV_API int nervecl_warp_fwd(const void* feat, int64_t ldf, const float* flow, vo
   return launch_status();
 }
 
-NV_API int nervecl_warp_bwd(const void* feat, int64_t ldf, const float* flow, const void* dout, int64_t lddo,
-                            float* dfeat, int64_t lddf, float* dflow, int dtype, int N, int H, int W, int C,
-                            int div_mode, nervecl_stream_t stream) {
+static int warp_bwd_launch(const void* feat, int64_t ldf, const float* flow, const void* dout, int64_t lddo,
+                           void* dfeat, int64_t lddf, int dfeat_dtype, float* dflow, int dtype, int N, int H, int W, int C,
+                           int div_mode, nervecl_stream_t stream) {
   if (!feat || !flow || !dout || !dfeat || !dflow) return NERVECL_EINVAL;
   int rc = warp_check(N, H, W, C);
   if (rc) return rc;
-  if ((ldf & 7) || (lddo & 7) || (lddf & 3) || !aligned(feat, 16) || !aligned(dout, 16) || !aligned(dfeat, 16) ||
-      !aligned(flow, 8) || !aligned(dflow, 8))
+  if (dfeat_dtype != NERVECL_F32 && !(dfeat_dtype == NERVECL_BF16 && dtype == NERVECL_BF16)) return NERVECL_EDTYPE;
+  if ((ldf & 7) || (lddo & 7) || (lddf & (dfeat_dtype == NERVECL_F32 ? 3 : 7)) || !aligned(feat, 16) || !aligned(dout, 16) ||
+      !aligned(dfeat, 16) || !aligned(flow, 8) || !aligned(dflow, 8))
     return NERVECL_EALIGN;
   float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
   const int ppb = 256 / (C >> 3);
   if (cdiv(W, ppb) > 65535 || (int64_t)N * H > 0x7fffffff) return NERVECL_EUNSUPPORTED;
   dim3 blocks((unsigned)((int64_t)N * H), (unsigned)cdiv(W, ppb));
-  NV_DISPATCH_DTYPE(dtype, E, (warp_bwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
-                                  (const E*)feat, ldf, flow, (const E*)dout, lddo, dfeat, lddf, dflow, N, H, W, C,
+  if (dfeat_dtype == NERVECL_BF16) {
+    warp_bwd_kernel<bf16, bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)feat, ldf, flow, (const bf16*)dout, lddo,
+                                                                       (bf16*)dfeat, lddf, dflow, N, H, W, C, inv_w, inv_h,
+                                                                       div_mode);
+    return launch_status();
+  }
+  NV_DISPATCH_DTYPE(dtype, E, (warp_bwd_kernel<E, float><<<blocks, 256, 0, as_stream(stream)>>>(
+                                  (const E*)feat, ldf, flow, (const E*)dout, lddo, (float*)dfeat, lddf, dflow, N, H, W, C,
                                   inv_w, inv_h, div_mode)));
   return launch_status();
+}
+
+NV_API int nervecl_warp_bwd(const void* feat, int64_t ldf, const float* flow, const void* dout, int64_t lddo,
+                            float* dfeat, int64_t lddf, float* dflow, int dtype, int N, int H, int W, int C,
+                            int div_mode, nervecl_stream_t stream) {
+  return warp_bwd_launch(feat, ldf, flow, dout, lddo, dfeat, lddf, NERVECL_F32, dflow, dtype, N, H, W, C, div_mode, stream);
+}
+
+NV_API int nervecl_warp_bwd_lp(const void* feat, int64_t ldf, const float* flow, const void* dout, int64_t lddo,
+                               void* dfeat, int64_t lddf, float* dflow, int dtype, int N, int H, int W, int C,
+                               int div_mode, nervecl_stream_t stream) {
+  return warp_bwd_launch(feat, ldf, flow, dout, lddo, dfeat, lddf, dtype, dflow, dtype, N, H, W, C, div_mode, stream);
 }

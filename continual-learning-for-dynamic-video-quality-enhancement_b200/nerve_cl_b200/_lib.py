@@ -71,6 +71,8 @@ _SIGNATURES = {
     "nervecl_warp_fwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp],
     "nervecl_warp_bwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                          c_i32, c_vp],
+    "nervecl_warp_bwd_lp": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
+                         c_i32, c_vp],
     "nervecl_tfuse_fwd": [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp],
     "nervecl_tfuse_bwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i64, c_i32,
                           c_i32, c_vp],

@@ -557,9 +557,14 @@ class Plan:
         nv.axpy(dcat[..., self.mid * F:(self.mid + 1) * F], dfeat[self.mid], 1.0, False)
         nv.axpy(ws["dfused"], dfeat[self.mid], 1.0, True)        # gff skip: fused = relu(..) + centre
         for t in self.others:
-            nv.fill_zero(ws["dfeat32"])
-            nv.warp_bwd(feat[t], A.flow[t], dcat[..., t * F:(t + 1) * F], ws["dfeat32"], ws["dflow"], self.div_mode)
-            nv.axpy(ws["dfeat32"], dfeat[t], 1.0, False)
+            if self.adt == torch.bfloat16:
+                # scatter straight into the bf16 gradient (packed 8 x bf16 reductions): no fp32 staging round trip
+                nv.fill_zero(dfeat[t])
+                nv.warp_bwd_lp(feat[t], A.flow[t], dcat[..., t * F:(t + 1) * F], dfeat[t], ws["dflow"], self.div_mode)
+            else:
+                nv.fill_zero(ws["dfeat32"])
+                nv.warp_bwd(feat[t], A.flow[t], dcat[..., t * F:(t + 1) * F], ws["dfeat32"], ws["dflow"], self.div_mode)
+                nv.axpy(ws["dfeat32"], dfeat[t], 1.0, False)
             dflow = ws["dflow_a"][..., :2]
             nv.axpy(ws["dflow"], dflow, 1.0, False)
             self.wgrad("motion_estimator.flow_net.6", A.fn3[t], dflow, G, dy_padded=ws["dflow_a"])

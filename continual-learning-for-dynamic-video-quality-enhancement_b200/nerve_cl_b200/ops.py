@@ -388,6 +388,18 @@ def _warp_bwd(feat, flow, dout, dfeat, dflow, div_mode) -> None:
                                            _dt(feat), n, h, w, c, div_mode, _stream()), "warp_bwd")
 
 
+@_op("warp_bwd_lp(Tensor feat, Tensor flow, Tensor dout, Tensor(a!) dfeat, Tensor(b!) dflow, int div_mode) -> ()")
+def _warp_bwd_lp(feat, flow, dout, dfeat, dflow, div_mode) -> None:
+    """``warp_bwd`` accumulating into ``dfeat`` of the activation dtype (packed bf16 reductions)."""
+    pf, ldf, n, h, w, c = _nhwc(feat, "feat")
+    pg, ldg, *_ = _nhwc(dout, "dout")
+    pd, ldd, *_ = _nhwc(dfeat, "dfeat")
+    if dfeat.dtype != feat.dtype:
+        raise RuntimeError("nervecl.warp_bwd_lp: dfeat must have the activation dtype")
+    _lib.check(_lib.load().nervecl_warp_bwd_lp(pf, ldf, _flat(flow, "flow"), pg, ldg, pd, ldd, _flat(dflow, "dflow"),
+                                              _dt(feat), n, h, w, c, div_mode, _stream()), "warp_bwd_lp")
+
+
 # --------------------------------------------------------------------------------------------
 # temporal fusion + CBAM
 # --------------------------------------------------------------------------------------------

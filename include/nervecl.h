@@ -237,6 +237,12 @@ int nervecl_warp_fwd(const void* feat, int64_t ldf, const float* flow, void* out
 int nervecl_warp_bwd(const void* feat, int64_t ldf, const float* flow, const void* dout,
                      int64_t lddo, float* dfeat, int64_t lddf, float* dflow, int dtype, int N,
                      int H, int W, int C, int div_mode, nervecl_stream_t stream);
+/* Same, with dfeat in the ACTIVATION dtype: for bf16 the scatter uses packed 8 x bf16 reductions (half the L2
+ * reduction traffic of the fp32 form; every partial sum is rounded to bf16).  fp32 activations: identical to
+ * nervecl_warp_bwd. */
+int nervecl_warp_bwd_lp(const void* feat, int64_t ldf, const float* flow, const void* dout,
+                        int64_t lddo, void* dfeat, int64_t lddf, float* dflow, int dtype, int N,
+                        int H, int W, int C, int div_mode, nervecl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Temporal fusion: softmax over the T logits + attention-weighted sum of the T aligned feature

@@ -267,6 +267,24 @@ def test_warp_backward():
     assert relerr(fb.grad, b.grad) <= TOL
 
 
+def test_warp_backward_bf16_packed_reductions():
+    """warp_bwd_lp scatters into a bf16 gradient with packed 8 x bf16 reductions: same result as the fp32 scatter
+    of the same bf16 operands up to bf16 rounding of the (<= ~8) partial sums per element."""
+    g = torch.Generator().manual_seed(19)
+    n, c, h, w = 2, 64, 21, 70
+    feat = nhwc(torch.randn(n, c, h, w, generator=g), torch.bfloat16)
+    dy = nhwc(torch.randn(n, c, h, w, generator=g), torch.bfloat16)
+    flow = (1.7 * torch.randn(n, h, w, 2, generator=g) + 0.013).cuda()
+    d32 = torch.zeros((n, h, w, c), device="cuda")
+    dfl32 = torch.zeros_like(flow)
+    nv().warp_bwd(feat, flow, dy, d32, dfl32, 0)
+    d16 = torch.zeros((n, h, w, c), device="cuda", dtype=torch.bfloat16)
+    dfl16 = torch.zeros_like(flow)
+    nv().warp_bwd_lp(feat, flow, dy, d16, dfl16, 0)
+    assert relerr(d16.float(), d32) <= 1e-2
+    assert torch.equal(dfl16, dfl32)
+
+
 def test_temporal_fusion():
     T, B, C, H, W = 3, 2, 16, 7, 9
     g = torch.Generator().manual_seed(10)
