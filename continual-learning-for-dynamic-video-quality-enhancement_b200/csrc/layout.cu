@@ -105,6 +105,63 @@ NV_API int nervecl_pack_frames_unfold3(const float* src, int64_t sB, int64_t sT,
   return launch_status();
 }
 
+// dst[p][o*9 + tap] = src[p - tap offset][o]: gradient-side unfold of a narrow tensor (C <= 3), ldd % 8 == 0
+template <typename TS, typename TD, bool VEC>
+__global__ void unfold3_grad_kernel(const TS* __restrict__ src, int64_t lds, int C, TD* __restrict__ dst, int64_t ldd,
+                                    int N, int H, int W) {
+  int64_t total = (int64_t)N * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int64_t r = i / W;
+    const int y = (int)(r % H);
+    float v[3][9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const TS* sp = src + (i + (int64_t)(yy - y) * W + (xx - x)) * lds;
+      if (VEC) {                                           // bf16, 8-byte aligned pixels: one load per neighbour
+        const f4 q = ok ? ld4(sp) : f4{{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int o = 0; o < 3; ++o) v[o][tap] = o < C ? q.v[o] : 0.f;
+      } else {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) v[o][tap] = (ok && o < C) ? ldf(sp + o) : 0.f;
+      }
+    }
+    TD* d = dst + i * ldd;
+#pragma unroll
+    for (int c8 = 0; c8 < 32; c8 += 8) {                   // (ldd <= 32; static columns: no dynamic register indexing)
+      if (c8 >= (int)ldd) break;
+      f8 o8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int col = c8 + k;
+        o8.v[k] = col < 27 ? v[col / 9][col % 9] : 0.f;
+      }
+      st8(d + c8, o8);
+    }
+  }
+}
+
+NV_API int nervecl_unfold3_grad(const void* src, int64_t lds, int src_dtype, int C, void* dst, int64_t ldd,
+                                int dst_dtype, int N, int H, int W, nervecl_stream_t stream) {
+  if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > 3 || lds < C || ldd < 9 * C || ldd > 32) return NERVECL_EINVAL;
+  if ((ldd & 7) || !aligned(dst, 16)) return NERVECL_EALIGN;
+  const int64_t total = (int64_t)N * H * W;
+  const int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
+  cudaStream_t s = as_stream(stream);
+#define NV_UNF(TS, TD, V) unfold3_grad_kernel<TS, TD, V><<<blocks, 256, 0, s>>>((const TS*)src, lds, C, (TD*)dst, ldd, N, H, W)
+  if (src_dtype == NERVECL_F32 && dst_dtype == NERVECL_F32) NV_UNF(float, float, false);
+  else if (src_dtype == NERVECL_F32 && dst_dtype == NERVECL_BF16) NV_UNF(float, bf16, false);
+  else if (src_dtype == NERVECL_BF16 && dst_dtype == NERVECL_BF16) {
+    if (lds >= 4 && !(lds & 3) && aligned(src, 8)) NV_UNF(bf16, bf16, true); else NV_UNF(bf16, bf16, false);
+  } else return NERVECL_EDTYPE;
+#undef NV_UNF
+  return launch_status();
+}
+
 // ---------------------------------------------------------------------------------------
 // NHWC slice <-> NCHW fp32 via a 32x32 shared-memory transpose over (pixel, channel)
 // ---------------------------------------------------------------------------------------

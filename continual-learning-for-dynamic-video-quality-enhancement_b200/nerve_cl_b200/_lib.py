@@ -45,6 +45,7 @@ _SIGNATURES = {
                             c_vp],
     "nervecl_pack_frames_unfold3": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                             c_vp],
+    "nervecl_unfold3_grad": [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_nhwc_to_nchw": [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_nchw_to_nhwc": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_pack_conv_weight": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],

@@ -309,8 +309,25 @@ class Plan:
         """``dy_padded``: the zero-padded (>= 16 channel) buffer ``dy`` is a prefix view of, for the small-Cout
         convs -- lets the row-resident tcgen05 weight gradient take them (it masks the unused columns)."""
         c = self.convs[name]
-        if (dy_padded is not None and c.k == 3 and self.adt == torch.bfloat16 and self.engine != CONV_SIMT
-                and self.W >= 64 and x.shape[-1] >= 16):
+        tc3 = (dy_padded is not None and c.k == 3 and self.adt == torch.bfloat16 and self.engine != CONV_SIMT
+               and self.W >= 64 and x.shape[-1] >= 16)
+        if tc3 and c.cout <= 3 and x.shape[-1] % 8 == 0 and x.shape[-1] <= 64:
+            # 2-3 output channels: unfold dy (9 shifted copies per channel) and take ONE 1x1 weight-gradient GEMM
+            # dW1[o*9+tap, c] = sum_q U[q, o*9+tap] x[q, c]; its centre-tap columns' sums are the bias gradient
+            ws = self._workspace()
+            cin = x.shape[-1]
+            nv.unfold3_grad(dy, ws["unf"])
+            tw = ws["wg_tmp"][:32 * cin].view(32, cin, 1, 1)
+            tb = ws["wg_tmp"][32 * 64:32 * 64 + 32]
+            nv.fill_zero(ws["wg_tmp"])
+            with self._span("conv_wgrad", x, cin, dy.shape[-1], c.k):
+                nv.conv2d_wgrad(x, ws["unf"], tw, tb, scale, self.engine)
+            o = c.cout
+            G[name + ".weight"].view(o, cin, 9).add_(tw.view(32, cin)[:o * 9].view(o, 9, cin).transpose(1, 2))
+            if c.has_bias:
+                G[name + ".bias"].add_(tb[:o * 9].view(o, 9)[:, 4])
+            return
+        if tc3:
             with self._span("conv_wgrad", x, x.shape[-1], dy.shape[-1], c.k):
                 nv.conv3x3_wgrad_grouped(x, dy_padded, [G[name + ".weight"]],
                                          [G[name + ".bias"]] if c.has_bias else [], [0], scale)
@@ -425,6 +442,8 @@ class Plan:
             ws["dfeat32"] = act(B, F, f32)
             ws["dflow"] = act(B, 2, f32)
             ws["dflow_a"] = torch.zeros((B, H, W, 16), device=dev, dtype=adt)
+            ws["unf"] = torch.zeros((B, H, W, 32), device=dev, dtype=adt)           # unfolded 2-3 channel gradients
+            ws["wg_tmp"] = torch.zeros(32 * 64 + 32, device=dev, dtype=f32)         # their 1x1 weight / bias gradients
             ws["dfn3"], ws["dfn2"], ws["dfn1"] = act(B, 32), act(B, 64), act(B, 128)
             ws["dcorr"] = act(B, CORR_PAD)
             ws["t"] = [act(T * B, F) for _ in range(3)]

@@ -127,6 +127,18 @@ def _pack_frames_unfold3(src: Tensor, dst: Tensor) -> None:
                "pack_frames_unfold3")
 
 
+@_op("unfold3_grad(Tensor src, Tensor(a!) dst) -> ()")
+def _unfold3_grad(src: Tensor, dst: Tensor) -> None:
+    """dst[p, o*9 + tap] = src[p - tap offset, o] for a narrow NHWC ``src`` (<= 3 channels), see
+    ``nervecl_unfold3_grad``; ``dst`` is contiguous [N,H,W,Cpad >= 9*C], padding zeroed."""
+    sp, lds, n, h, w, c = _nhwc(src, "src")
+    dp, ldd, dn, dh, dw, dc = _nhwc(dst, "dst")
+    if (dn, dh, dw) != (n, h, w) or ldd != dc:
+        raise RuntimeError("nervecl.unfold3_grad: dst must be contiguous [N,H,W,Cpad] matching src")
+    _lib.check(_lib.load().nervecl_unfold3_grad(sp, lds, _dt(src), c, dp, ldd, _dt(dst), n, h, w, _stream()),
+               "unfold3_grad")
+
+
 @_op("nhwc_to_nchw(Tensor src, Tensor(a!) dst) -> ()")
 def _nhwc_to_nchw(src: Tensor, dst: Tensor) -> None:
     sp, ld, n, h, w, c = _nhwc(src, "src")

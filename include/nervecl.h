@@ -78,6 +78,14 @@ int nervecl_pack_frames_unfold3(const float* src, int64_t sB, int64_t sT, int64_
                                 void* dst, int64_t ldd, int dtype, int B, int T, int C, int H, int W,
                                 nervecl_stream_t stream);
 
+/* Gradient-side 3x3 unfold of a narrow NHWC tensor (C <= 3 live channels of pitch lds):
+ *   dst[n][y][x][o*9 + ky*3 + kx] = src[n][y-(ky-1)][x-(kx-1)][o]   (zero outside the image), columns 9C..ldd-1 zero.
+ * With it the weight gradient of a 3x3 conv with 2-3 OUTPUT channels (flow_net.6, attention.4) is one 1x1
+ * weight-gradient GEMM  dW[o][c][tap] = sum_q x[q][c] * dst[q][o*9+tap]  instead of nine taps of an MMA whose
+ * N dimension is 87 % padding; column o*9+4 (the centre tap) sums to the bias gradient. */
+int nervecl_unfold3_grad(const void* src, int64_t lds, int src_dtype, int C, void* dst, int64_t ldd,
+                         int dst_dtype, int N, int H, int W, nervecl_stream_t stream);
+
 /* NHWC (dtype) channel slice -> NCHW fp32 contiguous.  Used only to hand intermediates back to
  * Python for return_intermediate=True (super_resolution.py:384-389) and by tests. */
 int nervecl_nhwc_to_nchw(const void* src, int64_t ld, int dtype, float* dst,

@@ -413,6 +413,26 @@ def test_pack_frames_unfold3(dtype):
     assert float(dst[..., 27:].float().abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("c", [2, 3])
+def test_unfold3_grad_gives_small_cout_weight_gradient(c):
+    """dW of a 3x3 conv with 2-3 output channels == x^T unfold3_grad(dy), bias gradient == its centre-tap columns."""
+    g = torch.Generator().manual_seed(30 + c)
+    n, cin, h, w = 2, 8, 11, 19
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(c, cin, 3, 3, generator=g, requires_grad=True)
+    dy = torch.randn(n, c, h, w, generator=g)
+    F.conv2d(x, wt, None, 1, 1).backward(dy)
+    src = nhwc(dy, torch.float32, pad_to=16)[..., :c]
+    unf = torch.full((n, h, w, 32), 5.0, device="cuda")
+    nv().unfold3_grad(src, unf)
+    xm = nhwc(x).reshape(-1, cin)
+    dw1 = unf.reshape(-1, 32).t() @ xm                                   # [o*9+tap, cin]
+    dw = dw1[:c * 9].view(c, 9, cin).transpose(1, 2).reshape(c, cin, 3, 3)
+    assert relerr(dw, wt.grad) <= TOL
+    assert relerr(unf.reshape(-1, 32).sum(0)[:c * 9].view(c, 9)[:, 4], dy.sum((0, 2, 3))) <= TOL
+    assert float(unf[..., c * 9:].abs().max()) == 0.0
+
+
 TC_SHAPES = [  # (N, H, W, Cin, Cout, K)
     (1, 16, 128, 64, 32, 3), (2, 20, 72, 96, 32, 3), (1, 9, 200, 192, 32, 3), (1, 24, 40, 64, 64, 3),
     (1, 16, 64, 224, 64, 1), (1, 12, 136, 32, 192, 3), (2, 8, 16, 128, 64, 3), (1, 33, 65, 96, 128, 3),
