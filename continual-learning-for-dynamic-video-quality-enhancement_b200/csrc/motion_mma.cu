@@ -30,7 +30,15 @@ constexpr int ROWCH = PW * 8;        // 16-byte chunks per ring row (gradient ke
 constexpr int ROWCH_F = PWU * 8;     // forward kernel: no pad needed (k < 24)
 constexpr int RING = 9;
 constexpr int NT = 128;
-constexpr int GPITCH = 98;           // bf16 per staged G pixel: 196 B keeps 16-pixel strides off one bank
+// Staged gradient row G[px][i][j] (gradient kernels): 10 half-words per vertical displacement i (9 + 1 unused)
+// and an ODD pixel pitch, so that the two band entries (j0, j0+1) an A-fragment register needs are ALWAYS one
+// aligned 32-bit word: (px*GP + i*GS + k - px) has the parity of k = 2*tig + {0,8,16,24}.  Entries outside the
+// band (j0 = -1 or j0+1 = 9 at the band edge) are masked with a per-slot constant instead of zero padding.
+constexpr int GS = 10;               // half-words per displacement row
+constexpr int GP = 91;               // half-words per pixel (9*GS + 1)
+constexpr int GFRONT = 2;            // half-words before pixel 0: the j0 = -1 word of (px 0, i 0) stays inside the buffer
+constexpr int GBUF = ((GFRONT + 64 * GP) * 2 + 15) / 16 * 8;     // half-words per G buffer (16-byte multiple, TW = 64)
+__device__ __forceinline__ int gidx(int px, int i, int j) { return GFRONT + px * GP + i * GS + j; }
 
 __device__ __forceinline__ int swz(int px, int chunk) { return px * 8 + (chunk ^ (px & 7)); }
 
@@ -193,37 +201,50 @@ constexpr int GQ = (ND * PWU + 127) / 128;        // (i, source pixel) items per
 constexpr int GV = (TW * 11 + 127) / 128;         // 16-byte chunks per loader thread in MODE 0 (6)
 constexpr int GXP = (PWU * 8 + 127) / 128;        // X-row chunks per loader thread (5)
 
+// 16 consecutive half-words starting at half-word `h0` (compile-time) of the word array w -> pick half-word u
+template <int NW>
+__device__ __forceinline__ uint16_t pick_half(const uint32_t (&w)[NW], int h) {
+  return (uint16_t)((h & 1) ? (w[h >> 1] >> 16) : (w[h >> 1] & 0xFFFFu));
+}
+
 template <int MODE>
 __device__ __forceinline__ void stage_G(bf16* __restrict__ G, const bf16* __restrict__ g, int64_t ldg, int n, int y, int x0,
                                         int H, int W, int lt, bool vec_g) {
   if (MODE == 0) {
     if (vec_g) {
-      uint4 v[GV];
+      // thread = (pixel, half of the displacement rows): rows 0-4 live in bytes [0, 90) of the pixel = chunks 0-5,
+      // rows 5-8 in bytes [90, 162) = chunks 5-10; six vector loads, compile-time half-word picks, 2-byte stores
+      const int px = lt & 63, ih = lt >> 6;                 // (ih is warp-uniform)
+      const bool ok = x0 + px < W;
+      const uint4* src = reinterpret_cast<const uint4*>(g + (((int64_t)n * H + y) * W + x0 + px) * ldg) + ih * 5;
+      uint32_t w[24];
 #pragma unroll
-      for (int k = 0; k < GV; ++k) {
-        const int e = lt + k * 128;
-        const int px = e / 11, ch = e - px * 11;
-        v[k] = make_uint4(0, 0, 0, 0);
-        if (e < TW * 11 && x0 + px < W) v[k] = __ldg(reinterpret_cast<const uint4*>(g + (((int64_t)n * H + y) * W + x0 + px) * ldg) + ch);
+      for (int c = 0; c < 6; ++c) {
+        const uint4 v = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
       }
+      bf16* dst = G + gidx(px, 0, 0);
+      if (ih == 0) {
 #pragma unroll
-      for (int k = 0; k < GV; ++k) {
-        const int e = lt + k * 128;
-        const int px = e / 11, ch = e - px * 11;
-        if (e < TW * 11) {
-          uint32_t* dst = reinterpret_cast<uint32_t*>(G + px * GPITCH + ch * 8);
-          dst[0] = v[k].x; dst[1] = v[k].y; dst[2] = v[k].z; dst[3] = v[k].w;
-        }
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int j = 0; j < ND; ++j) dst[i * GS + j] = __ushort_as_bfloat16(pick_half(w, i * ND + j));
+      } else {
+#pragma unroll
+        for (int i = 5; i < ND; ++i)
+#pragma unroll
+          for (int j = 0; j < ND; ++j) dst[i * GS + j] = __ushort_as_bfloat16(pick_half(w, i * ND + j - 40));
       }
     } else {
       for (int e = lt; e < TW * NDISP; e += 128) {
         const int px = e / NDISP, d = e - px * NDISP;
-        G[px * GPITCH + d] = x0 + px < W ? g[(((int64_t)n * H + y) * W + x0 + px) * ldg + d] : __float2bfloat16_rn(0.f);
+        G[gidx(px, d / ND, d % ND)] =
+            x0 + px < W ? g[(((int64_t)n * H + y) * W + x0 + px) * ldg + d] : __float2bfloat16_rn(0.f);
       }
     }
   } else {
     // source-pixel major: pixel (y+i-4, sx) holds, in its 9 consecutive channels (8-i)*9 + u, the entries
-    // G[px = sp - 8 + u][i*9 + 8 - u] of 9 neighbouring output pixels (sp = sx - x0 + 4)
+    // G[px = sp - 8 + u][i][8 - u] of 9 neighbouring output pixels (sp = sx - x0 + 4)
     if (vec_g) {
       // one source pixel per loader thread, all nine vertical displacements: the 18 bytes of displacement row i
       // start (8-i)*18 bytes into the pixel, i.e. inside two aligned 16-byte chunks -- two vector loads and
@@ -253,10 +274,8 @@ __device__ __forceinline__ void stage_G(bf16* __restrict__ G, const bf16* __rest
             const int sh = (((8 - i) * 18) & 15) >> 1;          // first half-word inside the two chunks
 #pragma unroll
             for (int u = 0; u < ND; ++u) {
-              const int h = sh + u;
-              const uint16_t val = (uint16_t)((h & 1) ? (w[h >> 1] >> 16) : (w[h >> 1] & 0xFFFFu));
               const int px = sp - 8 + u;
-              if (px >= 0 && px < TW) G[px * GPITCH + i * ND + 8 - u] = __ushort_as_bfloat16(val);
+              if (px >= 0 && px < TW) G[gidx(px, i, 8 - u)] = __ushort_as_bfloat16(pick_half(w, sh + u));
             }
           }
         }
@@ -282,7 +301,7 @@ __device__ __forceinline__ void stage_G(bf16* __restrict__ G, const bf16* __rest
 #pragma unroll
         for (int u = 0; u < ND; ++u) {
           const int px = sp - 8 + u;
-          if (px >= 0 && px < TW) G[px * GPITCH + i * ND + 8 - u] = __ushort_as_bfloat16(v[k][u]);
+          if (px >= 0 && px < TW) G[gidx(px, i, 8 - u)] = __ushort_as_bfloat16(v[k][u]);
         }
       }
     }
@@ -296,7 +315,7 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
                      int strips) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4* ring = reinterpret_cast<uint4*>(smem_raw);                  // [RING][PWU*8]
-  bf16* Gbuf = reinterpret_cast<bf16*>(ring + RING * ROWCH_F);       // [2][TW][GPITCH]
+  bf16* Gbuf = reinterpret_cast<bf16*>(ring + RING * ROWCH_F);       // [2][GBUF]: staged gradient rows (see GS / GP)
   constexpr int OP = 32 + 4;                                         // fp32 output staging pitch (aliases the G in use)
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const bool loader = t >= 128;
@@ -316,15 +335,29 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
     const int slot = ((yy % RING) + RING) % RING;
     for (int e = t; e < PWU * 8; e += GNT) ring[slot * ROWCH_F + swz(e >> 3, e & 7)] = ld_px_chunk(X, ldX, n, yy, x0 - RAD + (e >> 3), e & 7, H, W);
   }
-  if (loader) stage_G<MODE>(Gbuf + (y0 & 1) * TW * GPITCH, g, ldg, n, y0, x0, H, W, lt, vec_g);
+  if (loader) stage_G<MODE>(Gbuf + (y0 & 1) * GBUF, g, ldg, n, y0, x0, H, W, lt, vec_g);
   __syncthreads();
+
+  // A-fragment register (ks, q) of displacement row i is ONE aligned word of the staged row: byte offset inside a
+  // G buffer (+ i*GS*2) and the mask that clears band-edge neighbours -- both fixed per thread
+  uint32_t aoff[8], amask[8];
+#pragma unroll
+  for (int sl = 0; sl < 8; ++sl) {
+    const int ks = sl >> 2, q = sl & 3;
+    const int r = gid + (q & 1) * 8;
+    const int k = ks * 16 + 2 * tig + (q >> 1) * 8;
+    const int j0 = k - r;
+    const bool lo = j0 >= 0 && j0 < ND, hi = j0 + 1 >= 0 && j0 + 1 < ND;
+    amask[sl] = (lo ? 0xFFFFu : 0u) | (hi ? 0xFFFF0000u : 0u);
+    aoff[sl] = (lo || hi) ? (uint32_t)(gidx(px0 + r, 0, 0) + j0) * 2u : 0u;
+  }
 
   const float inv_c = 1.f / (float)C;
   const int b_k = (lane & 7) + ((lane >> 3) & 1) * 8;
   const int b_ch = lane >> 4;
   for (int y = y0; y < y1; ++y) {
     const bool more = y + 1 < y1;
-    bf16* G = Gbuf + (y & 1) * TW * GPITCH;
+    bf16* G = Gbuf + (y & 1) * GBUF;
     uint4 pf[GXP];
     if (loader) {
       if (more) {
@@ -333,7 +366,7 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
           const int e = lt + k * 128;
           pf[k] = e < PWU * 8 ? ld_px_chunk(X, ldX, n, y + 1 + RAD, x0 - RAD + (e >> 3), e & 7, H, W) : make_uint4(0, 0, 0, 0);
         }
-        stage_G<MODE>(Gbuf + ((y + 1) & 1) * TW * GPITCH, g, ldg, n, y + 1, x0, H, W, lt, vec_g);
+        stage_G<MODE>(Gbuf + ((y + 1) & 1) * GBUF, g, ldg, n, y + 1, x0, H, W, lt, vec_g);
       }
     } else {
       float acc[8][4];
@@ -341,25 +374,18 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
-#pragma unroll 1
+      const uint8_t* Gb = reinterpret_cast<const uint8_t*>(G);
+#pragma unroll
       for (int i = 0; i < ND; ++i) {
         const int yy = y + i - RAD;
         const uint4* row = ring + (((yy % RING) + RING) % RING) * ROWCH_F;
-        const bf16* Gi = G + i * ND;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          // A fragment = band of G: element (r, k) = G[px0 + r][i*9 + k - r] for 0 <= k - r <= 8
+          // A fragment = band of G: element (r, k) = G[px0 + r][i][k - r] for 0 <= k - r <= 8
           uint32_t af[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r = gid + (q & 1) * 8;
-            const int k = ks * 16 + 2 * tig + (q >> 1) * 8;
-            const int j0 = k - r, j1 = j0 + 1;
-            const bf16* gp = Gi + (px0 + r) * GPITCH;
-            const uint16_t lo = (j0 >= 0 && j0 < ND) ? __bfloat16_as_ushort(gp[j0]) : (uint16_t)0;
-            const uint16_t hi = (j1 >= 0 && j1 < ND) ? __bfloat16_as_ushort(gp[j1]) : (uint16_t)0;
-            af[q] = (uint32_t)lo | ((uint32_t)hi << 16);
-          }
+          for (int q = 0; q < 4; ++q)
+            af[q] = *reinterpret_cast<const uint32_t*>(Gb + aoff[ks * 4 + q] + i * GS * 2) & amask[ks * 4 + q];
           // ring pixel of this lane's k row; k >= 24 lies outside every band (A is zero there), so clamp into the
           // row instead of padding it: the operand only has to be finite
           const int kpx = min(px0 + ks * 16 + b_k, PWU - 1);
@@ -441,7 +467,7 @@ int corr_bwd_mma(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const
   const int strips = (int)cdiv(W, TW);
   const int TH = pick_th(N, H, strips);
   const int segs = (int)cdiv(H, TH);
-  const size_t smem = (size_t)(RING * ROWCH_F) * 16 + 2 * (size_t)TW * GPITCH * 2;
+  const size_t smem = (size_t)(RING * ROWCH_F) * 16 + 2 * (size_t)GBUF * 2;
   const unsigned grid = (unsigned)((int64_t)N * strips * segs);
   cudaError_t e = cudaFuncSetAttribute(corr_grad_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
