@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--engine", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true",
+                    help="warm-up + the K device-resident steps only (what the ncu passes of scripts/gpu_round.sh run)")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for cpu_baseline")
     return ap.parse_args()
 
@@ -260,18 +262,27 @@ def run_native(args):
     for _ in range(max(args.warmup, 3)):
         step(lr_dev, hr_dev)
 
-    # ---- device-resident throughput, with per-launch CUDA-event timing of the conv family ----
+    # ---- device-resident throughput (the line's `value`): K steps, nothing but the step in the timed region ----
+    launches0 = ops.LAUNCHES[0]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(lambda: step(lr_dev, hr_dev), args.steps)
+    clocks = sampler.stop()
+    launches = ops.LAUNCHES[0] - launches0
+
+    if args.value_only:
+        if rank == 0:
+            print(json.dumps({"value_only": True, "ms_per_step": ms / args.steps, "steps": args.steps,
+                              "gpu_launches": launches}))
+        return
+
+    # ---- the same K steps again with per-launch CUDA-event spans (kernel shares, roofline numerators) ----
     plan = next(iter(model._plans.values()))
     timer = KernelTimer()
     plan.timer = timer
     import nerve_cl_b200.engine as _eng
     _eng.nv.timer = timer
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = ops.LAUNCHES[0]
-    ms = timed(lambda: step(lr_dev, hr_dev), args.steps)
-    launches = ops.LAUNCHES[0] - launches0
-    clocks = sampler.stop()
+    ms_spans = timed(lambda: step(lr_dev, hr_dev), args.steps)
     plan.timer = None
     _eng.nv.timer = None
     kdetail = timer.summary()
@@ -290,9 +301,28 @@ def run_native(args):
     # ---- end to end: pinned host -> device copies and loss read-back inside the timed region ----
     losses = []
 
+    # The loader a user writes: pinned host batches, non_blocking copies on a side stream, the next step's batch in
+    # flight while this step computes (every step's copies and its loss read-back are inside the timed region).
+    copy_stream = torch.cuda.Stream(device=dev)
+    inflight = []
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            lr = lr_host.to(dev, non_blocking=True)
+            hr = hr_host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        inflight.append((lr, hr, ev))
+
     def e2e_step():
-        lr = lr_host.to(dev, non_blocking=True)
-        hr = hr_host.to(dev, non_blocking=True)
+        if not inflight:
+            fetch()
+        lr, hr, ev = inflight.pop(0)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        lr.record_stream(cur)
+        hr.record_stream(cur)
+        fetch()
         losses.append(float(step(lr, hr).item()))
 
     e2e_step()
@@ -374,6 +404,16 @@ def run_native(args):
     conv_launches = sum(d["launches"] for k, d in ksum.items() if k.startswith("conv"))
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+    # DRAM bytes per conv-family launch from the committed ncu pass (profiles/conv_traffic.json, written by
+    # scripts/summarize_profile.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one step)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == workload_config(args, world).get("workload"):
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -386,10 +426,11 @@ def run_native(args):
         "roofline": {
             "kernel": "dense conv family (fwd + dgrad + wgrad launches of nervecl_conv2d_*)",
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak if peak else None, "traffic": None,
+            "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['_source']})",
             "launches_timed": conv_launches, "avg_launch_ms": conv_ms / max(conv_launches, 1),
-            "share_of_step": conv_ms / ms if ms else None,
+            "share_of_step": conv_ms / ms_spans if ms_spans else None,
+            "span_pass_ms_per_step": ms_spans / args.steps,
             "by_kind": {k: {"launches": d["launches"], "ms": round(d["ms"], 3),
                             "tflops": d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0}
                         for k, d in ksum.items() if k.startswith("conv")},

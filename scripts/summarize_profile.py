@@ -51,7 +51,7 @@ if os.path.exists(launches):
     tot = sum(v[1] for v in agg.values())
     out += ["## ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare SHARES)",
             "", f"total {tot:.1f} ms over {sum(v[0] for v in agg.values())} launches "
-            "(`python bench.py --steps 1 --warmup 3 --no-cpu-baseline`: 3 warm-up + 1 timed + 2 e2e steps)", "",
+            "(`python bench.py --steps 1 --warmup 3 --value-only`: 3 warm-up + 1 timed step)", "",
             "| kernel | launches | ms | share |", "|---|---:|---:|---:|"]
     with open(os.path.join(dst, f"{tag}_launch_shares.csv"), "w") as f:
         f.write("kernel,launches,ms,share\n")
@@ -82,6 +82,43 @@ if os.path.exists(rep):
     for r in rows[2:]:
         out.append("| " + " | ".join(r[i][:70] for _, i in idx) + " |")
     out.append("")
+
+traffic = os.path.join(src, f"{tag}_traffic.csv")
+if os.path.exists(traffic):
+    rows = list(csv.reader(open(traffic)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr, data = rows[hi], rows[hi + 1:]
+    ii, ki, mi, vi, ui = (hdr.index(c) for c in ("ID", "Kernel Name", "Metric Name", "Metric Value", "Metric Unit"))
+    per = collections.OrderedDict()              # launch id -> [kernel, bytes]
+    for r in data:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1.0)
+        e = per.setdefault(r[ii], [r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", ""), 0.0])
+        e[1] += v
+    ids = list(per)
+    nstep = len(ids) // 4                         # 3 warm-up + 1 timed step, identical launch sequences
+    last = [per[i] for i in ids[len(ids) - nstep:]]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for k, b in last:
+        agg[k][0] += 1
+        agg[k][1] += b
+    tot_b = sum(v[1] for v in agg.values())
+    out += ["## DRAM traffic of the conv family, one training step (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "",
+            f"{nstep} launches, {tot_b / 1e9:.2f} GB per step = {tot_b / max(nstep, 1) / 1e6:.1f} MB per launch", "",
+            "| kernel | launches | GB | MB / launch |", "|---|---:|---:|---:|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{k}` | {v[0]} | {v[1] / 1e9:.2f} | {v[1] / v[0] / 1e6:.1f} |")
+    out.append("")
+    workload = None
+    if os.path.exists(bench) and os.path.getsize(bench):
+        workload = json.loads(open(bench).read().strip().splitlines()[-1])["config"]["workload"]
+    json.dump({"dram_bytes_per_launch": tot_b / max(nstep, 1), "dram_bytes_per_step": tot_b, "launches_per_step": nstep,
+               "workload": workload,
+               "source": f"profiles/{tag}_summary.md (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, "
+                         "conv-family kernels of one training step)"},
+              open(os.path.join(dst, "conv_traffic.json"), "w"), indent=1)
 
 open(os.path.join(dst, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
