@@ -4,8 +4,9 @@
 // tile through TMA -- 9x the L2 traffic of the input -- and with N = Cout = 32 each SS-mode MMA reads 5 KB of
 // shared memory per 16 tensor cycles, so the kernel sat at ~10 % tensor-pipe activity (profiles/r01a_summary.md).
 //
-// Here a persistent CTA owns work items (image n, 128-pixel column strip, R output rows) and streams the
-// item's R+2 input rows top to bottom:
+// Here a persistent CTA owns an equal share of all (image, 128-pixel column strip, row) output rows -- a contiguous
+// range of the linearised row space, cut into work items (image n, strip, first row, row count) wherever it
+// crosses a strip boundary -- and streams each item's rows+2 input rows top to bottom:
 //   * TMA brings each halo'd input row {64 ch, 130 px} per 64-channel chunk into shared memory ONCE
 //     (128B swizzle, out-of-image pixels / rows / channels are zero-filled = conv padding); the ring is
 //     chunk-granular, so wide inputs still get several stages;
@@ -69,6 +70,28 @@ __device__ __forceinline__ int wtile_index(const RowArgs& a, int kx, int c) {
   return (a.x_center ? 1 : 3) * a.nchunks + (a.x2_center ? c2 : kx * a.nchunks2 + c2);
 }
 
+// The CTA's share of the linearised output rows ((n * strips + strip) * H + y), split evenly (to within one row)
+// over the CTAs of a channel group; next() yields the items of that share in order.  Every role (TMA producer,
+// MMA issuer, epilogue) walks the same sequence.
+struct ItemIter {
+  int pos, end;                       // (N * strips * H < 2^31: checked by conv_rows_supported)
+  __device__ __forceinline__ ItemIter(const RowArgs& a) {
+    const int64_t total = (int64_t)a.N * a.strips * a.H;
+    pos = (int)(total * blockIdx.x / gridDim.x);
+    end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  }
+  __device__ __forceinline__ bool next(const RowArgs& a, int& n, int& strip, int& y0, int& rows) {
+    if (pos >= end) return false;
+    const int unit = pos / a.H;
+    y0 = pos - unit * a.H;
+    rows = min(end - pos, a.H - y0);
+    n = unit / a.strips;
+    strip = unit - n * a.strips;
+    pos += rows;
+    return true;
+  }
+};
+
 template <typename OutT, bool PF>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
@@ -93,7 +116,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = a.N * a.strips * a.segs;
   const int grp = blockIdx.y;                       // output-channel group
   const int S = a.slots;
 
@@ -133,11 +155,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int seg = item % a.segs;
-        const int t = item / a.segs;
-        const int strip = t % a.strips, n = t / a.strips;
-        const int y0 = seg * a.R, rows = min(a.R, a.H - y0), x0 = strip * BM;
+      ItemIter it(a);
+      int n, strip, y0, rows;
+      while (it.next(a, n, strip, y0, rows)) {
+        const int x0 = strip * BM;
         for (int ri = 0; ri < rows + 2; ++ri) {
           for (int gi = 0; gi < ngrp; ++gi) {
             mbar_wait(&ch_empty[stage], phase ^ 1);
@@ -176,9 +197,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       bool ready = false;                 // early, non-blocking probe of the next chunk's barrier succeeded
       bool acc_ready = false;             // same for the accumulator slot the next input row starts
       mbar_wait(w_bar, 0);
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int seg = item % a.segs;
-        const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
+      ItemIter it(a);
+      int n_, strip_, y0_, rows;
+      while (it.next(a, n_, strip_, y0_, rows)) {
         int s2 = jbase % S;               // slot of output row oi = ri (the row this input row starts)
         uint32_t r2 = (uint32_t)(jbase / S);   // how many times that slot has been used before
         acc_ready = false;                     // (the probe at the end of the previous item was for another slot)
@@ -310,11 +331,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
       const bool relu = a.relu != 0;
       const float alpha = a.alpha;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int seg = item % a.segs;
-        const int t = item / a.segs;
-        const int strip = t % a.strips, n = t / a.strips;
-        const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
+      ItemIter it(a);
+      int n, strip, y0, rows;
+      while (it.next(a, n, strip, y0, rows)) {
         const int x = strip * BM + row;
         const bool valid = x < a.W;
         const int64_t p0 = ((int64_t)n * a.H + y0) * a.W + x;
@@ -427,11 +446,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       }
     } else
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int seg = item % a.segs;
-      const int t = item / a.segs;
-      const int strip = t % a.strips, n = t / a.strips;
-      const int y0 = seg * a.R, rows = min(a.R, a.H - y0);
+    {
+     ItemIter it(a);
+     int n, strip, y0, rows;
+     while (it.next(a, n, strip, y0, rows)) {
       const int x = strip * BM + row;
       const bool valid = x < a.W;
       const int64_t p0 = ((int64_t)n * a.H + y0) * a.W + x;
@@ -492,6 +510,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (++slot == S) { slot = 0; par ^= 1u; }
        }
       }
+     }
     }
   }
   tc_fence_before();
@@ -526,8 +545,9 @@ bool plan_rows(const nervecl_conv_params& a, int sms, RowPlan& p) {
     const int chunks_fit = (int)((kSmemBudget - fixed) / CHUNK_BYTES);
     // a ring stage holds `cps` chunks (a divisor of the chunks per row): whole rows when two of them fit
     // (one barrier round trip and one commit per row), else the largest group that still leaves >= 3 stages
+    static const int cps_cap = getenv("NERVECL_ROWS_CPS") ? atoi(getenv("NERVECL_ROWS_CPS")) : 1 << 20;   // (tuning knob)
     for (int cps = nct; cps >= 1; --cps) {
-      if (nct % cps) continue;
+      if (nct % cps || cps > cps_cap) continue;
       const int st = chunks_fit / cps;
       if (st >= (cps == nct ? 2 : 3)) {
         p.nsplit = ns;
@@ -569,6 +589,7 @@ bool conv_rows_supported(const nervecl_conv_params& a) {
   if (a.K == 1 && a.x2) return false;
   if (a.Cin < 16 || a.Cin % 16 || a.Cin > 512) return false;
   if (a.W < 64 || a.H < 3) return false;
+  if ((int64_t)a.N * ((a.W + BM - 1) / BM) * a.H >= (int64_t)1 << 30) return false;
   if (a.x2) {
     if (a.Cin2 < 16 || a.Cin2 % 16 || a.Cin2 > 256 || a.ldx2 % 8 || !aligned(a.x2, 16)) return false;
     if (a.w_ld < (a.Cin + KC - 1) / KC * KC + a.Cin2) return false;   // x2 weights start at the next 64-column boundary
@@ -633,8 +654,9 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   if (whole && !a.res && a.mask && !a.bias && !a.relu && a.mask_c0 == 0) t.fast = 2;
   if (whole && a.res && a.res_channels >= a.Cout && !a.mask && !a.bias && !a.relu) t.fast = 3;
 
-  const int64_t items = (int64_t)a.N * p.strips * p.segs;
-  dim3 grid((unsigned)imin(items, imax(1, sms / p.nsplit)), (unsigned)p.nsplit);
+  // one CTA per SM (per channel group); each takes an equal share of the N * strips * H output rows
+  const int64_t total_rows = (int64_t)a.N * p.strips * a.H;
+  dim3 grid((unsigned)imin(cdiv(total_rows, 4), imax(1, sms / p.nsplit)), (unsigned)p.nsplit);
   cudaError_t e = cudaSuccess;
   const bool pf = a.mask && !a.mask_sub && p.NOUT <= 32;
 #define NV_LAUNCH_ROWS(OT, PFV)                                                                                       \
