@@ -162,47 +162,73 @@ __device__ __forceinline__ WarpCoord warp_coord(int x, int y, float fx, float fy
   return c;
 }
 
+// Forward warp.  The first version gave each pixel C/8 adjacent lanes that ALL replayed the ~70-instruction
+// coordinate sequence: 69 warp instructions per pixel, instruction-issue bound at 0.40 of the HBM roofline
+// (profiles/r01z_summary.md).  Here a warp owns 32 consecutive pixels: phase A computes one pixel per LANE
+// (coalesced flow load, coordinates, corner weights, validity), phase B walks the 32 pixels 32/cg at a time with
+// the lanes regrouped as (pixel, 8-channel vector) and the pixel's parameters broadcast by shuffles.
 template <typename T>
 __global__ void __launch_bounds__(256)
 warp_fwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow, T* __restrict__ out,
                 int64_t ldo, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode,
                 int32_t* __restrict__ idx_out) {
-  // grid = (N*H rows, pixel groups of a row); the C/8 threads of a pixel are adjacent lanes (cg is a power of two):
-  // no 64-bit division per element
-  const int cg = C >> 3;
-  const int ppb = blockDim.x / cg;                       // pixels per block
-  const int x = blockIdx.y * ppb + (int)threadIdx.x / cg;
-  const int c0 = ((int)threadIdx.x % cg) << 3;
-  const int64_t rowi = blockIdx.x;                       // n*H + y
-  const int y = (int)(rowi % H);
-  if (x < W) {
-    const int64_t p = rowi * W + x;
-    const int64_t img = (rowi - y) * W;                  // n*H*W
-    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
-    WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
-    if (idx_out && c0 == 0) {
-      idx_out[p * 2] = (int)c.x0f;
-      idx_out[p * 2 + 1] = (int)c.y0f;
+  const int lane = threadIdx.x & 31;
+  const int npix = N * H * W;                                        // (< 2^31: checked by the launcher)
+  const int p = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+  // ---- phase A: lane = pixel ----
+  float wnw = 0.f, wne = 0.f, wsw = 0.f, wse = 0.f;
+  int q = 0;                                                         // pixel index of the north-west corner
+  unsigned vmask = 0;                                                // bit0 nw, bit1 ne, bit2 sw, bit3 se, bit4 active
+  if (p < npix) {
+    const int x = p % W, r = p / W;
+    const int y = r % H;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+    const WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
+    if (idx_out) {
+      idx_out[(int64_t)p * 2] = (int)c.x0f;
+      idx_out[(int64_t)p * 2 + 1] = (int)c.y0f;
     }
-    float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
-    float wnw = (x1f - c.ix) * (y1f - c.iy);
-    float wne = (c.ix - c.x0f) * (y1f - c.iy);
-    float wsw = (x1f - c.ix) * (c.iy - c.y0f);
-    float wse = (c.ix - c.x0f) * (c.iy - c.y0f);
-    bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
-    bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
-    float acc[8];
+    const float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
+    wnw = (x1f - c.ix) * (y1f - c.iy);
+    wne = (c.ix - c.x0f) * (y1f - c.iy);
+    wsw = (x1f - c.ix) * (c.iy - c.y0f);
+    wse = (c.ix - c.x0f) * (c.iy - c.y0f);
+    const bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
+    const bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
+    vmask = (yin0 && xin0 ? 1u : 0u) | (yin0 && xin1 ? 2u : 0u) | (yin1 && xin0 ? 4u : 0u) | (yin1 && xin1 ? 8u : 0u) | 16u;
+    q = (r - y) * W + c.y0 * W + c.x0;                               // n*H*W + y0*W + x0 (only used where valid)
+  }
+  // ---- phase B: lane = (pixel of the group, 8-channel vector) ----
+  const int cg = C >> 3;                                             // lanes per pixel (power of two <= 32)
+  const int ppi = 32 / cg;                                           // pixels per iteration
+  const int c0 = (lane % cg) << 3;
+  const int sub = lane / cg;
+  const int pbase = p - lane;
+#pragma unroll 2
+  for (int it = 0; it < cg; ++it) {
+    const int src = it * ppi + sub;
+    const float a = __shfl_sync(0xffffffffu, wnw, src), b = __shfl_sync(0xffffffffu, wne, src);
+    const float c = __shfl_sync(0xffffffffu, wsw, src), d = __shfl_sync(0xffffffffu, wse, src);
+    const int qq = __shfl_sync(0xffffffffu, q, src);
+    const unsigned vm = __shfl_sync(0xffffffffu, vmask, src);
+    if (vm & 16u) {
+      const T* base = feat + (int64_t)qq * ldf_ + c0;
+      const f8 z = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+      const f8 v0 = (vm & 1u) ? ld8(base) : z;
+      const f8 v1 = (vm & 2u) ? ld8(base + ldf_) : z;
+      const f8 v2 = (vm & 4u) ? ld8(base + (int64_t)W * ldf_) : z;
+      const f8 v3 = (vm & 8u) ? ld8(base + (int64_t)(W + 1) * ldf_) : z;
+      f8 o;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const T* base = feat + (img + (int64_t)c.y0 * W + c.x0) * ldf_ + c0;
-    if (yin0 && xin0) { f8 v = ld8(base);                        for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wnw, acc[k]); }
-    if (yin0 && xin1) { f8 v = ld8(base + ldf_);                 for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wne, acc[k]); }
-    if (yin1 && xin0) { f8 v = ld8(base + (int64_t)W * ldf_);    for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wsw, acc[k]); }
-    if (yin1 && xin1) { f8 v = ld8(base + (int64_t)(W + 1) * ldf_); for (int k = 0; k < 8; ++k) acc[k] = fmaf(v.v[k], wse, acc[k]); }
-    f8 o;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
-    st8(out + p * ldo + c0, o);
+      for (int k = 0; k < 8; ++k) {                                  // (nw, ne, sw, se; fused multiply-adds from zero)
+        float acc = fmaf(v0.v[k], a, 0.f);
+        acc = fmaf(v1.v[k], b, acc);
+        acc = fmaf(v2.v[k], c, acc);
+        acc = fmaf(v3.v[k], d, acc);
+        o.v[k] = acc;
+      }
+      st8(out + (int64_t)(pbase + src) * ldo + c0, o);
+    }
   }
 }
 
@@ -358,7 +384,8 @@ NV_API int nervecl_warp_fwd(const void* feat, int64_t ldf, const float* flow, vo
   float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
   const int ppb = 256 / (C >> 3);
   if (cdiv(W, ppb) > 65535 || (int64_t)N * H > 0x7fffffff) return NERVECL_EUNSUPPORTED;
-  dim3 blocks((unsigned)((int64_t)N * H), (unsigned)cdiv(W, ppb));
+  if ((int64_t)N * H * W >= ((int64_t)1 << 31) - 64) return NERVECL_EUNSUPPORTED;
+  const unsigned blocks = (unsigned)cdiv((int64_t)N * H * W, 256);
   NV_DISPATCH_DTYPE(dtype, E, (warp_fwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
                                   (const E*)feat, ldf, flow, (E*)out, ldo, N, H, W, C, inv_w, inv_h, div_mode, idx_out)));
   return launch_status();
