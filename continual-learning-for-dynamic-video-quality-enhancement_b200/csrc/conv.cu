@@ -29,6 +29,10 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
     if ((engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) || !conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
     return conv_rows_fwd(*p, s);
   }
+  if (p->colsum) {                               // fused column sums: row-streaming engine only
+    if ((engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) || !conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
+    return conv_rows_fwd(*p, s);
+  }
   if (engine == NERVECL_CONV_AUTO) engine = conv_tc_fwd_supported(*p) ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
   if (engine == NERVECL_CONV_TC) {               // best tcgen05 kernel for the shape
     // (1x1: the row kernel wins while the per-row MMA count stays small; wide inputs are at the HBM roofline

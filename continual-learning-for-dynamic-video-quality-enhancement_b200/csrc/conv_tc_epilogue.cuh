@@ -15,6 +15,7 @@ struct EpiArgs {
   const bf16* mask; int64_t ldmask;
   const bf16* msub; int64_t ldmsub;
   void* out;        int64_t ldo;
+  float* colsum;    // optional per-channel sum of the written values (row kernel, mask-gated lean epilogue only)
 };
 
 // 16 consecutive bf16 (two 16-byte loads) -> fp32

@@ -323,12 +323,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       //      for NOUT = 64, chunk part + 2.
       const bool has0 = part < nch_all, two = !PF && part + 2 < nch_all;     // (PF kernels: NOUT <= 32)
       const int ch0 = c_lo + part * 16, ch1 = ch0 + 32;
-      float bz0[16], bz1[16];
+      // (PF kernels always have a mask: fast == 1 never runs there, and its 32 bias registers make room for the
+      //  16 running column sums of the fused bias gradient)
+      float bz0[16], bz1[16], cs[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        bz0[j] = (a.fast == 1 && a.bias && has0) ? __ldg(a.bias + ch0 + j) : 0.f;
-        bz1[j] = (a.fast == 1 && a.bias && two) ? __ldg(a.bias + ch1 + j) : 0.f;
+        bz0[j] = (!PF && a.fast == 1 && a.bias && has0) ? __ldg(a.bias + ch0 + j) : 0.f;
+        bz1[j] = (!PF && a.fast == 1 && a.bias && two) ? __ldg(a.bias + ch1 + j) : 0.f;
+        cs[j] = 0.f;
       }
+      const bool want_cs = PF && a.colsum != nullptr;
       const bool relu = a.relu != 0;
       const float alpha = a.alpha;
       ItemIter it(a);
@@ -383,7 +387,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (two) tmem_st16_zero(tcol + 32u);
             if (valid && has0 && !(a.dbg & 4)) {
               float f[16];
-              if (a.fast == 1) {
+              if (!PF && a.fast == 1) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   f[j] = __uint_as_float(v0[j]) + bz0[j];
@@ -407,6 +411,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   f[2 * j + 1] = mh > 0.f ? alpha * __uint_as_float(v0[2 * j + 1]) : 0.f;
                 }
                 store16(op, f);
+                if (want_cs) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) cs[j] += f[j];
+                }
                 if (two) {
                   const uint32_t nw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
 #pragma unroll
@@ -443,6 +451,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (lane == 0) mbar_arrive(&acc_empty[slot]);
             if (++slot == S) { slot = 0; par ^= 1u; }
           }
+        }
+      }
+      if (want_cs && has0) {
+        // fused bias gradient: the warp's 32 pixels, then one atomic per channel and warp
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t = warp_sum(cs[j]);
+          if (lane == 0) atomicAdd(a.colsum + ch0 + j, t);
         }
       }
     } else
@@ -641,6 +657,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.mask = (const bf16*)a.mask; t.ldmask = a.ldmask;
   t.msub = (const bf16*)a.mask_sub; t.ldmsub = a.ldmask_sub;
   t.out = a.out; t.ldo = a.ldo;
+  t.colsum = a.colsum;
   t.N = a.N; t.H = a.H; t.W = a.W;
   t.NOUT = p.NOUT; t.nchunks = p.nchunks; t.ksteps_last = p.ksteps_last;
   t.nchunks2 = p.nchunks2; t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
@@ -655,6 +672,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   if (whole && a.res && a.res_channels >= a.Cout && !a.mask && !a.bias && !a.relu) t.fast = 3;
 
   // one CTA per SM (per channel group); each takes an equal share of the N * strips * H output rows
+  if (a.colsum && !(t.fast == 2 && p.NOUT <= 32)) return NERVECL_EUNSUPPORTED;
   const int64_t total_rows = (int64_t)a.N * p.strips * a.H;
   dim3 grid((unsigned)imin(cdiv(total_rows, 4), imax(1, sms / p.nsplit)), (unsigned)p.nsplit);
   cudaError_t e = cudaSuccess;

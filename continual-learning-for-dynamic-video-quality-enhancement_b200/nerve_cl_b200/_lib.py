@@ -33,6 +33,7 @@ class ConvParams(C.Structure):
         ("mask_sub", c_vp), ("ldmask_sub", c_i64),
         ("out", c_vp), ("ldo", c_i64),
         ("x2", c_vp), ("ldx2", c_i64), ("Cin2", c_i32), ("x2_center", c_i32),
+        ("colsum", c_vp),
     ]
 
 

@@ -479,9 +479,12 @@ class Plan:
         lff = f"residual_blocks.{k}.lff"
         # last slice: only the LFF reaches it.  dy_4 = relu'(o_4) * 0.2 * W_lff[:, slice]^T dblock
         c4 = F + (RDB_LAYERS - 1) * GROWTH
+        # (every slice gradient g is the previous layer's output gradient: its per-channel sum, taken in the conv
+        #  epilogue, is that layer's bias gradient -- no reduction pass over the gradient buffer)
+        names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
         with self._span("conv_dgrad", dblock, F, GROWTH, 1):
             nv.conv2d_fwd(dblock, self.wb[lff][:, c4:CT, :], None, None, buf[..., c4:CT], None, g[..., c4:CT], GROWTH,
-                          False, False, 0, 0, 0.2, self.engine)
+                          False, False, 0, 0, 0.2, self.engine, None, False, G[names[RDB_LAYERS - 1] + ".bias"])
         for s in range(RDB_LAYERS - 1, -1, -1):              # slices F+(s-1)G .. (s >= 1), then the x slice (s = 0)
             rows = F if s == 0 else GROWTH
             c_lo = 0 if s == 0 else F + (s - 1) * GROWTH
@@ -492,13 +495,12 @@ class Plan:
                 # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
                 nv.conv2d_fwd(g[..., x_lo:CT], w, None, dblock if s == 0 else None, mask, None,
                               g[..., c_lo:c_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,
-                              dblock, True)
-        names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
+                              dblock, True, G[names[s - 1] + ".bias"] if s > 0 else None)
         cx = F + (RDB_LAYERS - 1) * GROWTH
         with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
                                                                 for i in range(RDB_LAYERS))):
-            nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names],
-                                     [G[n + ".bias"] for n in names], [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
+            nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names], [],
+                                     [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
 
     def backward(self, A: Activations, dout: Tensor, P: Dict[str, Tensor], G: Dict[str, Tensor],
                  on_grads_ready=None) -> None:

@@ -192,9 +192,9 @@ def _pack_conv_weights_batched(w, dst, transpose_flip) -> None:
 # --------------------------------------------------------------------------------------------
 @_op("conv2d_fwd(Tensor x, Tensor w, Tensor? bias, Tensor? res, Tensor? mask, Tensor? mask_sub, "
      "Tensor(a!) out, int cout, bool relu, bool accumulate, int res_channels, int mask_c0, float alpha, "
-     "int engine, Tensor? x2=None, bool x2_center=False) -> ()")
+     "int engine, Tensor? x2=None, bool x2_center=False, Tensor(b!)? colsum=None) -> ()")
 def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, res_channels, mask_c0, alpha,
-                engine, x2=None, x2_center=False) -> None:
+                engine, x2=None, x2_center=False, colsum=None) -> None:
     """Fused conv (see ``nervecl_conv2d_fwd``).  ``w`` is a packed [K*K, rows, cols] tensor; ``cout`` is the
     number of output channels actually computed (<= rows)."""
     xp, ldx, n, h, wd, cin = _nhwc(x, "x")
@@ -232,6 +232,10 @@ def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, re
         if (n2, h2, w2) != (n, h, wd) or x2.dtype != x.dtype:
             raise RuntimeError("nervecl.conv2d_fwd: x2 must match x in batch, size and dtype")
         p.x2, p.ldx2, p.Cin2, p.x2_center = x2p, ldx2, c2, int(x2_center)
+    if colsum is not None:                       # fused per-channel sum of the written values (+=, fp32 [cout])
+        if colsum.numel() < cout:
+            raise RuntimeError("nervecl.conv2d_fwd: colsum must have at least cout elements")
+        p.colsum = _flat(colsum, "colsum")
     _lib.check(_lib.load().nervecl_conv2d_fwd(C.byref(p), _stream()), "conv2d_fwd")
 
 

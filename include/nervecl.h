@@ -148,6 +148,12 @@ typedef struct nervecl_conv_params {
   const void* x2;  int64_t ldx2;
   int32_t Cin2;
   int32_t x2_center;
+  /* ABI v3: optional fp32 [Cout] vector that receives (+=, atomically) the per-channel sum over all pixels of
+   * the values written to `out` -- when `out` is the output gradient of the previous layer (a data-gradient
+   * conv gated by that layer's ReLU mask) this IS that layer's bias gradient, so no separate reduction pass over
+   * the gradient is needed.  Row-streaming engine, mask-gated bf16 outputs with <= 32 channels per CTA only
+   * (NERVECL_EUNSUPPORTED otherwise). */
+  float* colsum;
 } nervecl_conv_params;
 
 int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t stream);

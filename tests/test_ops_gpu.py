@@ -516,6 +516,26 @@ def test_conv_rows_lean_epilogues(k, cout):
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
 
 
+def test_conv_rows_fused_column_sums():
+    """colsum: per-channel sum of the mask-gated values the row kernel writes (the previous layer's bias gradient)."""
+    from nerve_cl_b200 import ops
+    n, h, w, cin, cout = 2, 37, 200, 96, 32
+    g = torch.Generator().manual_seed(77)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    act = bf(torch.randn(n, cout, h, w, generator=g))
+    out = torch.empty((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+    cs = torch.full((cout,), 3.0, device="cuda")
+    nv().conv2d_fwd(nhwc(x, torch.bfloat16), pack(wt, torch.bfloat16), None, None, nhwc(act, torch.bfloat16), None, out,
+                    cout, False, False, 0, 0, 0.5, ops.CONV_TC, None, False, cs)
+    ref = 0.5 * F.conv2d(x, wt, None, 1, 1) * (act > 0)
+    assert relerr(nchw(out), ref) <= BF16_TOL
+    assert relerr(cs.cpu() - 3.0, ref.sum((0, 2, 3))) <= 2e-3
+    with pytest.raises(RuntimeError):            # not a mask-gated <= 32-channel bf16 output: refused, never ignored
+        nv().conv2d_fwd(nhwc(x, torch.bfloat16), pack(wt, torch.bfloat16), None, None, None, None, out, cout, False,
+                        False, 0, 0, 1.0, ops.CONV_TC, None, False, cs)
+
+
 def test_conv_tc_matches_simt_bitwise_inputs():
     """Same bf16 operands through both engines: results agree to bf16 rounding (different summation order)."""
     from nerve_cl_b200 import ops
