@@ -78,10 +78,11 @@ if __name__ == "__main__":
             fwd_case(cin, 32, 3, 256, 32, [ops.CONV_TC])
             fwd_case(cin, 32, 3, 256, 256, [ops.CONV_TC])
     if which == "rows":
-        fwd_case(64, 32, 3, 224, 224, [ops.CONV_TC])
+        # (component timing with NERVECL_ROWS_DBG: scripts/bench_rows_dbg.sh)
         fwd_case(64, 32, 3, 256, 256, [ops.CONV_TC])
-        fwd_case(192, 32, 3, 224, 224, [ops.CONV_TC])
         fwd_case(192, 32, 3, 256, 256, [ops.CONV_TC])
+        fwd_case(64, 64, 1, 64, 64, [ops.CONV_TC])
+        fwd_case(32, 128, 3, 256, 256, [ops.CONV_TC], accumulate=False, mask=True)
     if which == "k1":
         # 1x1 shapes of the step: LFF data gradient of the last dense layer (B images), extractor pointwise (T*B),
         # LFF forward

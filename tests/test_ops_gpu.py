@@ -491,7 +491,7 @@ def test_conv_dgrad_tcgen05_accumulate_mask(shape):
 
 
 @pytest.mark.parametrize("k", [1, 3])
-@pytest.mark.parametrize("cout", [32, 64])
+@pytest.mark.parametrize("cout", [32, 64, 96, 128, 192])
 def test_conv_rows_lean_epilogues(k, cout):
     """The row kernel's lean epilogues (bias + ReLU -> bf16; alpha * acc gated by the ReLU mask) for 3x3 and 1x1."""
     from nerve_cl_b200 import ops
@@ -512,6 +512,10 @@ def test_conv_rows_lean_epilogues(k, cout):
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
     nv().conv2d_fwd(xo, wp, None, nhwc(act, torch.bfloat16), None, None, out[..., :cout], cout, False, False, cout, 0,
                     0.5, ops.CONV_TC)
+    assert relerr(nchw(out[..., :cout]), 0.5 * F.conv2d(x, wt, None, 1, k // 2) + act) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
+    out[..., :cout] = nhwc(act, torch.bfloat16)                      # plain accumulate: out += alpha * conv
+    nv().conv2d_fwd(xo, wp, None, None, None, None, out[..., :cout], cout, False, True, 0, 0, 0.5, ops.CONV_TC)
     assert relerr(nchw(out[..., :cout]), 0.5 * F.conv2d(x, wt, None, 1, k // 2) + act) <= BF16_TOL
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
 
