@@ -93,6 +93,26 @@ __device__ __forceinline__ void st8(bf16* p, const f8& x) {
   *reinterpret_cast<uint4*>(p) = t;
 }
 
+// ---- 16-wide store: one 256-bit access for bf16 (sm_100; p must be 32-byte aligned), 4 x 128-bit for f32 -------
+// (a thread-per-pixel kernel that writes a pixel as 16-byte pieces touches half a 32-byte sector per instruction)
+struct f16v { float v[16]; };
+__device__ __forceinline__ void st16(bf16* p, const f16v& x) {
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(x.v[2 * i], x.v[2 * i + 1]);
+    r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void st16(float* p, const f16v& x) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(p + 4 * i) = make_float4(x.v[4 * i], x.v[4 * i + 1], x.v[4 * i + 2], x.v[4 * i + 3]);
+}
+
 // ---- reductions ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

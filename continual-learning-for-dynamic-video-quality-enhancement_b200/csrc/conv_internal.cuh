@@ -1,8 +1,16 @@
 // Internal interface between the conv ABI entry points (conv.cu) and the two engines.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace nv {
+
+// every bf16 epilogue operand present allows 256-bit accesses (32-byte aligned base, pitch a multiple of 16 channels)
+static inline int epi_v256(const nervecl_conv_params& a) {
+  auto ok = [](const void* p, int64_t ld) { return !p || (ld % 16 == 0 && nv::aligned(p, 32)); };
+  return a.out_dtype == NERVECL_BF16 && ok(a.out, a.ldo) && ok(a.res, a.ldres) && ok(a.mask, a.ldmask) &&
+         ok(a.mask_sub, a.ldmask_sub) && !getenv("NERVECL_NO_V256");
+}
 
 int conv_simt_fwd(const nervecl_conv_params& a, cudaStream_t s);
 int conv_simt_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, float* dw, float* db,

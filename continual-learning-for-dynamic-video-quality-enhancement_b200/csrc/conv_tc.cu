@@ -256,7 +256,7 @@ int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.mask = (const bf16*)a.mask; t.ldmask = a.ldmask;
   t.msub = (const bf16*)a.mask_sub; t.ldmsub = a.ldmask_sub;
   t.out = a.out; t.ldo = a.ldo;
-  t.colsum = nullptr;
+  t.colsum = nullptr; t.v256_out = 0; t.v256_in = 0; t.v256_gen = epi_v256(a);
 
   const size_t stage_bytes = ((size_t)BM * KC * 2 + (size_t)BN * KC * 2 + 1023) & ~(size_t)1023;
   int stages = (int)((200 * 1024) / stage_bytes);

@@ -16,6 +16,9 @@ struct EpiArgs {
   const bf16* msub; int64_t ldmsub;
   void* out;        int64_t ldo;
   float* colsum;    // optional per-channel sum of the written values (row kernel, mask-gated lean epilogue only)
+  int v256_out;     // out rows / channel offsets are 32-byte aligned: one 256-bit store per 16-channel chunk
+  int v256_in;      // same for the mask / residual operand of the lean epilogues (one 256-bit load)
+  int v256_gen;     // generic epilogue: out, res, mask and mask_sub all allow 256-bit accesses
 };
 
 // 16 consecutive bf16 (two 16-byte loads) -> fp32
@@ -46,11 +49,36 @@ __device__ __forceinline__ void store16(bf16* p, const float (&f)[16]) {
   *reinterpret_cast<uint4*>(p) = r[0];
   *reinterpret_cast<uint4*>(p + 8) = r[1];
 }
+// 32 bytes (16 bf16) per thread: one full 32-byte sector per instruction when the address allows it (sm_100
+// 256-bit global accesses); the two 16-byte halves of a thread otherwise go out as separate half-sector writes
+__device__ __forceinline__ void store16(bf16* p, const float (&f)[16], bool v256) {
+  if (!v256) { store16(p, f); return; }
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void load32B(const bf16* p, uint4& lo, uint4& hi, bool v256) {
+  if (v256) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+  } else {
+    lo = *reinterpret_cast<const uint4*>(p);
+    hi = *reinterpret_cast<const uint4*>(p + 8);
+  }
+}
 __device__ __forceinline__ void store16(float* p, const float (&f)[16]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(p + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
 }
+__device__ __forceinline__ void store16(float* p, const float (&f)[16], bool) { store16(p, f); }
 
 // One 16-column chunk of the epilogue in two phases so that the TMEM load and every global load of
 // (up to) two chunks are in flight together before anything is consumed.
@@ -70,12 +98,13 @@ struct EpiChunk {
     has_res = a.res && c0 < a.res_channels;
     has_mask = a.mask && c0 >= a.mask_c0;
     if (vec) {
-      if (a.accumulate) load16(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c0, acc);
-      if (has_res) load16(a.res + p * a.ldres + c0, res);
+      const bool v = a.v256_gen != 0;
+      if (a.accumulate) load32B(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c0, acc[0], acc[1], v);
+      if (has_res) load32B(a.res + p * a.ldres + c0, res[0], res[1], v);
       if (has_mask) {
         if (have_pm) { msk[0] = pm0; msk[1] = pm1; }
-        else load16(a.mask + p * a.ldmask + c0, msk);
-        if (a.msub) load16(a.msub + p * a.ldmsub + c0, sub);
+        else load32B(a.mask + p * a.ldmask + c0, msk[0], msk[1], v);
+        if (a.msub) load32B(a.msub + p * a.ldmsub + c0, sub[0], sub[1], v);
       }
     }
   }
@@ -123,7 +152,7 @@ struct EpiChunk {
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = t[j] > 0.f ? f[j] : 0.f;
       }
-      store16(op, f);
+      store16(op, f, a.v256_gen != 0);
     } else {
       // ragged chunk (Cout tail, or a range boundary inside the chunk): element-wise
       for (int j = 0; j < 16; ++j) {

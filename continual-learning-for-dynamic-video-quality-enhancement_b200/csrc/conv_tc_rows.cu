@@ -73,7 +73,7 @@ __device__ __forceinline__ int wtile_index(const RowArgs& a, int kx, int c) {
 // One 16-channel chunk of a lean epilogue (bf16 out): kind 1: relu?(acc + bias); 2: alpha * acc where mask > 0;
 // 3: alpha * acc + residual.  e0/e1 hold the chunk's 16 mask / residual values.
 __device__ __forceinline__ void lean_emit(int kind, const uint32_t (&v)[16], const uint4& e0, const uint4& e1, bf16* op,
-                                          const float* bias, bool relu, float alpha) {
+                                          const float* bias, bool relu, float alpha, bool v256) {
   float f[16];
   if (kind == 1) {
 #pragma unroll
@@ -102,7 +102,7 @@ __device__ __forceinline__ void lean_emit(int kind, const uint32_t (&v)[16], con
       }
     }
   }
-  store16(op, f);
+  store16(op, f, v256);
 }
 
 // The CTA's share of the linearised output rows ((n * strips + strip) * H + y), split evenly (to within one row)
@@ -358,6 +358,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int kind = a.fast;
       const bool relu = a.relu != 0;
       const float alpha = a.alpha;
+      const bool vo = a.v256_out != 0, vi = a.v256_in != 0;
       ItemIter it(a);
       int n, strip, y0, rows;
       while (it.next(a, n, strip, y0, rows)) {
@@ -375,9 +376,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int i = 0; i < 4; ++i) {
             e[i][0] = e[i][1] = make_uint4(0, 0, 0, 0);
             if (kind >= 2 && valid && part + 2 * i < nch_all) {
-              const uint4* e4 = reinterpret_cast<const uint4*>(ep + i * 32);
-              e[i][0] = e4[0];
-              e[i][1] = e4[1];
+              load32B(ep + i * 32, e[i][0], e[i][1], vi);
             }
           }
           ep += estride;
@@ -394,9 +393,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (ha) tmem_st16_zero(tcol + (uint32_t)(i * 32));                  // re-arm the slot for its next output row
             if (hb) tmem_st16_zero(tcol + (uint32_t)(i * 32 + 32));
             if (valid) {
-              if (ha) lean_emit(kind, va, e[i][0], e[i][1], op + i * 32, a.bias ? a.bias + cf + i * 32 : nullptr, relu, alpha);
+              if (ha) lean_emit(kind, va, e[i][0], e[i][1], op + i * 32, a.bias ? a.bias + cf + i * 32 : nullptr, relu, alpha, vo);
               if (hb) lean_emit(kind, vb, e[i + 1][0], e[i + 1][1], op + i * 32 + 32,
-                                a.bias ? a.bias + cf + i * 32 + 32 : nullptr, relu, alpha);
+                                a.bias ? a.bias + cf + i * 32 + 32 : nullptr, relu, alpha, vo);
             }
           }
           op += ostride;
@@ -426,6 +425,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const bool want_cs = PF && a.colsum != nullptr;
       const bool relu = a.relu != 0;
       const float alpha = a.alpha;
+      const bool vo = a.v256_out != 0, vi = a.v256_in != 0;
       ItemIter it(a);
       int n, strip, y0, rows;
       while (it.next(a, n, strip, y0, rows)) {
@@ -443,9 +443,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
           for (int d = 0; d < 4; ++d)
             if (d < rows) {
-              const uint4* m4 = reinterpret_cast<const uint4*>(mp + d * mstride);
-              mqa[d] = m4[0];
-              mqb[d] = m4[1];
+              load32B(mp + d * mstride, mqa[d], mqb[d], vi);
             }
         }
         for (int oi4 = 0; oi4 < rows; oi4 += 4) {
@@ -455,16 +453,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (oi >= rows) break;
             uint4 m0 = mqa[D], m1 = mqb[D];
             if (PF && valid && has0 && oi + 4 < rows) {
-              const uint4* m4 = reinterpret_cast<const uint4*>(mp + (int64_t)(oi + 4) * mstride);
-              mqa[D] = m4[0];
-              mqb[D] = m4[1];
+              load32B(mp + (int64_t)(oi + 4) * mstride, mqa[D], mqb[D], vi);
             }
             uint4 e0 = m0, e1 = m1, e2 = m0, e3 = m1;
             if (!PF && a.fast >= 2 && valid && has0) {                 // issued before the wait: latency overlaps it
-              const uint4* e4 = reinterpret_cast<const uint4*>(ep);
-              e0 = e4[0];
-              e1 = e4[1];
-              if (two) { e2 = e4[4]; e3 = e4[5]; }
+              load32B(ep, e0, e1, vi);
+              if (two) load32B(ep + 32, e2, e3, vi);
             }
             ep += estride;
             mbar_wait(&acc_full[slot], par);
@@ -484,14 +478,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   f[j] = __uint_as_float(v0[j]) + bz0[j];
                   if (relu) f[j] = fmaxf(f[j], 0.f);
                 }
-                store16(op, f);
+                store16(op, f, vo);
                 if (two) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     f[j] = __uint_as_float(v1[j]) + bz1[j];
                     if (relu) f[j] = fmaxf(f[j], 0.f);
                   }
-                  store16(op + 32, f);
+                  store16(op + 32, f, vo);
                 }
               } else if (a.fast == 2) {                              // alpha * acc where mask > 0
                 const uint32_t mw[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -501,7 +495,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   f[2 * j] = ml > 0.f ? alpha * __uint_as_float(v0[2 * j]) : 0.f;
                   f[2 * j + 1] = mh > 0.f ? alpha * __uint_as_float(v0[2 * j + 1]) : 0.f;
                 }
-                store16(op, f);
+                store16(op, f, vo);
                 if (want_cs) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) cs[j] += f[j];
@@ -514,7 +508,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     f[2 * j] = ml > 0.f ? alpha * __uint_as_float(v1[2 * j]) : 0.f;
                     f[2 * j + 1] = mh > 0.f ? alpha * __uint_as_float(v1[2 * j + 1]) : 0.f;
                   }
-                  store16(op + 32, f);
+                  store16(op + 32, f, vo);
                 }
               } else {                                               // fast == 3: alpha * acc + residual
                 const uint32_t rw[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -523,7 +517,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   f[2 * j] = fmaf(alpha, __uint_as_float(v0[2 * j]), __uint_as_float(rw[j] << 16));
                   f[2 * j + 1] = fmaf(alpha, __uint_as_float(v0[2 * j + 1]), __uint_as_float(rw[j] & 0xFFFF0000u));
                 }
-                store16(op, f);
+                store16(op, f, vo);
                 if (two) {
                   const uint32_t sw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
 #pragma unroll
@@ -531,7 +525,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     f[2 * j] = fmaf(alpha, __uint_as_float(v1[2 * j]), __uint_as_float(sw[j] << 16));
                     f[2 * j + 1] = fmaf(alpha, __uint_as_float(v1[2 * j + 1]), __uint_as_float(sw[j] & 0xFFFF0000u));
                   }
-                  store16(op + 32, f);
+                  store16(op + 32, f, vo);
                 }
               }
             }
@@ -749,6 +743,10 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.msub = (const bf16*)a.mask_sub; t.ldmsub = a.ldmask_sub;
   t.out = a.out; t.ldo = a.ldo;
   t.colsum = a.colsum;
+  // 256-bit epilogue accesses: 16-channel chunks start on 32-byte boundaries of 32-byte aligned pixels
+  t.v256_out = a.out_dtype == NERVECL_BF16 && a.ldo % 16 == 0 && aligned(a.out, 32);
+  t.v256_in = 0;
+  t.v256_gen = epi_v256(a);
   t.N = a.N; t.H = a.H; t.W = a.W;
   t.NOUT = p.NOUT; t.nchunks = p.nchunks; t.ksteps_last = p.ksteps_last;
   t.nchunks2 = p.nchunks2; t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
@@ -770,6 +768,9 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   }
 
   // one CTA per SM (per channel group); each takes an equal share of the N * strips * H output rows
+  if (t.fast == 2) t.v256_in = a.ldmask % 16 == 0 && aligned(a.mask, 32);
+  if (t.fast == 3) t.v256_in = t.ldres % 16 == 0 && aligned(t.res, 32);
+  if (getenv("NERVECL_NO_V256")) t.v256_out = t.v256_in = 0;
   if (a.colsum && !(t.fast == 2 && p.NOUT <= 32)) return NERVECL_EUNSUPPORTED;
   const int64_t total_rows = (int64_t)a.N * p.strips * a.H;
   dim3 grid((unsigned)imin(cdiv(total_rows, 4), imax(1, sms / p.nsplit)), (unsigned)p.nsplit);

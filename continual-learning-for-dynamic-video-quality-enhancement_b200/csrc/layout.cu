@@ -65,7 +65,7 @@ NV_API int nervecl_pack_frames(const float* src, int64_t sB, int64_t sT, int64_t
 }
 
 // (B,T,C,H,W) strided fp32 -> [T][B][H][W][c*9 + tap] (3x3 unfold, zero padding); ldd % 8 == 0
-template <typename T>
+template <typename T, bool W16>
 __global__ void pack_frames_unfold3_kernel(const float* __restrict__ src, int64_t sB, int64_t sT, int64_t sC,
                                            int64_t sH, T* __restrict__ dst, int64_t ldd, int B, int Tn, int C,
                                            int H, int W) {
@@ -80,6 +80,19 @@ __global__ void pack_frames_unfold3_kernel(const float* __restrict__ src, int64_
     int t = (int)(r / B);
     const float* s = src + b * sB + t * sT;
     T* d = dst + i * ldd;
+    if (W16) {                                              // 32-byte aligned rows: full-sector stores
+      for (int c16 = 0; c16 < (int)ldd; c16 += 16) {
+        f16v v;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int col = c16 + k, c = col / 9, tap = col - c * 9;
+          const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+          v.v[k] = (c < C && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(s + c * sC + yy * sH + xx) : 0.f;
+        }
+        st16(d + c16, v);
+      }
+      continue;
+    }
     for (int c8 = 0; c8 < (int)ldd; c8 += 8) {
       f8 v;
 #pragma unroll
@@ -100,8 +113,13 @@ NV_API int nervecl_pack_frames_unfold3(const float* src, int64_t sB, int64_t sT,
   if ((ldd & 7) || !aligned(dst, 16)) return NERVECL_EALIGN;
   int64_t total = (int64_t)T * B * H * W;
   int blocks = (int)imin(cdiv(total, 256), kSMs * 16);
-  NV_DISPATCH_DTYPE(dtype, E, (pack_frames_unfold3_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
-                                  src, sB, sT, sC, sH, (E*)dst, ldd, B, T, C, H, W)));
+  if (!(ldd & 15) && aligned(dst, 32)) {
+    NV_DISPATCH_DTYPE(dtype, E, (pack_frames_unfold3_kernel<E, true><<<blocks, 256, 0, as_stream(stream)>>>(
+                                    src, sB, sT, sC, sH, (E*)dst, ldd, B, T, C, H, W)));
+  } else {
+    NV_DISPATCH_DTYPE(dtype, E, (pack_frames_unfold3_kernel<E, false><<<blocks, 256, 0, as_stream(stream)>>>(
+                                    src, sB, sT, sC, sH, (E*)dst, ldd, B, T, C, H, W)));
+  }
   return launch_status();
 }
 
@@ -131,6 +149,19 @@ __global__ void unfold3_grad_kernel(const TS* __restrict__ src, int64_t lds, int
       }
     }
     TD* d = dst + i * ldd;
+    if (VEC && ldd == 32) {                                // (VEC also asserts a 32-byte aligned dst: full-sector stores)
+#pragma unroll
+      for (int c16 = 0; c16 < 32; c16 += 16) {
+        f16v o16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int col = c16 + k;
+          o16.v[k] = col < 27 ? v[col / 9][col % 9] : 0.f;
+        }
+        st16(d + c16, o16);
+      }
+      continue;
+    }
 #pragma unroll
     for (int c8 = 0; c8 < 32; c8 += 8) {                   // (ldd <= 32; static columns: no dynamic register indexing)
       if (c8 >= (int)ldd) break;
@@ -156,7 +187,7 @@ NV_API int nervecl_unfold3_grad(const void* src, int64_t lds, int src_dtype, int
   if (src_dtype == NERVECL_F32 && dst_dtype == NERVECL_F32) NV_UNF(float, float, false);
   else if (src_dtype == NERVECL_F32 && dst_dtype == NERVECL_BF16) NV_UNF(float, bf16, false);
   else if (src_dtype == NERVECL_BF16 && dst_dtype == NERVECL_BF16) {
-    if (lds >= 4 && !(lds & 3) && aligned(src, 8)) NV_UNF(bf16, bf16, true); else NV_UNF(bf16, bf16, false);
+    if (lds >= 4 && !(lds & 3) && aligned(src, 8) && aligned(dst, 32)) NV_UNF(bf16, bf16, true); else NV_UNF(bf16, bf16, false);
   } else return NERVECL_EDTYPE;
 #undef NV_UNF
   return launch_status();
