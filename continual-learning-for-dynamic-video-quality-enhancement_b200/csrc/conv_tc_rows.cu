@@ -231,6 +231,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       int jbase = 0;                      // output rows issued so far by this CTA (running index -> TMEM slot)
       bool ready = false;                 // early, non-blocking probe of the next chunk's barrier succeeded
       bool acc_ready = false;             // same for the accumulator slot the next input row starts
+      // "output row final" commit of the previous input row, issued behind the first MMAs of the next one: the
+      // issuing thread is blocked on the MMA queue there anyway, so the commit's ~125 cycles leave the row-to-row
+      // critical path (the accumulator ring has >= 4 slots: the slot is not needed again before that)
+      int pend = -1;
       mbar_wait(w_bar, 0);
       ItemIter it(a);
       int n_, strip_, y0_, rows;
@@ -273,7 +277,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int nstage = stage + 1;
             uint32_t nphase = phase;
             if (nstage == a.stages) { nstage = 0; nphase ^= 1; }
+            const int commit_pend = gi == 0 ? pend : -1;
             if (elect_one()) {
+              bool first = commit_pend >= 0;
+              if ((a.dbg & 1) && first) { umma_commit(&acc_full[commit_pend]); first = false; }
               if (!(a.dbg & 1)) {
                 for (int cc = 0; cc < a.cps; ++cc) {
                   const int c = gi * a.cps + cc;
@@ -302,13 +309,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int k = 0; k < KC / 16 - 1; ++k)
                           if (k < ks) umma_bf16_acc(d, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)(bl + 2u * k), id);
                       }
+                      if (first) { umma_commit(&acc_full[commit_pend]); first = false; }
                     }
                   }
                 }
               }
+              if (first) umma_commit(&acc_full[commit_pend]);                 // (no MMA was issued in this stage)
               umma_commit(&ch_empty[stage]);                                  // stage consumed when these MMAs retire
-              if (gi == ngrp - 1 && ri >= 2) umma_commit(&acc_full[s0]);      // output row ri-2 (slot s0) is final
             }
+            if (gi == 0) pend = -1;
             // probe the next stage's barrier (and, after the row's last stage, the accumulator slot of the next
             // row) now: the latencies overlap each other and the MMAs just issued
             ready = mbar_try_wait(&ch_full[nstage], nphase);
@@ -320,10 +329,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             stage = nstage;
             phase = nphase;
           }
+          if (ri >= 2) pend = s0;                                             // output row ri-2 (slot s0) is final
           if (++s2 == S) { s2 = 0; ++r2; }
         }
         jbase += rows;
       }
+      if (pend >= 0 && elect_one()) umma_commit(&acc_full[pend]);
+      __syncwarp();
     }
   } else {
     // ================= epilogue (warps 2..9) =================
