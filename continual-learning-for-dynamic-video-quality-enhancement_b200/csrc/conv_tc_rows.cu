@@ -235,6 +235,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // issuing thread is blocked on the MMA queue there anyway, so the commit's ~125 cycles leave the row-to-row
       // critical path (the accumulator ring has >= 4 slots: the slot is not needed again before that)
       int pend = -1;
+      // same for the "stage consumed" commit (behind the second MMA group) -- only with a deep ring: with the two
+      // whole-row stages of the K >= 160 layers the refill latency is exposed and deferring costs 25-40 %
+      int pend_stage = -1;
+      const bool defer_stage = a.stages >= 4;
       mbar_wait(w_bar, 0);
       ItemIter it(a);
       int n_, strip_, y0_, rows;
@@ -280,6 +284,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int commit_pend = gi == 0 ? pend : -1;
             if (elect_one()) {
               bool first = commit_pend >= 0;
+              int second_left = pend_stage >= 0 ? 2 : 0;          // k-loops until the deferred stage commit goes out
               if ((a.dbg & 1) && first) { umma_commit(&acc_full[commit_pend]); first = false; }
               if (!(a.dbg & 1)) {
                 for (int cc = 0; cc < a.cps; ++cc) {
@@ -310,13 +315,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                           if (k < ks) umma_bf16_acc(d, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)(bl + 2u * k), id);
                       }
                       if (first) { umma_commit(&acc_full[commit_pend]); first = false; }
+                      if (second_left && --second_left == 0) umma_commit(&ch_empty[pend_stage]);
                     }
                   }
                 }
               }
               if (first) umma_commit(&acc_full[commit_pend]);                 // (no MMA was issued in this stage)
-              umma_commit(&ch_empty[stage]);                                  // stage consumed when these MMAs retire
+              if (second_left) umma_commit(&ch_empty[pend_stage]);            // (fewer than two MMA groups in this stage)
+              if (!defer_stage) umma_commit(&ch_empty[stage]);                // stage consumed when these MMAs retire
             }
+            pend_stage = defer_stage ? stage : -1;
             if (gi == 0) pend = -1;
             // probe the next stage's barrier (and, after the row's last stage, the accumulator slot of the next
             // row) now: the latencies overlap each other and the MMAs just issued
@@ -334,7 +342,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         jbase += rows;
       }
-      if (pend >= 0 && elect_one()) umma_commit(&acc_full[pend]);
+      if (elect_one()) {
+        if (pend_stage >= 0) umma_commit(&ch_empty[pend_stage]);
+        if (pend >= 0) umma_commit(&acc_full[pend]);
+      }
       __syncwarp();
     }
   } else {
