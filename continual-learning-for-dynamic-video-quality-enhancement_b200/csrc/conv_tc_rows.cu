@@ -73,7 +73,7 @@ __device__ __forceinline__ int wtile_index(const RowArgs& a, int kx, int c) {
 // One 16-channel chunk of a lean epilogue (bf16 out): kind 1: relu?(acc + bias); 2: alpha * acc where mask > 0;
 // 3: alpha * acc + residual.  e0/e1 hold the chunk's 16 mask / residual values.
 __device__ __forceinline__ void lean_emit(int kind, const uint32_t (&v)[16], const uint4& e0, const uint4& e1, bf16* op,
-                                          const float* bias, bool relu, float alpha, bool v256) {
+                                          const float* bias, bool relu, float alpha, bool v256, bool add_res = false) {
   float f[16];
   if (kind == 1) {
 #pragma unroll
@@ -87,6 +87,14 @@ __device__ __forceinline__ void lean_emit(int kind, const uint32_t (&v)[16], con
     if (relu) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (add_res) {
+      const uint32_t w[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[2 * j] += __uint_as_float(w[j] << 16);
+        f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+      }
     }
   } else {
     const uint32_t w[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -391,14 +399,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int cf = c_lo + part * 16;                         // first channel of this thread's first chunk
         bf16* op = reinterpret_cast<bf16*>(a.out) + p0 * a.ldo + cf;
         const int64_t ostride = (int64_t)a.W * a.ldo;
-        const bf16* ep = kind == 3 ? a.res + p0 * a.ldres + cf : a.mask + p0 * a.ldmask + cf;
-        const int64_t estride = (int64_t)a.W * (kind == 3 ? a.ldres : a.ldmask);
+        const bool has_e = kind >= 2 || a.res != nullptr;       // kind 1 may carry a residual (added after the ReLU)
+        const bf16* ep = kind != 2 ? a.res + p0 * a.ldres + cf : a.mask + p0 * a.ldmask + cf;
+        const int64_t estride = (int64_t)a.W * (kind != 2 ? a.ldres : a.ldmask);
         for (int oi = 0; oi < rows; ++oi) {
           uint4 e[4][2];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             e[i][0] = e[i][1] = make_uint4(0, 0, 0, 0);
-            if (kind >= 2 && valid && part + 2 * i < nch_all) {
+            if (has_e && valid && part + 2 * i < nch_all) {
               load32B(ep + i * 32, e[i][0], e[i][1], vi);
             }
           }
@@ -416,9 +425,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (ha) tmem_st16_zero(tcol + (uint32_t)(i * 32));                  // re-arm the slot for its next output row
             if (hb) tmem_st16_zero(tcol + (uint32_t)(i * 32 + 32));
             if (valid) {
-              if (ha) lean_emit(kind, va, e[i][0], e[i][1], op + i * 32, a.bias ? a.bias + cf + i * 32 : nullptr, relu, alpha, vo);
+              if (ha) lean_emit(kind, va, e[i][0], e[i][1], op + i * 32, a.bias ? a.bias + cf + i * 32 : nullptr, relu, alpha, vo, kind == 1 && has_e);
               if (hb) lean_emit(kind, vb, e[i + 1][0], e[i + 1][1], op + i * 32 + 32,
-                                a.bias ? a.bias + cf + i * 32 + 32 : nullptr, relu, alpha, vo);
+                                a.bias ? a.bias + cf + i * 32 + 32 : nullptr, relu, alpha, vo, kind == 1 && has_e);
             }
           }
           op += ostride;
@@ -460,8 +469,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bf16* mp = a.mask + p0 * a.ldmask + ch0;
         const int64_t mstride = (int64_t)a.W * a.ldmask;
         // second epilogue operand when it is not prefetched: the mask (fast 2, NOUT = 64) or the residual (fast 3)
-        const bf16* ep = a.fast == 3 ? a.res + p0 * a.ldres + ch0 : mp;
-        const int64_t estride = a.fast == 3 ? (int64_t)a.W * a.ldres : mstride;
+        const bool res1 = !PF && a.fast == 1 && a.res != nullptr;   // bias / ReLU epilogue with a residual added after
+        const bf16* ep = (a.fast == 3 || res1) ? a.res + p0 * a.ldres + ch0 : mp;
+        const int64_t estride = (a.fast == 3 || res1) ? (int64_t)a.W * a.ldres : mstride;
         if (PF && valid && has0) {
 #pragma unroll
           for (int d = 0; d < 4; ++d)
@@ -479,7 +489,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               load32B(mp + (int64_t)(oi + 4) * mstride, mqa[D], mqb[D], vi);
             }
             uint4 e0 = m0, e1 = m1, e2 = m0, e3 = m1;
-            if (!PF && a.fast >= 2 && valid && has0) {                 // issued before the wait: latency overlaps it
+            if (!PF && (a.fast >= 2 || res1) && valid && has0) {       // issued before the wait: latency overlaps it
               load32B(ep, e0, e1, vi);
               if (two) load32B(ep + 32, e2, e3, vi);
             }
@@ -501,12 +511,28 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   f[j] = __uint_as_float(v0[j]) + bz0[j];
                   if (relu) f[j] = fmaxf(f[j], 0.f);
                 }
+                if (res1) {
+                  const uint32_t rw[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    f[2 * j] += __uint_as_float(rw[j] << 16);
+                    f[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+                  }
+                }
                 store16(op, f, vo);
                 if (two) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     f[j] = __uint_as_float(v1[j]) + bz1[j];
                     if (relu) f[j] = fmaxf(f[j], 0.f);
+                  }
+                  if (res1) {
+                    const uint32_t sw[8] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      f[2 * j] += __uint_as_float(sw[j] << 16);
+                      f[2 * j + 1] += __uint_as_float(sw[j] & 0xFFFF0000u);
+                    }
                   }
                   store16(op + 32, f, vo);
                 }
@@ -780,7 +806,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
                      p.NOUT <= 128 && !(t.dbg & 64);
   t.fast = 0;
   if (whole && !a.accumulate) {
-    if (!a.res && !a.mask && a.alpha == 1.0f) t.fast = 1;
+    if ((!a.res || a.res_channels >= a.Cout) && !a.mask && a.alpha == 1.0f && (a.bias || a.relu || !a.res)) t.fast = 1;
     if (!a.res && a.mask && !a.bias && !a.relu && a.mask_c0 == 0) t.fast = 2;
     if (a.res && a.res_channels >= a.Cout && !a.mask && !a.bias && !a.relu) t.fast = 3;
   } else if (whole && !a.res && !a.mask && !a.bias && !a.relu) {
@@ -792,7 +818,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
 
   // one CTA per SM (per channel group); each takes an equal share of the N * strips * H output rows
   if (t.fast == 2) t.v256_in = a.ldmask % 16 == 0 && aligned(a.mask, 32);
-  if (t.fast == 3) t.v256_in = t.ldres % 16 == 0 && aligned(t.res, 32);
+  if (t.fast == 3 || (t.fast == 1 && t.res)) t.v256_in = t.ldres % 16 == 0 && aligned(t.res, 32);
   if (getenv("NERVECL_NO_V256")) t.v256_out = t.v256_in = 0;
   if (a.colsum && !(t.fast == 2 && p.NOUT <= 32)) return NERVECL_EUNSUPPORTED;
   const int64_t total_rows = (int64_t)a.N * p.strips * a.H;

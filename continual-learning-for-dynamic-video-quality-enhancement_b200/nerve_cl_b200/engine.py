@@ -24,6 +24,8 @@ from __future__ import annotations
 import weakref
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -243,12 +245,16 @@ class Plan:
             self._free.append(acts)
 
     # ---- weights ---------------------------------------------------------------------------
-    def pack_weights(self, P: Dict[str, Tensor], need_bwd: bool) -> None:
+    def pack_weights(self, P: Dict[str, Tensor], need_bwd: bool, fold_bn: Optional[Dict[str, Tensor]] = None) -> None:
+        """``fold_bn``: pointwise conv name -> per-output-channel BatchNorm scale to fold into its packed weights
+        (pure inference, see ``forward``)."""
         ws, ds, fl = [], [], []
         for name in self.convs:
             w = P[name + ".weight"]
             if name == "feature_extractor.head.0":
                 w = w.view(w.shape[0], -1, 1, 1)           # OIHW flattening == unfolded channel order c*9 + tap
+            if fold_bn is not None and name in fold_bn:
+                w = w * fold_bn[name].view(-1, 1, 1, 1)
             ws.append(w); ds.append(self.wf[name]); fl.append(False)
             if need_bwd and name in self.wb:
                 ws.append(w); ds.append(self.wb[name]); fl.append(True)
@@ -345,7 +351,20 @@ class Plan:
         B, T, H, W, F, s = self.B, self.T, self.H, self.W, self.F, self.scale
         A = self.acquire()
         A.training = training
-        self.pack_weights(P, need_bwd)
+        # Pure inference (eval mode, no backward) on the tcgen05 path: BatchNorm's running statistics are folded into
+        # the pointwise conv -- W' = W * gamma / sqrt(var + eps) per output channel, b' = beta - mean * that -- so
+        # conv + BN + ReLU (+ the extractor skip) is ONE conv launch with a bias / ReLU / residual epilogue and the
+        # pre-BN tensor is never written (three full passes over the 64-channel extractor maps less per layer).
+        fold = ((not training) and (not need_bwd) and self.adt == torch.bfloat16 and self.engine != CONV_SIMT
+                and not os.environ.get("NERVECL_NO_BN_FOLD"))
+        fold_scale, fold_bias = {}, {}
+        if fold:
+            for j in range(3):
+                pre = f"feature_extractor.body.{j}."
+                sc = P[pre + "bn.weight"] * torch.rsqrt(BUF[pre + "bn.running_var"] + BN_EPS)
+                fold_scale[pre + "pointwise"] = sc
+                fold_bias[j] = (P[pre + "bn.bias"] - BUF[pre + "bn.running_mean"] * sc).contiguous()
+        self.pack_weights(P, need_bwd, fold_scale if fold else None)
 
         # ---- feature extractor over all T*B frames (super_resolution.py:346-349) ----
         nv.pack_frames_unfold3(lr_frames, A.x_in)
@@ -354,6 +373,13 @@ class Plan:
         for j in range(3):
             pre = f"feature_extractor.body.{j}."
             nv.dwconv3x3_fwd(x, P[pre + "depthwise.weight"], A.dwo[j], False, False)
+            if fold:
+                y = A.fact[j] if j < 2 else A.feat
+                with self._span("conv_fwd", A.dwo[j], F, F, 1):
+                    nv.conv2d_fwd(A.dwo[j], self.wf[pre + "pointwise"], fold_bias[j], A.head if j == 2 else None, None,
+                                  None, y, F, True, False, F if j == 2 else 0, 0, 1.0, self.engine)
+                x = y
+                continue
             self.conv(pre + "pointwise", A.dwo[j], A.pwo[j], P)
             if training:
                 nv.fill_zero(A.bn_sums[j])

@@ -85,7 +85,9 @@ class _SRFunction(torch.autograd.Function):
         names = module._param_names
         P = {n: p.detach() for n, p in zip(names, params)}
         BUF = {n: b for n, b in module.named_buffers()}
-        need_bwd = any(ctx.needs_input_grad[2:])     # False under no_grad or when nothing requires grad
+        # (needs_input_grad reflects requires_grad only; the grad mode of the CALLER is recorded by the module,
+        #  because autograd runs this method with grad mode off)
+        need_bwd = module._grad_mode and any(ctx.needs_input_grad[2:])
         plan = module._plan_for(lr_frames)
         B, T, C, H, W = lr_frames.shape
         s = module.scale_factor
@@ -166,6 +168,7 @@ class SuperResolutionNet(nn.Module):
         self.warp_div_mode = 0
         self._plans: Dict[Tuple, _engine.Plan] = {}
         self._keep_intermediate = False
+        self._grad_mode = True
         self._last_acts = None
         self._last_flat_grad: Optional[Tensor] = None
         self._grad_sync = None
@@ -230,6 +233,7 @@ class SuperResolutionNet(nn.Module):
         if lr_frames.dtype != torch.float32:
             lr_frames = lr_frames.float()
         self._keep_intermediate = return_intermediate
+        self._grad_mode = torch.is_grad_enabled()
         try:
             out = _SRFunction.apply(self, lr_frames, *self.parameters())
             if not return_intermediate:

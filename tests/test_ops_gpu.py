@@ -514,6 +514,10 @@ def test_conv_rows_lean_epilogues(k, cout):
                     0.5, ops.CONV_TC)
     assert relerr(nchw(out[..., :cout]), 0.5 * F.conv2d(x, wt, None, 1, k // 2) + act) <= BF16_TOL
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
+    nv().conv2d_fwd(xo, wp, b.cuda(), nhwc(act, torch.bfloat16), None, None, out[..., :cout], cout, True, False, cout,
+                    0, 1.0, ops.CONV_TC)                             # bias + ReLU, then the residual
+    assert relerr(nchw(out[..., :cout]), F.relu(F.conv2d(x, wt, b, 1, k // 2)) + act) <= BF16_TOL
+    assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
     out[..., :cout] = nhwc(act, torch.bfloat16)                      # plain accumulate: out += alpha * conv
     nv().conv2d_fwd(xo, wp, None, None, None, None, out[..., :cout], cout, False, True, 0, 0, 0.5, ops.CONV_TC)
     assert relerr(nchw(out[..., :cout]), 0.5 * F.conv2d(x, wt, None, 1, k // 2) + act) <= BF16_TOL

@@ -110,6 +110,31 @@ def test_module_contract():
         m(torch.rand(1, 3, 3, 16, 16))                       # CPU input: no fallback
 
 
+def test_bf16_inference_folds_batchnorm():
+    """Pure inference (eval, no_grad) folds the running BatchNorm statistics into the pointwise convs; the result must
+    agree with the unfolded eval forward (taken when a backward may follow) to bf16 noise."""
+    from nerve_cl_b200.models import SuperResolutionNet
+    torch.manual_seed(5)
+    model = SuperResolutionNet(scale_factor=2, num_features=64, num_residual_blocks=1).cuda()
+    model.compute_dtype = torch.bfloat16
+    x = torch.rand(2, 3, 3, 24, 136, device="cuda")
+    model.train()
+    for _ in range(2):                                    # move the running statistics away from (0, 1)
+        with torch.no_grad():
+            model(x)
+    model.eval()
+    y_ref = model(x)                                      # parameters require grad: unfolded path
+    with torch.no_grad():
+        y_fold = model(x)
+    assert y_ref.requires_grad and not y_fold.requires_grad
+    assert psnr(y_fold, y_ref.detach()) >= 50.0
+    model.compute_dtype = torch.float32                   # fp32 parity path never folds: bitwise the same forward
+    model._plans.clear()
+    with torch.no_grad():
+        y32 = model(x)
+    assert psnr(y_fold, y32) >= 40.0
+
+
 @pytest.mark.parametrize("cfg", [(2, 64, 2, 1, 2, 40, 160), (4, 64, 1, 2, 1, 24, 136)])
 def test_bf16_tcgen05_engine_gradients(cfg):
     """The bf16 path at a size where every fast kernel engages (row-streaming tcgen05 convs, fused dense-block
