@@ -351,7 +351,7 @@ def run_native(args):
     C = args.features
     px, pxT = B * H * W, B * T * H * W
     byte_model = {                       # kernel -> (bytes per launch, launches counted per span)
-        "warp_fwd": (2 * C * e + 8) * px, "warp_bwd": (3 * C * e + 16) * px,
+        "warp_fwd": (2 * C * e + 8) * px, "warp_bwd": (3 * C * e + 16) * px, "warp_bwd_lp": (3 * C * e + 16) * px,
         "corr_fwd": (2 * C * e + 96 * e) * px, "corr_bwd": (96 * e + 4 * C * e) * px,
         "dwconv3x3_fwd": 2 * C * e * pxT, "dwconv3x3_wgrad": 2 * C * e * pxT,
         "bn_stats": C * e * pxT, "bn_relu_fwd": 2 * C * e * pxT, "bn_relu_bwd_reduce": 2 * C * e * pxT,
