@@ -761,8 +761,13 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)a.W * ld * 2, (cuuint64_t)a.H * a.W * ld * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)PXB, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
+    // a channel count that is not a multiple of 64 ends inside a 128-byte line whose other half belongs to a
+    // neighbouring slice of the same buffer: 128-byte L2 promotion would fetch it from DRAM (ncu: 96 -> 32 read
+    // 128 channels' worth), 64-byte promotion does not
+    static const bool promo64 = !getenv("NERVECL_ROWS_PROMO128");
+    const CUtensorMapL2promotion promo = (C % KC && promo64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
   if (!encode_act(&tx, a.x, a.Cin, a.ldx)) return NERVECL_EUNSUPPORTED;
