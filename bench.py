@@ -339,6 +339,23 @@ def run_native(args):
     ms_infer = timed(infer_step, args.steps)
     model.train()
 
+    # ---- BASELINE.json configs[2]: x4 inference, 320x180 -> 1280x720, T=5 (clip-sharded: each rank its own clips) ----
+    ms_x4, x4_batch = None, 16
+    if args.dtype == "bf16" and (args.height, args.width) == (360, 640):
+        m4 = SuperResolutionNet(scale_factor=4, num_features=args.features, num_residual_blocks=args.blocks,
+                                temporal_window=2).to(dev).eval()
+        m4.compute_dtype = torch.bfloat16
+        lr4 = torch.rand(x4_batch, 5, 3, 180, 320, device=dev)
+
+        def infer4_step():
+            with torch.no_grad():
+                m4(lr4)
+
+        infer4_step()
+        infer4_step()
+        ms_x4 = timed(infer4_step, args.steps)
+        del m4, lr4
+
     if rank != 0:
         return
     pk = peaks()
@@ -437,6 +454,10 @@ def run_native(args):
         },
         "infer": {"metric": "sr_x2_infer_frames_per_sec", "value": frames / (ms_infer / 1e3), "unit": UNIT,
                   "ms_per_batch": ms_infer / args.steps, "note": "eval-mode forward only, same windows, inputs in HBM"},
+        "infer_x4": ({"metric": "sr_x4_infer_frames_per_sec", "value": x4_batch * world * args.steps / (ms_x4 / 1e3),
+                      "unit": UNIT, "ms_per_batch": ms_x4 / args.steps,
+                      "note": "BASELINE configs[2]: scale 4, T=5, 320x180 -> 1280x720, B=16/GPU, eval forward, inputs in HBM"}
+                     if ms_x4 else None),
         "hbm_kernels": {"peak_GBs": hbm_peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk['_source']})",
                         "kernels": hbm_kernels},
         "loss_last": losses[-1] if losses else None,
