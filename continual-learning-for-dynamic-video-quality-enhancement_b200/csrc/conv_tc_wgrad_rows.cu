@@ -45,6 +45,9 @@ struct WgrArgs {
   // per class: M tile, ky, first dY column, UMMA N, dY chunks, first CTA of the class, CTAs in the class
   int c_mt[kMaxClasses], c_ky[kMaxClasses], c_col0[kMaxClasses], c_n16[kMaxClasses], c_nby[kMaxClasses],
       c_cta0[kMaxClasses], c_ctas[kMaxClasses];
+  // an M tile with <= 64 live channels carries a SECOND kernel row in its upper 64 accumulator rows: the same
+  // channels of input row y + ky2 - 1 (-1: none), so its three taps need two classes instead of three
+  int c_ky2[kMaxClasses];
   int stages;
   float scale;
 };
@@ -130,6 +133,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   for (int c = 1; c < a.nclasses; ++c)
     if ((int)blockIdx.x >= a.c_cta0[c]) cls = c;
   const int mt = a.c_mt[cls], ky = a.c_ky[cls], col0 = a.c_col0[cls], n16 = a.c_n16[cls], nby = a.c_nby[cls];
+  const int ky2 = a.c_ky2[cls];
   const int idx = blockIdx.x - a.c_cta0[cls], nctas = a.c_ctas[cls];
   const uint32_t stage_bytes = 2u * XCHUNK + 3u * YCHUNK;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
@@ -162,7 +166,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       uint32_t phase = 0;
       // channel chunks of this M tile that exist (the second one may lie entirely beyond Cx: not loaded; its
       // accumulator rows are never drained)
-      const int nxc = (mt * 128 + KC < a.Cx) ? 2 : 1;
+      const int nxc = (mt * 128 + KC < a.Cx || ky2 >= 0) ? 2 : 1;
       const uint32_t bytes = (uint32_t)nxc * (PXB * ROWB) + (uint32_t)nby * YCHUNK;
       for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
         const int strip = (int)(rt % a.strips);
@@ -174,7 +178,8 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         uint8_t* sx = smem + (size_t)stage * stage_bytes;
         uint8_t* sy = sx + 2 * XCHUNK;
         for (int c = 0; c < nxc; ++c)
-          tma_load_4d(sx + (size_t)c * XCHUNK, &tmap_x, &full_bar[stage], mt * 128 + c * KC, x0 - 1, y + ky - 1, n);
+          tma_load_4d(sx + (size_t)c * XCHUNK, &tmap_x, &full_bar[stage], mt * 128 + (ky2 >= 0 ? 0 : c * KC), x0 - 1,
+                      y + (ky2 >= 0 && c ? ky2 : ky) - 1, n);
         for (int c = 0; c < nby; ++c)
           tma_load_4d(sy + (size_t)c * YCHUNK, &tmap_dy, &full_bar[stage], col0 + c * KC, x0, y, n);
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -215,13 +220,15 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   } else {
     // drain: TMEM -> fp32 atomics into the OIHW gradients
     const int q = warp & 3;
-    const int c = mt * 128 + q * 32 + lane;                  // input channel of this lane
+    const bool upper = ky2 >= 0 && q >= 2;                   // this lane's accumulator row belongs to kernel row ky2
+    const int c = mt * 128 + q * 32 + lane - (upper ? 64 : 0);   // input channel of this lane
+    const int kyl = upper ? ky2 : ky;
     const bool any = idx < row_tiles;
     mbar_wait(done_bar, 0);
     tc_fence_after();
     if (any) {
       for (int kx = 0; kx < 3; ++kx) {
-        const int tap = ky * 3 + kx;
+        const int tap = kyl * 3 + kx;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kx * n16);
         for (int c0 = 0; c0 < n16; c0 += 16) {
           uint32_t v[16];
@@ -297,8 +304,11 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
     lo = lo / 8 * 8;                                           // 16-byte aligned TMA start
     const int n16 = (hi - lo + 15) / 16 * 16;
     if (3 * n16 > 512) return NERVECL_EUNSUPPORTED;
+    const bool half = Cx - mt * 128 <= KC;                     // <= 64 live channels: two kernel rows per class
     for (int ky = 0; ky < 3; ++ky) {
+      if (half && ky == 1) continue;                           // (rides in the upper half of the ky = 0 class)
       const int c = a.nclasses++;
+      a.c_ky2[c] = half && ky == 0 ? 1 : -1;
       a.c_mt[c] = mt; a.c_ky[c] = ky; a.c_col0[c] = lo; a.c_n16[c] = n16; a.c_nby[c] = (n16 + KC - 1) / KC;
       const double mma = 24.0 * n16 / 2.0;
       const double ld = (2.0 * PXB * ROWB + a.c_nby[c] * YCHUNK) / 48.0;
