@@ -1,0 +1,39 @@
+"""Batched clip inference: window table pinned to the reference's enhance_video, batched run."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import psnr  # noqa: F401  (path setup)
+
+
+def test_sr_window_indices_match_reference_enhance_video():
+    from nerve_cl_b200.inference import sr_window_indices
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "enhance_windows.npz"))
+    assert len(g.files) == 36
+    for key in g.files:
+        sr_w, rec_w, T = map(int, re.match(r"sr(\d+)_rec(\d+)_T(\d+)", key).groups())
+        got = sr_window_indices(T, sr_w, rec_w).numpy()
+        assert np.array_equal(got, g[key]), key
+
+
+@pytest.mark.gpu
+def test_enhance_video_batched_equals_per_frame_loop():
+    from nerve_cl_b200.inference import enhance_video, sr_window_indices
+    from nerve_cl_b200.models import SuperResolutionNet
+    torch.manual_seed(3)
+    model = SuperResolutionNet(scale_factor=2, num_features=16, num_residual_blocks=1).cuda().eval()
+    video = torch.rand(2, 5, 3, 16, 72, device="cuda")
+    out = enhance_video(model, video, batch_size=4)
+    assert out.shape == (2, 5, 3, 32, 144)
+    idx = sr_window_indices(5, 1, 2)
+    with torch.no_grad():
+        for t in range(5):
+            ref = model(video[:, idx[t].tolist()])
+            assert float((out[:, t] - ref).abs().max()) <= 1e-5, t     # same kernels, same inputs (atomics order aside)
+    single = enhance_video(model, video[0], batch_size=16)
+    assert float((single - out[0]).abs().max()) <= 1e-5
+    blend = enhance_video(model, video, batch_size=16, enhancement_strength=0.25)
+    assert float((blend - out).abs().max()) > 0
