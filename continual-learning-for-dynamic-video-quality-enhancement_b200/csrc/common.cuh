@@ -1,5 +1,6 @@
 // Shared device/host helpers for libnervecl (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,6 +10,15 @@
 #define NV_API extern "C" __attribute__((visibility("default")))
 
 namespace nv {
+
+// Tuning / profiling knobs (NERVECL_* environment variables) are read only by libraries built with -DNERVECL_TUNING;
+// the default build has no environment-dependent behaviour at all.
+#ifdef NERVECL_TUNING
+inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+inline const char* tune_env(const char*) { return nullptr; }
+#endif
+
 
 typedef __nv_bfloat16 bf16;
 

@@ -37,7 +37,7 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
   if (engine == NERVECL_CONV_TC) {               // best tcgen05 kernel for the shape
     // (1x1: the row kernel wins while the per-row MMA count stays small; wide inputs are at the HBM roofline
     //  with the per-tap kernel already)
-    static const int k1_max_cin = getenv("NERVECL_ROWS_K1_MAXCIN") ? atoi(getenv("NERVECL_ROWS_K1_MAXCIN")) : 128;
+    static const int k1_max_cin = nv::tune_env("NERVECL_ROWS_K1_MAXCIN") ? atoi(nv::tune_env("NERVECL_ROWS_K1_MAXCIN")) : 128;
     if ((p->K == 3 || p->Cin <= k1_max_cin) && conv_rows_supported(*p)) return conv_rows_fwd(*p, s);
     if (!conv_tc_fwd_supported(*p)) return NERVECL_EUNSUPPORTED;
     return conv_tc_fwd(*p, s);

@@ -9,7 +9,7 @@ namespace nv {
 static inline int epi_v256(const nervecl_conv_params& a) {
   auto ok = [](const void* p, int64_t ld) { return !p || (ld % 16 == 0 && nv::aligned(p, 32)); };
   return a.out_dtype == NERVECL_BF16 && ok(a.out, a.ldo) && ok(a.res, a.ldres) && ok(a.mask, a.ldmask) &&
-         ok(a.mask_sub, a.ldmask_sub) && !getenv("NERVECL_NO_V256");
+         ok(a.mask_sub, a.ldmask_sub) && !nv::tune_env("NERVECL_NO_V256");
 }
 
 int conv_simt_fwd(const nervecl_conv_params& a, cudaStream_t s);

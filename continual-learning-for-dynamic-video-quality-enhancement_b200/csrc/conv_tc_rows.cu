@@ -35,6 +35,14 @@ using namespace nv::tc;
 
 namespace {
 
+// profiling-only work-skipping switches exist only in -DNERVECL_TUNING builds: the shipped library cannot time a
+// kernel that does no work
+#ifdef NERVECL_TUNING
+#define ROWS_DBG(a, bit) (((a).dbg & (bit)) != 0)
+#else
+#define ROWS_DBG(a, bit) false
+#endif
+
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);     // warp 0 = TMA, warp 1 = MMA issuer, warps 2..9 = epilogue
 constexpr int KC = 64;                             // channels per chunk = one 128-byte swizzle span
@@ -205,7 +213,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int ri = 0; ri < rows + 2; ++ri) {
           for (int gi = 0; gi < ngrp; ++gi) {
             mbar_wait(&ch_empty[stage], phase ^ 1);
-            if (a.dbg & 2) {
+            if (ROWS_DBG(a, 2)) {
               mbar_arrive(&ch_full[stage]);
             } else {
               mbar_expect_tx(&ch_full[stage], (uint32_t)a.cps * (PXB * ROWB));
@@ -293,8 +301,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (elect_one()) {
               bool first = commit_pend >= 0;
               int second_left = pend_stage >= 0 ? 2 : 0;          // k-loops until the deferred stage commit goes out
-              if ((a.dbg & 1) && first) { umma_commit(&acc_full[commit_pend]); first = false; }
-              if (!(a.dbg & 1)) {
+              if (ROWS_DBG(a, 1) && first) { umma_commit(&acc_full[commit_pend]); first = false; }
+              if (!ROWS_DBG(a, 1)) {
                 for (int cc = 0; cc < a.cps; ++cc) {
                   const int c = gi * a.cps + cc;
                   const uint32_t a_lo = ring_lo + (uint32_t)stage * (stage_bytes >> 4) + (uint32_t)cc * (CHUNK_BYTES >> 4);
@@ -376,7 +384,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // next 4 rows of the item are kept in flight so the epilogue is not a chain of exposed HBM latencies.
     const int cm = c_lo + part * 16;                       // absolute first channel of that chunk
     // (PF kernels are only launched with a mask, no mask_sub and NOUT <= 32)
-    const bool pf = PF && part < nch && cm >= a.mask_c0 && cm + 16 <= a.Cout && !(a.dbg & 4);
+    const bool pf = PF && part < nch && cm >= a.mask_c0 && cm + 16 <= a.Cout && !ROWS_DBG(a, 4);
     uint4 mqa[4], mqb[4];            // [row slot]: channels cm..cm+7 and cm+8..cm+15
 #pragma unroll
     for (int d = 0; d < 4; ++d) mqa[d] = mqb[d] = make_uint4(0, 0, 0, 0);
@@ -394,7 +402,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       int n, strip, y0, rows;
       while (it.next(a, n, strip, y0, rows)) {
         const int x = strip * BM + row;
-        const bool valid = x < a.W && !(a.dbg & 4);
+        const bool valid = x < a.W && !ROWS_DBG(a, 4);
         const int64_t p0 = ((int64_t)n * a.H + y0) * a.W + x;
         const int cf = c_lo + part * 16;                         // first channel of this thread's first chunk
         bf16* op = reinterpret_cast<bf16*>(a.out) + p0 * a.ldo + cf;
@@ -503,7 +511,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tmem_ld_wait();
             if (has0) tmem_st16_zero(tcol);                          // re-arm the slot for its next output row
             if (two) tmem_st16_zero(tcol + 32u);
-            if (valid && has0 && !(a.dbg & 4)) {
+            if (valid && has0 && !ROWS_DBG(a, 4)) {
               float f[16];
               if (!PF && a.fast == 1) {
 #pragma unroll
@@ -633,7 +641,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (PF) {                                                  // one chunk per thread (c = part), mask prefetched
           if (part < nch_all) {
             EpiChunk<OutT> e0;
-            const bool live0 = part < nch && !(a.dbg & 4);
+            const bool live0 = part < nch && !ROWS_DBG(a, 4);
             if (live0) e0.issue(a, taddr, c_lo + part * 16, valid, p, pfv, cur0, cur1);
             tmem_ld_wait();
             tmem_st16_zero(tcol + (uint32_t)(part * 16));          // re-arm the slot for its next output row
@@ -643,7 +651,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int c = part; c < nch_all; c += 4) {
             EpiChunk<OutT> e0, e1;
             const bool two = c + 2 < nch_all;
-            const bool live0 = c < nch && !(a.dbg & 4), live1 = two && c + 2 < nch && !(a.dbg & 4);
+            const bool live0 = c < nch && !ROWS_DBG(a, 4), live1 = two && c + 2 < nch && !ROWS_DBG(a, 4);
             if (live0) e0.issue(a, taddr, c_lo + c * 16, valid, p);
             if (live1) e1.issue(a, taddr, c_lo + (c + 2) * 16, valid, p);
             tmem_ld_wait();
@@ -695,7 +703,7 @@ bool plan_rows(const nervecl_conv_params& a, int sms, RowPlan& p) {
     const int chunks_fit = (int)((kSmemBudget - fixed) / CHUNK_BYTES);
     // a ring stage holds `cps` chunks (a divisor of the chunks per row): whole rows when two of them fit
     // (one barrier round trip and one commit per row), else the largest group that still leaves >= 3 stages
-    static const int cps_cap = getenv("NERVECL_ROWS_CPS") ? atoi(getenv("NERVECL_ROWS_CPS")) : 1 << 20;   // (tuning knob)
+    static const int cps_cap = nv::tune_env("NERVECL_ROWS_CPS") ? atoi(nv::tune_env("NERVECL_ROWS_CPS")) : 1 << 20;   // (tuning knob)
     for (int cps = nct; cps >= 1; --cps) {
       if (nct % cps || cps > cps_cap) continue;
       const int st = chunks_fit / cps;
@@ -764,7 +772,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
     // a channel count that is not a multiple of 64 ends inside a 128-byte line whose other half belongs to a
     // neighbouring slice of the same buffer: 128-byte L2 promotion would fetch it from DRAM (ncu: 96 -> 32 read
     // 128 channels' worth), 64-byte promotion does not
-    static const bool promo64 = !getenv("NERVECL_ROWS_PROMO128");
+    static const bool promo64 = !nv::tune_env("NERVECL_ROWS_PROMO128");
     const CUtensorMapL2promotion promo = (C % KC && promo64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
@@ -806,9 +814,9 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.nchunks2 = p.nchunks2; t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
   t.x_center = a.K == 1;
   t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
-  { const char* d = getenv("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
+  { const char* d = nv::tune_env("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
   const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.mask_sub &&
-                     p.NOUT <= 128 && !(t.dbg & 64);
+                     p.NOUT <= 128 && !ROWS_DBG(t, 64);
   t.fast = 0;
   if (whole && !a.accumulate) {
     if ((!a.res || a.res_channels >= a.Cout) && !a.mask && a.alpha == 1.0f && (a.bias || a.relu || !a.res)) t.fast = 1;
@@ -824,7 +832,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   // one CTA per SM (per channel group); each takes an equal share of the N * strips * H output rows
   if (t.fast == 2) t.v256_in = a.ldmask % 16 == 0 && aligned(a.mask, 32);
   if (t.fast == 3 || (t.fast == 1 && t.res)) t.v256_in = t.ldres % 16 == 0 && aligned(t.res, 32);
-  if (getenv("NERVECL_NO_V256")) t.v256_out = t.v256_in = 0;
+  if (nv::tune_env("NERVECL_NO_V256")) t.v256_out = t.v256_in = 0;
   if (a.colsum && !(t.fast == 2 && p.NOUT <= 32)) return NERVECL_EUNSUPPORTED;
   const int64_t total_rows = (int64_t)a.N * p.strips * a.H;
   dim3 grid((unsigned)imin(cdiv(total_rows, 4), imax(1, sms / p.nsplit)), (unsigned)p.nsplit);

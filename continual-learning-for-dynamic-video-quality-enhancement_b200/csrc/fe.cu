@@ -377,7 +377,7 @@ NV_API int nervecl_bn_stats(const void* x, int64_t ldx, int dtype, int C, int64_
   if (!x || !sums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || C > 1024) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  if (!getenv("NERVECL_BN_SUMS_PLAIN") && bn_sums_fast_supported(C, ldx, ldx))
+  if (!nv::tune_env("NERVECL_BN_SUMS_PLAIN") && bn_sums_fast_supported(C, ldx, ldx))
     return bn_sums_fast(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, dtype, C, npix, groups, sums, as_stream(stream));
   int lanes = 256 / (C >> 2);
   int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups));
@@ -418,7 +418,7 @@ NV_API int nervecl_bn_relu_bwd_reduce(const void* x, int64_t ldx, const void* dy
   if (!x || !dy || !stat || !gamma || !beta || !bsums || C <= 0 || npix <= 0 || groups <= 0) return NERVECL_EINVAL;
   if ((C & 3) || (ldx & 3) || (lddy & 3) || C > 1024) return NERVECL_EALIGN;
   if (dtype != NERVECL_F32 && dtype != NERVECL_BF16) return NERVECL_EDTYPE;
-  if (!getenv("NERVECL_BN_SUMS_PLAIN") && bn_sums_fast_supported(C, ldx, lddy))
+  if (!nv::tune_env("NERVECL_BN_SUMS_PLAIN") && bn_sums_fast_supported(C, ldx, lddy))
     return bn_sums_fast(x, ldx, dy, lddy, stat, gamma, beta, dtype, C, npix, groups, bsums, as_stream(stream));
   int lanes = 256 / (C >> 2);
   int chunks = (int)imax(1, imin(cdiv(npix, lanes * 16), (kSMs * 8) / groups));

@@ -342,7 +342,7 @@ NV_API int nervecl_corr_fwd(const void* x1, int64_t ld1, const void* x2, int64_t
   if (cout_pad < NDISP || ldo < cout_pad) return NERVECL_EINVAL;
   if ((C & 7) || (ld1 & 7) || (ld2 & 7) || !aligned(x1, 16) || !aligned(x2, 16)) return NERVECL_EALIGN;
   if (corr_tiled_supported(dtype, C, ld1, ld2, x1, x2) && !(cout_pad & 7) && !(ldo & 7) && aligned(out, 16) && cout_pad <= 128)
-    return (getenv("NERVECL_CORR_SIMT") ? corr_fwd_tiled : corr_fwd_mma)(x1, ld1, x2, ld2, out, ldo, N, H, W, cout_pad,
+    return (nv::tune_env("NERVECL_CORR_SIMT") ? corr_fwd_tiled : corr_fwd_mma)(x1, ld1, x2, ld2, out, ldo, N, H, W, cout_pad,
                                                                             as_stream(stream));
   int64_t blocks = (int64_t)N * H * cdiv(W, 32);
   size_t smem = (size_t)32 * cout_pad * sizeof(float);
@@ -357,7 +357,7 @@ NV_API int nervecl_corr_bwd(const void* x1, int64_t ld1, const void* x2, int64_t
   if (!x1 || !x2 || !dout || !dx1 || !dx2 || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if ((C & 7) || (ld1 & 7) || (ld2 & 7) || (lddx1 & 7) || (lddx2 & 7)) return NERVECL_EALIGN;
   if (corr_tiled_supported(dtype, C, ld1, ld2, x1, x2) && aligned(dx1, 16) && aligned(dx2, 16))
-    return (getenv("NERVECL_CORR_SIMT") ? corr_bwd_tiled : corr_bwd_mma)(x1, ld1, x2, ld2, dout, lddo, dx1, lddx1, acc1, dx2,
+    return (nv::tune_env("NERVECL_CORR_SIMT") ? corr_bwd_tiled : corr_bwd_mma)(x1, ld1, x2, ld2, dout, lddo, dx1, lddx1, acc1, dx2,
                                                                             lddx2, acc2, N, H, W, as_stream(stream));
   int64_t total = (int64_t)N * H * W * (C >> 3);
   int blocks = (int)imax(1, imin(cdiv(total, 256), kSMs * 16));

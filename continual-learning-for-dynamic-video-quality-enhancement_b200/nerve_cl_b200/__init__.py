@@ -14,6 +14,6 @@ _lib.load()          # no library => RuntimeError here, never a silent fallback
 
 from . import ops  # noqa: E402,F401
 from .models import SuperResolutionNet, LightweightSuperResolution  # noqa: E402,F401
-from .continual import EWC, OnlineEWC  # noqa: E402,F401
+from .continual import EWC, OnlineEWC, SynapticIntelligence  # noqa: E402,F401
 
 __version__ = "0.1.0"

@@ -49,28 +49,43 @@ class _FlatState:
         return st
 
 
+def _flat_grad_for(model, layout, device):
+    """A zeroed flat fp32 gradient buffer + per-parameter views for ``layout``.  When ``model`` owns a padded
+    flat layout (``SuperResolutionNet._flat_layout``: the layout of the fused optimiser / DDP buckets) and ``layout``
+    covers exactly its parameters, the buffer uses THAT layout and is announced to the module, so that if autograd
+    adopts these views as ``param.grad`` (the penalty node usually runs before the network's own backward node) the
+    fused single-launch optimiser step still finds one flat gradient buffer."""
+    fl = getattr(model, "_flat_layout", None)
+    if fl is not None and [n for n, _, _ in layout] == list(fl):
+        flat = torch.zeros(model._flat_numel, device=device, dtype=torch.float32)
+        views = [flat[o:o + k].view(shape) for o, k, shape in (fl[n] for n, _, _ in layout)]
+        model._note_flat_grad(flat)
+        return flat, views
+    g = _FlatState(layout, device)
+    return g.flat, [g.views[name] for name, _, _ in layout]
+
+
 class _PenaltyFn(torch.autograd.Function):
-    """penalty = coef * sum F (theta - star)^2 as one autograd node over all parameters."""
+    """penalty = coef * sum_states sum F (theta - star)^2 as one autograd node over all parameters."""
 
     @staticmethod
-    def forward(ctx, ewc: "EWC", states: List[Tuple[_FlatState, _FlatState]], *params: Tensor):
+    def forward(ctx, model, coef: float, states: List[Tuple[_FlatState, _FlatState]], *params: Tensor):
         theta = [p.detach() for p in params]
         out = torch.zeros((), device=theta[0].device, dtype=torch.float32)
         for fisher, star in states:
-            nv.ewc_penalty_fwd(theta, fisher.flat, star.flat, ewc.ewc_lambda / 2.0, out)
-        ctx.ewc, ctx.states, ctx.theta = ewc, states, theta
+            nv.ewc_penalty_fwd(theta, fisher.flat, star.flat, coef, out)
+        ctx.model, ctx.coef, ctx.states, ctx.theta = model, coef, states, theta
         return out
 
     @staticmethod
     def backward(ctx, gout: Tensor):
         theta = ctx.theta
         layout = ctx.states[0][0].layout
-        g = _FlatState(layout, theta[0].device)             # fresh zeroed flat gradient
-        grads = [g.views[name] for name, _, _ in layout]
+        _, grads = _flat_grad_for(ctx.model, layout, theta[0].device)      # fresh zeroed flat gradient
         gs = gout.detach().reshape(1).float().contiguous()
         for fisher, star in ctx.states:
-            nv.ewc_penalty_bwd(theta, grads, fisher.flat, star.flat, float(ctx.ewc.ewc_lambda), gs)
-        return (None, None) + tuple(grads)
+            nv.ewc_penalty_bwd(theta, grads, fisher.flat, star.flat, 2.0 * ctx.coef, gs)
+        return (None, None, None) + tuple(grads)
 
 
 class EWC:
@@ -120,27 +135,37 @@ class EWC:
         numels = [p.numel() for p in params]
         self.model.eval()
         used = 0
-        for batch in dataloader:
-            if num_samples is not None and used >= num_samples:
-                break
-            if isinstance(batch, (tuple, list)):
-                inputs = batch[0]
-                targets = batch[1] if len(batch) > 1 else None
-            else:
-                inputs, targets = batch, None
-            inputs = inputs.to(dev)
-            self.model.zero_grad()
-            if empirical and targets is not None:
-                targets = targets.to(inputs.device)
-                loss = nn.functional.mse_loss(self.model(inputs), targets)
-                loss.backward()
-            else:
-                outputs = self.model(inputs)
-                log_prob = -0.5 * (outputs ** 2).sum() if outputs.dim() > 1 else outputs.sum()
-                log_prob.backward()
-            grads = [None if p.grad is None else p.grad.detach().contiguous() for p in params]
-            nv.ewc_fisher_accum(fisher.flat, grads, numels, 1.0)
-            used += inputs.size(0)
+        # Data-parallel runs: the Fisher is sum over LOCAL batches of (local batch-mean gradient)^2, summed over ranks
+        # below.  A gradient all-reduce inside backward would square the rank-AVERAGED
+        # gradient instead (and hang when ranks see different batch counts), so it is switched off for this pass.
+        saved_sync = getattr(self.model, "_grad_sync", None)
+        if saved_sync is not None:
+            self.model._grad_sync = None
+        try:
+            for batch in dataloader:
+                if num_samples is not None and used >= num_samples:
+                    break
+                if isinstance(batch, (tuple, list)):
+                    inputs = batch[0]
+                    targets = batch[1] if len(batch) > 1 else None
+                else:
+                    inputs, targets = batch, None
+                inputs = inputs.to(dev)
+                self.model.zero_grad()
+                if empirical and targets is not None:
+                    targets = targets.to(inputs.device)
+                    loss = nn.functional.mse_loss(self.model(inputs), targets)
+                    loss.backward()
+                else:
+                    outputs = self.model(inputs)
+                    log_prob = -0.5 * (outputs ** 2).sum() if outputs.dim() > 1 else outputs.sum()
+                    log_prob.backward()
+                grads = [None if p.grad is None else p.grad.detach().contiguous() for p in params]
+                nv.ewc_fisher_accum(fisher.flat, grads, numels, 1.0)
+                used += inputs.size(0)
+        finally:
+            if saved_sync is not None:
+                self.model._grad_sync = saved_sync
         if self.process_group is not None:
             import torch.distributed as dist
             cnt = torch.tensor([float(used)], device=dev)
@@ -207,7 +232,7 @@ class EWC:
         params = [by_name[n] for n in names]
         if not params[0].is_cuda:
             raise RuntimeError("nerve_cl_b200.EWC.penalty: model parameters must be on CUDA")
-        return _PenaltyFn.apply(self, states, *params)
+        return _PenaltyFn.apply(model, self.ewc_lambda / 2.0, states, *params)
 
     def get_importance_stats(self) -> Dict[str, Dict[str, float]]:
         """Reference ewc.py:234-257."""

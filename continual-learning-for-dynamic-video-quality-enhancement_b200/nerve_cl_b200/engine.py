@@ -24,8 +24,6 @@ from __future__ import annotations
 import weakref
 from typing import Dict, List, Optional, Tuple
 
-import os
-
 import torch
 
 from . import ops
@@ -183,6 +181,7 @@ class Plan:
         self.others = [t for t in range(T) if t != self.mid]
         self.engine = CONV_AUTO
         self.div_mode = 0
+        self.fold_bn = True               # fold running BatchNorm into the pointwise convs on the pure-inference path
         self.timer: Optional[KernelTimer] = None
         self._free: List[Activations] = []
         self._bwd_ws = None
@@ -356,7 +355,7 @@ class Plan:
         # conv + BN + ReLU (+ the extractor skip) is ONE conv launch with a bias / ReLU / residual epilogue and the
         # pre-BN tensor is never written (three full passes over the 64-channel extractor maps less per layer).
         fold = ((not training) and (not need_bwd) and self.adt == torch.bfloat16 and self.engine != CONV_SIMT
-                and not os.environ.get("NERVECL_NO_BN_FOLD"))
+                and self.fold_bn)
         fold_scale, fold_bias = {}, {}
         if fold:
             for j in range(3):

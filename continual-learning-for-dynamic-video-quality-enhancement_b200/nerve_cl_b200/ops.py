@@ -633,6 +633,26 @@ def _ewc_penalty_bwd(theta, grads, fisher, star, coef2, gscale) -> None:
                                                   _stream()), "ewc_penalty_bwd")
 
 
+@_op("si_update(Tensor[] theta, Tensor?[] grads, Tensor(a!) W, Tensor(b!) p_old) -> ()")
+def _si_update(theta, grads, W, p_old) -> None:
+    """Synaptic Intelligence running importance (``nervecl_si_update``, reference ewc.py:342-352)."""
+    _check_flat_list(theta, "theta")
+    _check_flat_list(grads, "grads")
+    tp, n = _table(theta)
+    gp, _ = _table(grads)
+    _lib.check(_lib.load().nervecl_si_update(tp, gp, _numels(theta), n, _flat(W, "W"), _flat(p_old, "p_old"), _stream()),
+               "si_update")
+
+
+@_op("si_register(Tensor[] theta, Tensor(a!) W, Tensor(b!) p_old, Tensor(c!) omega, float damping) -> ()")
+def _si_register(theta, W, p_old, omega, damping) -> None:
+    """Synaptic Intelligence consolidation (``nervecl_si_register``, reference ewc.py:354-366)."""
+    _check_flat_list(theta, "theta")
+    tp, n = _table(theta)
+    _lib.check(_lib.load().nervecl_si_register(tp, _numels(theta), n, _flat(W, "W"), _flat(p_old, "p_old"),
+                                              _flat(omega, "omega"), damping, _stream()), "si_register")
+
+
 @_op("adamw_step(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, "
      "float beta2, float eps, float weight_decay, int step, float grad_scale) -> ()")
 def _adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale) -> None:

@@ -359,6 +359,21 @@ int nervecl_ewc_penalty_bwd(const float* const* theta_host, float* const* grad_h
                             const float* star, float coef2, const float* gscale,
                             nervecl_stream_t stream);
 
+/* Synaptic Intelligence (nerve_cl/continual/ewc.py:306-379) on flat fp32 state laid out like the EWC
+ * buffers (tensor i at offset sum of the numels before it).
+ * update (ewc.py:342-352, after every optimiser step): for every tensor whose grad pointer is non-NULL
+ *   W[off_i+k] += -g_i[k] * (theta_i[k] - p_old[off_i+k]);  p_old[off_i+k] = theta_i[k]
+ * (a NULL grad -- param.grad is None -- leaves both untouched, like the reference). */
+int nervecl_si_update(const float* const* theta_host, const float* const* grad_host,
+                      const int64_t* numel_host, int ntensors, float* W, float* p_old,
+                      nervecl_stream_t stream);
+/* register_task (ewc.py:354-366): omega += W / ((theta - p_old)^2 + damping); W = 0; p_old = theta.
+ * The SI penalty  si_lambda * sum omega (theta - p_old)^2  (ewc.py:368-379) is
+ * nervecl_ewc_penalty_fwd/bwd with fisher = omega, star = p_old, coef = si_lambda, coef2 = 2 si_lambda. */
+int nervecl_si_register(const float* const* theta_host, const int64_t* numel_host, int ntensors,
+                        float* W, float* p_old, float* omega, float damping,
+                        nervecl_stream_t stream);
+
 /* Fused AdamW over a flat fp32 parameter buffer (torch.optim.AdamW semantics,
  * experiments/train_baseline.py:62).  step is 1-based. */
 int nervecl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,

@@ -45,3 +45,44 @@ def penalty_grad(theta: np.ndarray, fisher: np.ndarray, star: np.ndarray, ewc_la
     """d penalty / d theta = lambda * F * (theta - theta*)."""
     return (np.float32(ewc_lambda) * fisher.astype(np.float32)
             * (theta.astype(np.float32) - star.astype(np.float32))).astype(np.float32)
+
+
+def penalty_separate(theta: np.ndarray, fishers: Sequence[np.ndarray], stars: Sequence[np.ndarray],
+                     ewc_lambda: float) -> float:
+    """ewc.py:213-223 ('separate' mode): lambda/2 * sum over tasks of sum F_t (theta - theta*_t)^2."""
+    return sum(penalty(theta, f, s, ewc_lambda) for f, s in zip(fishers, stars))
+
+
+def penalty_separate_grad(theta: np.ndarray, fishers: Sequence[np.ndarray], stars: Sequence[np.ndarray],
+                          ewc_lambda: float) -> np.ndarray:
+    out = np.zeros_like(theta, dtype=np.float32)
+    for f, s in zip(fishers, stars):
+        out = (out + penalty_grad(theta, f, s, ewc_lambda)).astype(np.float32)
+    return out
+
+
+# ---- Synaptic Intelligence (ewc.py:306-379) over flat fp32 vectors ----
+def si_update(W: np.ndarray, p_old: np.ndarray, theta: np.ndarray, grad: np.ndarray):
+    """ewc.py:342-352: W += -grad * (theta - p_old); p_old = theta.  Returns (W, p_old)."""
+    delta = theta.astype(np.float32) - p_old.astype(np.float32)
+    W = (W.astype(np.float32) + (-grad.astype(np.float32)) * delta).astype(np.float32)
+    return W, theta.astype(np.float32).copy()
+
+
+def si_register(W: np.ndarray, p_old: np.ndarray, omega: np.ndarray, theta: np.ndarray, damping: float):
+    """ewc.py:354-366: omega += W / ((theta - p_old)^2 + damping); W = 0; p_old = theta.  Returns (W, p_old, omega)."""
+    delta = theta.astype(np.float32) - p_old.astype(np.float32)
+    denom = (delta * delta + np.float32(damping)).astype(np.float32)
+    omega = (omega.astype(np.float32) + W.astype(np.float32) / denom).astype(np.float32)
+    return np.zeros_like(W, dtype=np.float32), theta.astype(np.float32).copy(), omega
+
+
+def si_penalty(theta: np.ndarray, omega: np.ndarray, p_old: np.ndarray, si_lambda: float) -> float:
+    """ewc.py:368-379: si_lambda * sum omega (theta - p_old)^2 (float64 accumulation)."""
+    d = theta.astype(np.float64) - p_old.astype(np.float64)
+    return float(si_lambda) * float(np.sum(omega.astype(np.float64) * d * d))
+
+
+def si_penalty_grad(theta: np.ndarray, omega: np.ndarray, p_old: np.ndarray, si_lambda: float) -> np.ndarray:
+    return (np.float32(2.0 * si_lambda) * omega.astype(np.float32)
+            * (theta.astype(np.float32) - p_old.astype(np.float32))).astype(np.float32)

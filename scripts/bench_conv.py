@@ -78,7 +78,7 @@ if __name__ == "__main__":
             fwd_case(cin, 32, 3, 256, 32, [ops.CONV_TC])
             fwd_case(cin, 32, 3, 256, 256, [ops.CONV_TC])
     if which == "rows":
-        # (component timing with NERVECL_ROWS_DBG: scripts/bench_rows_dbg.sh)
+        # (component timing: build with -DNERVECL_TUNING and set NERVECL_ROWS_DBG)
         fwd_case(64, 32, 3, 256, 256, [ops.CONV_TC])
         fwd_case(192, 32, 3, 256, 256, [ops.CONV_TC])
         fwd_case(64, 64, 1, 64, 64, [ops.CONV_TC])

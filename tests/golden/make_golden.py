@@ -22,6 +22,7 @@ from nerve_cl.models import SuperResolutionNet  # noqa: E402  (the reference)
 from nerve_cl.models.super_resolution import warp_features  # noqa: E402
 from nerve_cl.models.layers import LiteFlowNetCorrelation  # noqa: E402
 from nerve_cl.continual import EWC  # noqa: E402
+from nerve_cl.continual.ewc import SynapticIntelligence  # noqa: E402
 
 from oracle import sr_oracle, ewc_oracle  # noqa: E402
 
@@ -215,7 +216,122 @@ def ewc_case():
          penalty1=pen1.detach(), penalty_grad1=gpen)
 
 
+def _flat_params(model):
+    return torch.cat([p.detach().flatten() for p in model.parameters()]).clone()
+
+
+def _flat_dict(d, model):
+    return torch.cat([d[n].flatten() for n, _ in model.named_parameters()]).clone()
+
+
+def ewc_separate_case():
+    """'separate' mode (ewc.py:172-178, 213-223): two tasks on different data, then the summed penalty and its
+    gradient at a third parameter point -- from the live reference."""
+    torch.manual_seed(12)
+    model = torch.nn.Linear(10, 10)
+    xa, ya = torch.randn(40, 10), torch.randn(40, 10)
+    xb, yb = torch.randn(24, 10) * 2.0, torch.randn(24, 10)
+    la = [(xa[i:i + 8], ya[i:i + 8]) for i in range(0, 40, 8)]
+    lb = [(xb[i:i + 8], yb[i:i + 8]) for i in range(0, 24, 8)]
+    ewc = EWC(model, ewc_lambda=300.0, mode="separate")
+    w0 = _flat_params(model)
+    ewc.register_task(0, la)
+    f0 = _flat_dict(ewc.task_fisher[0], model)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    w1 = _flat_params(model)
+    ewc.register_task(1, lb)
+    f1 = _flat_dict(ewc.task_fisher[1], model)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    w2 = _flat_params(model)
+    model.zero_grad()
+    pen = ewc.penalty()
+    pen.backward()
+    gpen = torch.cat([p.grad.flatten() for p in model.parameters()]).clone()
+    op = ewc_oracle.penalty_separate(w2.numpy(), [f0.numpy(), f1.numpy()], [w0.numpy(), w1.numpy()], 300.0)
+    assert abs(op - float(pen.detach())) <= 1e-5 * abs(float(pen.detach()))
+    og = ewc_oracle.penalty_separate_grad(w2.numpy(), [f0.numpy(), f1.numpy()], [w0.numpy(), w1.numpy()], 300.0)
+    assert np.allclose(og, gpen.numpy(), rtol=1e-5, atol=1e-7)
+    save("ewc_separate.npz", xa=xa, ya=ya, xb=xb, yb=yb, w0=w0, w1=w1, w2=w2, fisher0=f0, fisher1=f1,
+         penalty2=pen.detach(), penalty_grad2=gpen)
+
+
+def si_case():
+    """SynapticIntelligence (ewc.py:306-379) driven like a training loop: 6 SGD steps with update_importance after
+    each, register_task, 3 more steps (the last one WITHOUT update_importance, so register_task sees a non-zero
+    delta), register_task, then penalty + gradient after a final parameter move.  One parameter (the bias) has
+    grad=None during step 2 to pin the 'skipped tensor keeps W and p_old' behaviour."""
+    torch.manual_seed(13)
+    model = torch.nn.Linear(10, 10)
+    xs, ys = torch.randn(72, 10), torch.randn(72, 10)
+    si = SynapticIntelligence(model, si_lambda=0.7, damping=0.1)
+    w_init = _flat_params(model)
+    lr = 0.05
+    W = np.zeros(110, np.float32); po = w_init.numpy().copy(); om = np.zeros(110, np.float32)
+    grads, skip_bias = [], []
+
+    def sgd_step(i, update=True, drop_bias=False):
+        nonlocal W, po
+        model.zero_grad()
+        torch.nn.functional.mse_loss(model(xs[8 * i:8 * i + 8]), ys[8 * i:8 * i + 8]).backward()
+        g = torch.cat([p.grad.flatten() for p in model.parameters()]).clone()
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(-lr * p.grad)
+        if drop_bias:
+            model.bias.grad = None
+        if update:
+            si.update_importance()
+            th = _flat_params(model).numpy()
+            if drop_bias:
+                Wn, pn = ewc_oracle.si_update(W[:100], po[:100], th[:100], g.numpy()[:100])
+                W = np.concatenate([Wn, W[100:]]); po = np.concatenate([pn, po[100:]])
+            else:
+                W, po = ewc_oracle.si_update(W, po, th, g.numpy())
+        grads.append(g); skip_bias.append(drop_bias)
+
+    for i in range(6):
+        sgd_step(i, drop_bias=(i == 2))
+    si.register_task()
+    W, po, om = ewc_oracle.si_register(W, po, om, _flat_params(model).numpy(), 0.1)
+    omega_a = _flat_dict(si.omega, model)
+    assert np.allclose(om, omega_a.numpy(), rtol=1e-5, atol=1e-9)
+    for i in range(6, 9):
+        sgd_step(i, update=(i != 8))
+    si.register_task()
+    W, po, om = ewc_oracle.si_register(W, po, om, _flat_params(model).numpy(), 0.1)
+    omega_b = _flat_dict(si.omega, model)
+    pold_b = _flat_dict(si.p_old, model)
+    assert np.allclose(om, omega_b.numpy(), rtol=1e-5, atol=1e-9) and np.array_equal(po, pold_b.numpy())
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    w_final = _flat_params(model)
+    model.zero_grad()
+    pen = si.penalty()
+    pen.backward()
+    gpen = torch.cat([p.grad.flatten() for p in model.parameters()]).clone()
+    op = ewc_oracle.si_penalty(w_final.numpy(), om, po, 0.7)
+    assert abs(op - float(pen.detach())) <= 1e-5 * abs(float(pen.detach()))
+    assert np.allclose(ewc_oracle.si_penalty_grad(w_final.numpy(), om, po, 0.7), gpen.numpy(), rtol=1e-5, atol=1e-8)
+    save("si_linear.npz", xs=xs, ys=ys, w_init=w_init, lr=np.float32(lr), omega_a=omega_a, omega_b=omega_b,
+         p_old_b=pold_b, w_final=w_final, penalty=pen.detach(), penalty_grad=gpen)
+
+
 if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    only = ap.parse_args().only
+    if only:
+        for nm in only.split(","):
+            globals()[nm]()
+        sys.exit(0)
+    ewc_separate_case()
+    si_case()
     warp_case()
     corr_case()
     ewc_case()

@@ -92,3 +92,76 @@ def test_ewc_oracle_golden():
                                rtol=1e-5, atol=1e-7)
     f1 = ewc_oracle.consolidate(f0, ewc_oracle.fisher_from_batches(batch_grads(g["w1"]), [8] * 5), 0.9)
     np.testing.assert_allclose(f1, g["fisher1"], rtol=1e-5, atol=1e-9)
+
+
+def _linear_batch_grads(wflat, xs, ys, bs=8):
+    m = torch.nn.Linear(10, 10)
+    with torch.no_grad():
+        m.weight.copy_(torch.from_numpy(wflat[:100]).view(10, 10))
+        m.bias.copy_(torch.from_numpy(wflat[100:]))
+    out = []
+    for i in range(0, xs.shape[0], bs):
+        m.zero_grad()
+        torch.nn.functional.mse_loss(m(xs[i:i + bs]), ys[i:i + bs]).backward()
+        out.append(torch.cat([p.grad.flatten() for p in m.parameters()]).numpy().copy())
+    return out
+
+
+def test_ewc_separate_oracle_golden():
+    """'separate'-mode penalty (reference ewc.py:213-223) from the live reference: two tasks, summed penalty."""
+    g = load_golden("ewc_separate.npz")
+    f0 = ewc_oracle.fisher_from_batches(_linear_batch_grads(g["w0"], torch.from_numpy(g["xa"]), torch.from_numpy(g["ya"])), [8] * 5)
+    f1 = ewc_oracle.fisher_from_batches(_linear_batch_grads(g["w1"], torch.from_numpy(g["xb"]), torch.from_numpy(g["yb"])), [8] * 3)
+    np.testing.assert_allclose(f0, g["fisher0"], rtol=1e-6)
+    np.testing.assert_allclose(f1, g["fisher1"], rtol=1e-6)
+    pen = ewc_oracle.penalty_separate(g["w2"], [f0, f1], [g["w0"], g["w1"]], 300.0)
+    assert abs(pen - float(g["penalty2"])) <= 1e-5 * abs(float(g["penalty2"]))
+    np.testing.assert_allclose(ewc_oracle.penalty_separate_grad(g["w2"], [f0, f1], [g["w0"], g["w1"]], 300.0),
+                               g["penalty_grad2"], rtol=1e-5, atol=1e-7)
+
+
+def si_replay(g, update, register, params, step_grad, apply_step):
+    """The SI golden's training loop (tests/golden/make_golden.py::si_case) over abstract callbacks."""
+    for i in range(6):
+        gr = step_grad(i)
+        apply_step(gr)
+        update(gr, drop_bias=(i == 2))
+    register()
+    yield "a"
+    for i in range(6, 9):
+        gr = step_grad(i)
+        apply_step(gr)
+        if i != 8:
+            update(gr, drop_bias=False)
+    register()
+    yield "b"
+
+
+def test_si_oracle_golden():
+    """SynapticIntelligence (reference ewc.py:306-379) restated in oracle/ewc_oracle.py vs the live-reference golden."""
+    g = load_golden("si_linear.npz")
+    xs, ys, lr = torch.from_numpy(g["xs"]), torch.from_numpy(g["ys"]), float(g["lr"])
+    st = {"th": g["w_init"].copy(), "W": np.zeros(110, np.float32), "po": g["w_init"].copy(), "om": np.zeros(110, np.float32)}
+
+    def step_grad(i):
+        return _linear_batch_grads(st["th"], xs[8 * i:8 * i + 8], ys[8 * i:8 * i + 8])[0]
+
+    def apply_step(gr):
+        st["th"] = (st["th"] + np.float32(-lr) * gr).astype(np.float32)
+
+    def update(gr, drop_bias):
+        n = 100 if drop_bias else 110
+        W, po = ewc_oracle.si_update(st["W"][:n], st["po"][:n], st["th"][:n], gr[:n])
+        st["W"] = np.concatenate([W, st["W"][n:]])
+        st["po"] = np.concatenate([po, st["po"][n:]])
+
+    def register():
+        st["W"], st["po"], st["om"] = ewc_oracle.si_register(st["W"], st["po"], st["om"], st["th"], 0.1)
+
+    for tag in si_replay(g, update, register, None, step_grad, apply_step):
+        np.testing.assert_allclose(st["om"], g["omega_" + tag], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(st["po"], g["p_old_b"], rtol=1e-5, atol=1e-7)
+    pen = ewc_oracle.si_penalty(g["w_final"], g["omega_b"], g["p_old_b"], 0.7)
+    assert abs(pen - float(g["penalty"])) <= 1e-5 * abs(float(g["penalty"]))
+    np.testing.assert_allclose(ewc_oracle.si_penalty_grad(g["w_final"], g["omega_b"], g["p_old_b"], 0.7),
+                               g["penalty_grad"], rtol=1e-5, atol=1e-8)
