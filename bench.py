@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--engine", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--value-only", action="store_true",
                     help="warm-up + the K device-resident steps only (what the ncu passes of scripts/gpu_round.sh run)")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for cpu_baseline")
@@ -135,30 +136,80 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm on the host cores (oracle port; /root/reference is not on the box)
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_seconds(H, W, features, blocks, B=1, T=3, scale=2, reps=1):
-    import torch
-    from oracle import sr_oracle
-    from nerve_cl_b200.models import SuperResolutionNet
-    torch.manual_seed(0)
-    sd = {k: v.clone() for k, v in SuperResolutionNet(scale_factor=scale, num_features=features,
-                                                       num_residual_blocks=blocks).state_dict().items()}
-    lr, hr = synth_batch(B, T, H, W, scale, 1234, "cpu")
-    best = float("inf")
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        sr_oracle.train_step_grads(sd, lr, hr, scale, True)
-        best = min(best, time.perf_counter() - t0)
-    return best
+def _reference_module():
+    """The UNMODIFIED reference package (oracle/_ref, installed by oracle/build_ref.py) or None."""
+    from oracle import build_ref
+    path = build_ref.ref_path()
+    if path is None:
+        return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import nerve_cl.models as ref_models
+    return ref_models
 
 
-def pick_cpu_sample(args, budget_s):
+class CpuArm:
+    """One fwd + MSE + bwd step of the reference's SuperResolutionNet on the host cores.  Runs the reference's own
+    nn.Module when oracle/_ref exists (kind "reference"), else the oracle port over a random state_dict of the
+    same shapes (kind "port").  Never touches the product package or the GPU."""
+
+    def __init__(self, features, blocks, scale=2, tw=1):
+        import torch
+        from oracle import sr_oracle
+        self.scale, self.T = scale, 2 * tw + 1
+        ref = _reference_module()
+        torch.manual_seed(0)
+        if ref is not None:
+            self.kind = "reference"
+            self.model = ref.SuperResolutionNet(scale_factor=scale, num_features=features, num_residual_blocks=blocks,
+                                                temporal_window=tw).train()
+        else:
+            self.kind = "port"
+            self.sd = sr_oracle.random_state_dict(scale, features, blocks, self.T)
+
+    def step_seconds(self, B, H, W, reps=1):
+        import torch
+        from oracle import sr_oracle
+        lr, hr = synth_batch(B, self.T, H, W, self.scale, 1234, "cpu")
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            if self.kind == "reference":
+                self.model.zero_grad()
+                torch.nn.functional.mse_loss(self.model(lr), hr).backward()
+            else:
+                sr_oracle.train_step_grads(self.sd, lr, hr, self.scale, True)
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+
+def pick_cpu_sample(arm, args, budget_s):
     """Choose how many rows of one 640-wide clip fit `budget_s` seconds of CPU work per step, from a probe."""
     probe_h = 32
-    t = cpu_train_step_seconds(probe_h, args.width, args.features, args.blocks)   # includes first-call warm-up
-    t = min(t, cpu_train_step_seconds(probe_h, args.width, args.features, args.blocks))
+    t = arm.step_seconds(1, probe_h, args.width)          # includes first-call warm-up
+    t = min(t, arm.step_seconds(1, probe_h, args.width))
     rows = int(budget_s / max(t, 1e-6) * probe_h)
     rows = max(16, min(args.height, rows // 8 * 8))
     return rows
+
+
+def lscpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_cfg1(arm, iters=5):
+    """BASELINE.json configs[0]: B=4, 3x64x64 windows, fwd+bwd on the CPU: median and min of `iters` timed steps."""
+    arm.step_seconds(4, 64, 64)
+    ts = sorted(arm.step_seconds(4, 64, 64) for _ in range(iters))
+    return {"shape": [4, 3, 3, 64, 64], "iters": iters, "median_s": ts[len(ts) // 2], "min_s": ts[0],
+            "frames_per_s_median": 4.0 / ts[len(ts) // 2]}
 
 
 def run_reference(args):
@@ -168,24 +219,30 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    arm = CpuArm(args.features, args.blocks)
     total = max(args.steps + args.warmup, 1)
-    rows = pick_cpu_sample(args, budget_s=max(150.0 / total, 2.0))
+    rows = pick_cpu_sample(arm, args, budget_s=max(120.0 / total, 2.0))
     frac = rows / args.height
     for _ in range(args.warmup):
-        cpu_train_step_seconds(rows, args.width, args.features, args.blocks)
+        arm.step_seconds(1, rows, args.width)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_train_step_seconds(rows, args.width, args.features, args.blocks)
+        arm.step_seconds(1, rows, args.width)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = frac / dt
-    sample = (f"1 clip x {rows}/{args.height} rows of the {args.width}x{args.height} LR window per step "
-              f"(T=3, fwd+MSE+bwd, fp32, torch CPU {torch.get_num_threads()} threads), scaled by pixel count")
+    what = "the reference's own SuperResolutionNet (oracle/_ref)" if arm.kind == "reference" else "oracle port"
+    sample = (f"{what}: 1 clip x {rows}/{args.height} rows of the {args.width}x{args.height} LR window per step "
+              f"(T=3, fwd+MSE+bwd, fp32, torch CPU {torch.get_num_threads()} threads), scaled by pixel count; the rate "
+              f"is per clip, so the arm's B=1 sample compares with the native arm's B={args.batch}")
+    cfg = workload_config(args, args.gpus)
+    cfg["reference_arm_batch"] = 1
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / frac, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": sample,
+                         "cpu": lscpu_model(), "cfg1": cpu_cfg1(arm)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -199,6 +256,59 @@ def workload_config(args, n):
         "l2": "working set (tens of GB of activations per step) >> 126 MB L2; no explicit flush needed",
         "optimizer": "AdamW (fused nervecl kernel over the flat parameter buffer)",
     }
+
+
+def gpu_eager(dev, args, batch=2, iters=5):
+    """Same-box GPU comparator: the UNMODIFIED reference module (oracle/_ref; the oracle port
+    when it is absent) through ATen/cuDNN eager on this B200 -- fp32 with TF32 off and bf16 autocast -- on `batch`
+    windows of the benchmark shape (eager autograd keeps ~6.4 GB of fp32 activations per 360p sample), one
+    fwd + MSE + bwd per step, rate per clip.  None of our kernels run here."""
+    import torch
+    from oracle import sr_oracle
+    ref = _reference_module()
+    torch.manual_seed(0)
+    if ref is not None:
+        model = ref.SuperResolutionNet(scale_factor=2, num_features=args.features, num_residual_blocks=args.blocks,
+                                       temporal_window=1).to(dev).train()
+        kind = "reference"
+    else:
+        sd = {k: v.to(dev) for k, v in sr_oracle.random_state_dict(2, args.features, args.blocks, 3).items()}
+        kind = "port"
+    lr, hr = synth_batch(batch, 3, args.height, args.width, 2, 77, dev)
+    out = {"impl": kind, "batch": batch, "iters": iters,
+           "note": "ATen/cuDNN eager fwd+MSE+bwd of the reference module on this GPU; frames/s = clips/s"}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for tag, ac in (("fp32_tf32_off", False), ("bf16_autocast", True)):
+            def one():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    if kind == "reference":
+                        model.zero_grad()
+                        torch.nn.functional.mse_loss(model(lr).float(), hr).backward()
+                    else:
+                        sr_oracle.train_step_grads(sd, lr, hr, 2, True)
+            try:
+                one(); one()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                out[tag] = {"ms_per_step": ms, "frames_per_s": batch / (ms / 1e3)}
+            except Exception as exc:       # (an eager OOM must not take the benchmark line down)
+                out[tag] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+                torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    if kind == "reference":
+        del model
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,8 +466,10 @@ def run_native(args):
         ms_x4 = timed(infer4_step, args.steps)
         del m4, lr4
 
+    divergence = nd.param_divergence(model)       # max |theta_rank - theta_0| after all the steps above (must be 0)
     if rank != 0:
         return
+    eager = None if args.no_gpu_eager else gpu_eager(dev, args)
     pk = peaks()
     hbm_peak = pk.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
 
@@ -461,18 +573,24 @@ def run_native(args):
         "hbm_kernels": {"peak_GBs": hbm_peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk['_source']})",
                         "kernels": hbm_kernels},
         "loss_last": losses[-1] if losses else None,
+        "dp_param_divergence": divergence,
+        "gpu_eager": eager,
+        "env_overrides": sorted(k for k in os.environ if k.startswith("NERVECL_")),
         "other_kernels_ms_per_step": {k: round(d["ms"] / args.steps, 3) for k, d in
                                       sorted(ksum.items(), key=lambda kv: -kv[1]["ms"]) if not k.startswith("conv")},
     }
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        rows = pick_cpu_sample(args, args.cpu_budget)
-        t = cpu_train_step_seconds(rows, W, args.features, args.blocks)
+        arm = CpuArm(args.features, args.blocks)
+        rows = pick_cpu_sample(arm, args, args.cpu_budget)
+        t = arm.step_seconds(1, rows, W)
+        what = "the reference's own SuperResolutionNet (oracle/_ref)" if arm.kind == "reference" else "oracle port"
         line["cpu_baseline"] = {
-            "value": (rows / H) / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"oracle port (fp32 ATen-CPU, {torch.get_num_threads()} threads): 1 clip x {rows}/{H} rows of "
+            "value": (rows / H) / t, "unit": UNIT, "cores": cores, "kind": arm.kind, "cpu": lscpu_model(),
+            "sample": (f"{what} (fp32 ATen-CPU, {torch.get_num_threads()} threads): 1 clip x {rows}/{H} rows of "
                        f"the {W}x{H} window, one fwd+MSE+bwd step = {t:.1f} s, scaled by pixel count"),
+            "cfg1": cpu_cfg1(arm),
         }
     print(json.dumps(line), flush=True)
 

@@ -97,10 +97,10 @@ class GradSync:
         if self.world == 1:
             return
         chunk = self._flat[a:b]
-        if chunk.is_cuda:
+        if dist.get_backend(self.group) == "nccl":
             work = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             self._works.append((work, None))
-        else:   # gloo (CPU tests): no AVG
+        else:   # gloo (CPU tests, and the 2-ranks-on-one-GPU parity test): no AVG
             work = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._works.append((work, chunk))
 
@@ -136,6 +136,30 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+def sync_buffers(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Broadcast rank ``src``'s buffers (the BatchNorm running statistics) to every rank -- what DDP does at the start
+    of every forward.  The ranks' statistics drift apart during training because BatchNorm stays per-rank (the
+    single-process reference has no SyncBN); call this before validation / checkpointing so every rank evaluates,
+    and rank 0 saves, the same model."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in module.buffers():
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def param_divergence(module: torch.nn.Module, group=None) -> float:
+    """max over ranks and parameters of |theta_rank - theta_rank0| (must be exactly 0 under data parallelism)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0.0
+    worst = torch.zeros(1, device=next(module.parameters()).device)
+    for p in module.parameters():
+        ref = p.detach().clone()
+        dist.broadcast(ref, src=0, group=group)
+        worst = torch.maximum(worst, (p.detach() - ref).abs().max().reshape(1))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+    return float(worst.item())
 
 
 def shard_clips(num_clips: int, rank: int, world: int) -> List[int]:

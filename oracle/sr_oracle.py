@@ -263,3 +263,42 @@ def train_step_grads(sd: Dict[str, Tensor], lr_frames: Tensor, target: Tensor, s
         if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
             sd[k].copy_(work[k])
     return out.detach(), loss.detach(), {n: g for n, g in zip(names, grads)}
+
+
+def random_state_dict(scale: int = 2, features: int = 64, blocks: int = 8, frames: int = 3,
+                      seed: int = 0) -> Dict[str, Tensor]:
+    """A state_dict with the reference's key names and shapes and fan-in scaled random values,
+    for timing the port without importing either the reference or the product package."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, cout, cin, k, bias=True):
+        sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) / (cin * k * k) ** 0.5
+        if bias:
+            sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) / (cin * k * k) ** 0.5
+
+    F_ = features
+    conv("feature_extractor.head.0", F_, 3, 3)
+    for j in range(3):
+        pre = f"feature_extractor.body.{j}."
+        sd[pre + "depthwise.weight"] = (torch.rand(F_, 1, 3, 3, generator=g) * 2 - 1) / 3.0
+        conv(pre + "pointwise", F_, F_, 1, bias=False)
+        sd[pre + "bn.weight"], sd[pre + "bn.bias"] = torch.ones(F_), torch.zeros(F_)
+        sd[pre + "bn.running_mean"], sd[pre + "bn.running_var"] = torch.zeros(F_), torch.ones(F_)
+        sd[pre + "bn.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    for idx, (ci, co) in zip((0, 2, 4, 6), ((81, 128), (128, 64), (64, 32), (32, 2))):
+        conv(f"motion_estimator.flow_net.{idx}", co, ci, 3)
+    conv("temporal_aggregator.attention.0", F_, F_ * frames, 3)
+    conv("temporal_aggregator.attention.2", F_, F_, 3)
+    conv("temporal_aggregator.attention.4", frames, F_, 3)
+    r = max(F_ // 16, 1)
+    sd["temporal_aggregator.refine.channel_attention.fc.0.weight"] = (torch.rand(r, F_, generator=g) * 2 - 1) / F_ ** 0.5
+    sd["temporal_aggregator.refine.channel_attention.fc.2.weight"] = (torch.rand(F_, r, generator=g) * 2 - 1) / r ** 0.5
+    sd["temporal_aggregator.refine.spatial_attention.conv.weight"] = (torch.rand(1, 2, 7, 7, generator=g) * 2 - 1) / 98 ** 0.5
+    for k in range(blocks):
+        for i in range(5):
+            conv(f"residual_blocks.{k}.layers.{i}.0", 32, F_ + 32 * i, 3)
+        conv(f"residual_blocks.{k}.lff", F_, F_ + 160, 1)
+    conv("gff.0", F_, F_, 3)
+    conv("upsampler.conv", 3 * scale * scale, F_, 3)
+    return sd

@@ -1,0 +1,46 @@
+"""Data-parallel correctness on the real CUDA path with world_size 2: both ranks share cuda:0 over the gloo backend
+(a 1-GPU box cannot host two NCCL ranks), which exercises exactly the code the NCCL runs use -- broadcast at set-up,
+bucketed gradient all-reduce driven by the engine's backward, FlatAdamW on the flat buffers, the EWC Fisher reduction
+-- with only the collective's transport swapped.  With >= 2 GPUs the same worker also runs over NCCL."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def launch(backend, tmp_path, port):
+    out = str(tmp_path / f"dp_{backend}")
+    env = dict(os.environ, NERVECL_DP_BACKEND=backend, NERVECL_DP_OUT=out)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dp_worker.py")]
+    proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    return [json.load(open(f"{out}.{r}")) for r in range(2)]
+
+
+def check(results):
+    for r in results:
+        assert r["world"] == 2
+        assert r["divergence_after_broadcast"] == 0.0
+        assert r["sync_vs_mean_local"] <= 1e-6
+        assert r["buckets"] >= 2                          # really bucketed (64 KiB buckets on a ~100 k parameter model)
+        assert r["divergence_after_steps"] == 0.0         # identical parameters on every rank after 4 AdamW steps
+        assert r["bn_drift_before_sync"] > 0.0 and r["bn_drift_after_sync"] == 0.0
+        assert r["grad_sync_restored"]
+        assert r["fisher_vs_single_process"] <= 1e-5
+
+
+def test_two_ranks_one_gpu_gloo(tmp_path):
+    check(launch("gloo", tmp_path, 29631))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_ranks_nccl(tmp_path):
+    check(launch("nccl", tmp_path, 29632))

@@ -443,7 +443,8 @@ TC_SHAPES = [  # (N, H, W, Cin, Cout, K)
     (1, 19, 140, 96, 128, 3), (1, 64, 128, 64, 32, 3), (1, 3, 640, 64, 48, 3),
     # 1x1 through the row-streaming kernel (centre tap only, zero-filled ky = 0 / 2 weight blocks)
     (1, 20, 130, 64, 64, 1), (2, 9, 200, 64, 32, 1), (1, 16, 128, 128, 64, 1), (1, 12, 640, 32, 48, 1),
-    (1, 360, 640, 64, 32, 3),
+    # the benchmark's own geometry (cfg 2: 360 x 640 -> 5 column strips, 360-row items, accumulator-ring wrap)
+    (1, 360, 640, 64, 32, 3), (1, 360, 640, 160, 32, 3), (2, 360, 640, 64, 64, 1),
 ]
 BF16_TOL = 6e-3
 
@@ -470,7 +471,7 @@ def test_conv_fwd_tcgen05_epilogue(shape):
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0          # never writes outside its slice
 
 
-@pytest.mark.parametrize("shape", TC_SHAPES[:-1])
+@pytest.mark.parametrize("shape", TC_SHAPES)
 def test_conv_dgrad_tcgen05_accumulate_mask(shape):
     from nerve_cl_b200 import ops
     n, h, w, cout, cin, k = shape          # roles swapped: dY has `cout` channels, dX has `cin`
@@ -579,7 +580,8 @@ WG_SHAPES = [  # (N, H, W, Cin, Cout, K)
     (1, 20, 72, 64, 12, 3), (2, 17, 40, 32, 2, 3), (1, 24, 64, 3, 64, 3),
     (1, 16, 128, 64, 32, 3), (2, 20, 72, 96, 32, 3), (1, 9, 200, 192, 32, 3), (1, 24, 40, 64, 64, 3),
     (1, 16, 64, 224, 64, 1), (2, 8, 16, 128, 64, 3), (1, 33, 65, 81, 128, 3), (1, 30, 257, 160, 32, 3),
-    (3, 11, 23, 64, 64, 1), (1, 40, 136, 192, 64, 3), (2, 90, 160, 64, 32, 3),
+    (3, 11, 23, 64, 64, 1), (1, 40, 136, 192, 64, 3), (2, 90, 160, 64, 32, 3), (1, 360, 640, 64, 64, 3),
+    (1, 360, 640, 224, 64, 1),
 ]
 
 
@@ -602,7 +604,7 @@ def test_conv_wgrad_tcgen05(shape):
     assert relerr(db, 0.5 * b.grad) <= 1e-3
 
 
-@pytest.mark.parametrize("shape", [(1, 20, 200), (2, 33, 128), (1, 9, 640)])
+@pytest.mark.parametrize("shape", [(1, 20, 200), (2, 33, 128), (1, 9, 640), (1, 360, 640)])
 def test_conv3x3_wgrad_grouped_dense_block(shape):
     """One GEMM for the weight/bias gradients of the five dense-block layers (channel-prefix inputs of one
     buffer, adjacent output-gradient slices) == five separate ATen convolution_backward calls."""
@@ -625,7 +627,7 @@ def test_conv3x3_wgrad_grouped_dense_block(shape):
 
 
 @pytest.mark.parametrize("shape", [(1, 20, 130, 96, 32, 64), (2, 9, 200, 160, 64, 64), (1, 40, 128, 32, 32, 64),
-                                   (1, 12, 136, 64, 48, 32)])
+                                   (1, 12, 136, 64, 48, 32), (1, 360, 640, 96, 32, 64), (1, 360, 640, 160, 64, 64)])
 @pytest.mark.parametrize("center", [True, False])
 def test_conv_rows_second_input(shape, center):
     """Virtual channel concat [x | x2] (row-streaming tcgen05 engine): 3x3 over x plus x2 through all taps or
