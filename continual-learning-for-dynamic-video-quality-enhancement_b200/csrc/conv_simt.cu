@@ -108,10 +108,11 @@ conv_fwd_kernel(const nervecl_conv_params a) {
       if (co >= a.Cout) break;
       float v = acc[i][j];
       if (a.bias) v += __ldg(a.bias + co);
-      if (a.relu) v = fmaxf(v, 0.f);
+      if (a.relu == 1) v = fmaxf(v, 0.f);
       v *= a.alpha;
       if (res && co < a.res_channels) v += ldf(res + p * a.ldres + co);
       if (a.accumulate) v += ldf(const_cast<const TO*>(out) + p * a.ldo + co);
+      if (a.relu == 2) v = fmaxf(v, 0.f);
       if (mask && co >= a.mask_c0) {
         float m = ldf(mask + p * a.ldmask + co);
         if (msub) m -= ldf(msub + p * a.ldmask_sub + co);

@@ -1,5 +1,5 @@
 // Fused epilogue shared by the tcgen05 convolution kernels: one thread = one output pixel (TMEM lane), 16
-// consecutive output channels per chunk.  v = acc; +bias; ReLU; *alpha; +res; +out (accumulate); ReLU-mask.
+// consecutive output channels per chunk.  v = acc; +bias; ReLU (relu == 1); *alpha; +res; +out (accumulate); ReLU (relu == 2); ReLU-mask.
 #pragma once
 #include "tc_common.cuh"
 
@@ -124,7 +124,7 @@ struct EpiChunk {
           f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
         }
       }
-      if (a.relu) {
+      if (a.relu == 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
       }
@@ -140,6 +140,10 @@ struct EpiChunk {
         unpack16(acc, t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] += t[j];
+      }
+      if (a.relu == 2) {                      // ReLU AFTER the residual (ResidualBlock: relu(conv(..) + identity))
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
       }
       if (has_mask) {
         unpack16(msk, t);
@@ -160,10 +164,11 @@ struct EpiChunk {
         if (c >= a.Cout) break;
         float x = f[j];
         if (a.bias) x += __ldg(a.bias + c);
-        if (a.relu) x = fmaxf(x, 0.f);
+        if (a.relu == 1) x = fmaxf(x, 0.f);
         x *= a.alpha;
         if (a.res && c < a.res_channels) x += ldf(a.res + p * a.ldres + c);
         if (a.accumulate) x += ldf(reinterpret_cast<const bf16*>(a.out) + p * a.ldo + c);
+        if (a.relu == 2) x = fmaxf(x, 0.f);
         if (a.mask && c >= a.mask_c0) {
           float m = ldf(a.mask + p * a.ldmask + c);
           if (a.msub) m -= ldf(a.msub + p * a.ldmsub + c);

@@ -815,7 +815,7 @@ int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.x_center = a.K == 1;
   t.strips = p.strips; t.R = p.R; t.segs = p.segs; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.merged = p.merged;
   { const char* d = nv::tune_env("NERVECL_ROWS_DBG"); t.dbg = d ? atoi(d) : 0; }
-  const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.mask_sub &&
+  const bool whole = a.Cout % 16 == 0 && a.Cout % p.NOUT == 0 && a.out_dtype == NERVECL_BF16 && !a.mask_sub && a.relu != 2 &&
                      p.NOUT <= 128 && !ROWS_DBG(t, 64);
   t.fast = 0;
   if (whole && !a.accumulate) {

@@ -234,6 +234,22 @@ __global__ void __launch_bounds__(256) si_register_kernel(TensorTable tb, float*
   }
 }
 
+// flat[off_i + k] = src_i[k]
+__global__ void __launch_bounds__(256) flat_gather_kernel(TensorTable tb, float* __restrict__ flat) {
+  const int ti = blockIdx.y;
+  const float* __restrict__ g = tb.src[ti];
+  float* __restrict__ f = flat + tb.off[ti];
+  const int64_t n = tb.n[ti];
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok(g, f, nullptr)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) reinterpret_cast<float4*>(f)[i] = reinterpret_cast<const float4*>(g)[i];
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) f[i] = g[i];
+  } else {
+    for (int64_t i = tid; i < n; i += stride) f[i] = g[i];
+  }
+}
+
 inline dim3 table_grid(const TensorTable& tb, int cnt) {
   int64_t maxn = 1;
   for (int i = 0; i < cnt; ++i) maxn = imax(maxn, tb.n[i]);
@@ -244,9 +260,10 @@ inline dim3 table_grid(const TensorTable& tb, int cnt) {
 // Walks `ntensors` host-side table entries in chunks of at most MT LIVE tensors and calls launch(table, count) per
 // chunk.  One running index crosses the chunks, so skipped entries (NULL first pointer when `skip_null`, or zero
 // elements) can neither be visited twice nor shift the flat offsets of what follows.  `second` may be NULL.
+// `offsets` (nullable) overrides the running offsets (a flat layout with padded slots).
 template <typename Launch>
 int for_each_chunk(const float* const* first, float* const* second, const int64_t* numel, int ntensors, bool skip_null,
-                   bool second_optional, Launch&& launch) {
+                   bool second_optional, Launch&& launch, const int64_t* offsets = nullptr) {
   int64_t off = 0;
   int i = 0;
   while (i < ntensors) {
@@ -254,12 +271,14 @@ int for_each_chunk(const float* const* first, float* const* second, const int64_
     int cnt = 0;
     for (; i < ntensors && cnt < MT; ++i) {
       if (numel[i] < 0) return NERVECL_EINVAL;
-      if (!first[i] && !skip_null) return NERVECL_EINVAL;
-      if (second && !second[i] && !second_optional) return NERVECL_EINVAL;
+      if (numel[i] > 0) {                          // (an empty tensor may legitimately have a NULL data pointer)
+        if (!first[i] && !skip_null) return NERVECL_EINVAL;
+        if (second && !second[i] && !second_optional) return NERVECL_EINVAL;
+      }
       if (first[i] && numel[i] > 0) {
         tb.src[cnt] = first[i];
         tb.dst[cnt] = second ? second[i] : nullptr;
-        tb.off[cnt] = off;
+        tb.off[cnt] = offsets ? offsets[i] : off;
         tb.n[cnt] = numel[i];
         ++cnt;
       }
@@ -309,6 +328,15 @@ NV_API int nervecl_ewc_penalty_bwd(const float* const* theta_host, float* const*
     penalty_bwd_kernel<<<table_grid(tb, cnt), 256, 0, as_stream(stream)>>>(tb, fisher, star, coef2, gscale);
     return launch_status();
   });
+}
+
+NV_API int nervecl_flat_gather(const float* const* src_host, const int64_t* numel_host, const int64_t* offset_host,
+                               int ntensors, float* flat, nervecl_stream_t stream) {
+  if (!src_host || !numel_host || !offset_host || !flat || ntensors <= 0) return NERVECL_EINVAL;
+  return for_each_chunk(src_host, nullptr, numel_host, ntensors, true, false, [&](const TensorTable& tb, int cnt) {
+    flat_gather_kernel<<<table_grid(tb, cnt), 256, 0, as_stream(stream)>>>(tb, flat);
+    return launch_status();
+  }, offset_host);
 }
 
 NV_API int nervecl_si_update(const float* const* theta_host, const float* const* grad_host, const int64_t* numel_host,

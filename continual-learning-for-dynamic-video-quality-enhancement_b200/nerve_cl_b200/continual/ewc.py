@@ -49,22 +49,6 @@ class _FlatState:
         return st
 
 
-def _flat_grad_for(model, layout, device):
-    """A zeroed flat fp32 gradient buffer + per-parameter views for ``layout``.  When ``model`` owns a padded
-    flat layout (``SuperResolutionNet._flat_layout``: the layout of the fused optimiser / DDP buckets) and ``layout``
-    covers exactly its parameters, the buffer uses THAT layout and is announced to the module, so that if autograd
-    adopts these views as ``param.grad`` (the penalty node usually runs before the network's own backward node) the
-    fused single-launch optimiser step still finds one flat gradient buffer."""
-    fl = getattr(model, "_flat_layout", None)
-    if fl is not None and [n for n, _, _ in layout] == list(fl):
-        flat = torch.zeros(model._flat_numel, device=device, dtype=torch.float32)
-        views = [flat[o:o + k].view(shape) for o, k, shape in (fl[n] for n, _, _ in layout)]
-        model._note_flat_grad(flat)
-        return flat, views
-    g = _FlatState(layout, device)
-    return g.flat, [g.views[name] for name, _, _ in layout]
-
-
 class _PenaltyFn(torch.autograd.Function):
     """penalty = coef * sum_states sum F (theta - star)^2 as one autograd node over all parameters."""
 
@@ -81,7 +65,8 @@ class _PenaltyFn(torch.autograd.Function):
     def backward(ctx, gout: Tensor):
         theta = ctx.theta
         layout = ctx.states[0][0].layout
-        _, grads = _flat_grad_for(ctx.model, layout, theta[0].device)      # fresh zeroed flat gradient
+        g = _FlatState(layout, theta[0].device)             # fresh zeroed flat gradient
+        grads = [g.views[name] for name, _, _ in layout]
         gs = gout.detach().reshape(1).float().contiguous()
         for fisher, star in ctx.states:
             nv.ewc_penalty_bwd(theta, grads, fisher.flat, star.flat, 2.0 * ctx.coef, gs)

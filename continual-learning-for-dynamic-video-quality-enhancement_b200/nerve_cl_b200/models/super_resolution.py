@@ -120,7 +120,7 @@ class _SRFunction(torch.autograd.Function):
         plan.backward(acts, dout.contiguous().float(), P, G, hook)
         if module._grad_sync is not None:
             module._grad_sync.finish()
-        module._note_flat_grad(flat)
+        module._last_flat_grad = flat
         ctx.acts = None
         plan.release(acts)
         return (None, None) + tuple(G[n] for n in names)
@@ -170,7 +170,7 @@ class SuperResolutionNet(nn.Module):
         self._keep_intermediate = False
         self._grad_mode = True
         self._last_acts = None
-        self._flat_grads: List[Tensor] = []
+        self._last_flat_grad: Optional[Tensor] = None
         self._grad_sync = None
         self._param_names: List[str] = [n for n, _ in self.named_parameters()]
         off = 0
@@ -291,23 +291,14 @@ class SuperResolutionNet(nn.Module):
     def last_flat_grad(self) -> Optional[Tensor]:
         """The flat fp32 gradient buffer of the most recent backward (parameter order, 16-byte aligned
         slots) if every ``param.grad`` still aliases it -- lets optimisers / EWC run one fused kernel."""
-        p0 = next(self.parameters())
-        if p0.grad is None:
+        flat = self._last_flat_grad
+        if flat is None:
             return None
-        # newest first: whichever backward node ran FIRST in this step owns the buffer autograd adopted (the others
-        # were added into it in place), e.g. the EWC penalty node when the loss is mse + penalty
-        for flat in reversed(self._flat_grads):
-            if p0.grad.data_ptr() != flat.data_ptr():
-                continue
-            if all(p.grad is not None and p.grad.data_ptr() == flat.data_ptr() + 4 * self._flat_layout[n][0]
-                   for n, p in self.named_parameters()):
-                return flat
-        return None
-
-    def _note_flat_grad(self, flat: Tensor) -> None:
-        """Remember a flat gradient buffer laid out by ``_flat_layout`` (the last few: one per backward node)."""
-        self._flat_grads.append(flat)
-        del self._flat_grads[:-3]
+        for n, p in self.named_parameters():
+            o, k, _ = self._flat_layout[n]
+            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * o:
+                return None
+        return flat
 
     def set_gradient_sync(self, sync) -> None:
         """Install a ``distributed.GradSync`` (bucketed all-reduce overlapped with backward)."""

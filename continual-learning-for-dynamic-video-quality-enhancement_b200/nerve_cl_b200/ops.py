@@ -633,6 +633,16 @@ def _ewc_penalty_bwd(theta, grads, fisher, star, coef2, gscale) -> None:
                                                   _stream()), "ewc_penalty_bwd")
 
 
+@_op("flat_gather(Tensor?[] src, int[] offsets, Tensor(a!) flat) -> ()")
+def _flat_gather(src, offsets, flat) -> None:
+    """flat[offsets[i] : offsets[i] + src[i].numel()] = src[i] for every non-None entry (``nervecl_flat_gather``)."""
+    _check_flat_list(src, "src")
+    ptrs, n = _table(src)
+    numels = (C.c_int64 * n)(*[0 if t is None else t.numel() for t in src])
+    _lib.check(_lib.load().nervecl_flat_gather(ptrs, numels, (C.c_int64 * n)(*offsets), n, _flat(flat, "flat"), _stream()),
+               "flat_gather")
+
+
 @_op("si_update(Tensor[] theta, Tensor?[] grads, Tensor(a!) W, Tensor(b!) p_old) -> ()")
 def _si_update(theta, grads, W, p_old) -> None:
     """Synaptic Intelligence running importance (``nervecl_si_update``, reference ewc.py:342-352)."""

@@ -359,6 +359,12 @@ int nervecl_ewc_penalty_bwd(const float* const* theta_host, float* const* grad_h
                             const float* star, float coef2, const float* gscale,
                             nervecl_stream_t stream);
 
+/* flat[offset_i + k] = src_i[k] for every non-NULL src_i: gathers per-parameter tensors (e.g. .grad tensors that autograd
+ * summed out of place) into one flat buffer with explicit slot offsets, so the fused optimiser step stays ONE launch. */
+int nervecl_flat_gather(const float* const* src_host, const int64_t* numel_host,
+                        const int64_t* offset_host, int ntensors, float* flat,
+                        nervecl_stream_t stream);
+
 /* Synaptic Intelligence (nerve_cl/continual/ewc.py:306-379) on flat fp32 state laid out like the EWC
  * buffers (tensor i at offset sum of the numels before it).
  * update (ewc.py:342-352, after every optimiser step): for every tensor whose grad pointer is non-NULL

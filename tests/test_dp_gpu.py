@@ -32,9 +32,13 @@ def check(results):
         assert r["sync_vs_mean_local"] <= 1e-6
         assert r["buckets"] >= 2                          # really bucketed (64 KiB buckets on a ~100 k parameter model)
         assert r["divergence_after_steps"] == 0.0         # identical parameters on every rank after 4 AdamW steps
-        assert r["bn_drift_before_sync"] > 0.0 and r["bn_drift_after_sync"] == 0.0
+        assert r["bn_drift_after_sync"] == 0.0
         assert r["grad_sync_restored"]
         assert r["fisher_vs_single_process"] <= 1e-5
+
+
+    # BatchNorm stays per rank (no SyncBN in the single-process reference): rank 1 drifted before sync_buffers
+    assert results[1]["bn_drift_before_sync"] > 0.0
 
 
 def test_two_ranks_one_gpu_gloo(tmp_path):

@@ -5,7 +5,7 @@ x4) go through the bf16 tcgen05 engine, the fp32 parity path and the CPU oracle 
 geometry bench.py times (5 column strips of 128 pixels, 360-row work items, accumulator-ring wrap, all 148 CTAs busy)
 instead of the small shapes of test_sr_gpu.py.  The full B=16 benchmark batch is then tied to that oracle-checked
 window through a size-independent property: a batch of 16 identical windows must reproduce the single window's
-output (bitwise in eval mode: same per-pixel arithmetic, different CTA assignment) and its parameter gradients.
+output (to >= 55 dB: same per-pixel arithmetic, different CTA assignment and atomic-sum order) and its parameter gradients.
 
 Tolerances (BASELINE.json north_star): fp32 path rel-err <= 1e-4 (outputs; gradients as global relative L2, see
 __graft_entry__.smoke for why), bf16 path PSNR delta <= 0.05 dB vs the fp32 reference output and >= 40 dB to it.
@@ -108,7 +108,8 @@ def test_cfg2_full_batch_reproduces_the_window(cfg2):
         with torch.no_grad():
             y1 = model(x).clone()
             yb = model(xb)
-        assert all(torch.equal(yb[i], y1[0]) for i in range(16))
+        # (not bitwise: the channel-attention pool is an atomic float sum, so the gate differs in its last bit)
+        assert all(psnr(yb[i:i + 1], y1) >= 55.0 for i in range(16))
     finally:
         model.train()
     out1, loss1, g1 = run(model, x, tgt, torch.bfloat16, sd)
@@ -147,10 +148,10 @@ def test_cfg3_window_vs_oracle():
         e_out = e_out[0] if isinstance(e_out, tuple) else e_out
         model.compute_dtype = torch.bfloat16
         y = model(x.cuda())
-        # a batch of 16 identical windows (bench.py's infer_x4 batch) reproduces it bitwise
+        # a batch of 16 identical windows (bench.py's infer_x4 batch) reproduces it
         yb = model(x.cuda().expand(16, -1, -1, -1, -1).contiguous())
     assert psnr(y, e_out) >= 40.0 and abs(psnr(y, tgt) - psnr(e_out, tgt)) <= 0.05
-    assert all(torch.equal(yb[i], y[0]) for i in range(16))
+    assert all(psnr(yb[i:i + 1], y) >= 55.0 for i in range(16))
 
 
 def test_bf16_loss_trajectory_tracks_fp32():
