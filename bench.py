@@ -450,10 +450,14 @@ def run_native(args):
     model.train()
 
     # ---- BASELINE.json configs[2]: x4 inference, 320x180 -> 1280x720, T=5 (clip-sharded: each rank its own clips) ----
-    ms_x4, x4_batch = None, 16
-    if args.dtype == "bf16" and (args.height, args.width) == (360, 640):
-        m4 = SuperResolutionNet(scale_factor=4, num_features=args.features, num_residual_blocks=args.blocks,
-                                temporal_window=2).to(dev).eval()
+    ms_x4, x4_batch, x4_e2e, cfg4, cfg5 = None, 16, None, None, None
+    full_cfg = args.dtype == "bf16" and (args.height, args.width) == (360, 640)
+    if full_cfg:
+        from nerve_cl_b200.models import EnhancementConfig, EnhancementEngine
+        from nerve_cl_b200.continual import EWC
+        eng4 = EnhancementEngine(EnhancementConfig(frame_recovery_enabled=False, scale_factor=4, sr_num_features=args.features,
+                                                   sr_num_residual_blocks=args.blocks, sr_temporal_window=2)).to(dev).eval()
+        m4 = eng4.super_resolution
         m4.compute_dtype = torch.bfloat16
         lr4 = torch.rand(x4_batch, 5, 3, 180, 320, device=dev)
 
@@ -464,7 +468,82 @@ def run_native(args):
         infer4_step()
         infer4_step()
         ms_x4 = timed(infer4_step, args.steps)
-        del m4, lr4
+        del lr4
+        # end to end through the public API: one 32-frame clip per step, pinned host frames -> device ->
+        # EnhancementEngine.enhance_video (sliding windows batched 16 per network call) -> HR frames back in pinned host memory
+        clip_frames = 32
+        clip_host = torch.rand(clip_frames, 3, 180, 320).pin_memory()
+        hr_host4 = torch.empty(clip_frames, 3, 720, 1280).pin_memory()
+
+        def infer4_e2e():
+            v = clip_host.to(dev, non_blocking=True)
+            hr_host4.copy_(eng4.enhance_video(v, batch_size=x4_batch), non_blocking=True)
+
+        infer4_e2e()
+        ms = timed(infer4_e2e, args.steps)
+        x4_e2e = {"metric": "sr_x4_infer_frames_per_sec", "value": clip_frames * world * args.steps / (ms / 1e3), "unit": UNIT,
+                  "ms_per_clip": ms / args.steps, "frames_per_clip": clip_frames,
+                  "h2d_bytes_per_step": clip_host.numel() * 4, "d2h_bytes_per_step": hr_host4.numel() * 4,
+                  "note": "host frames -> EnhancementEngine.enhance_video (16 windows per call) -> HR frames in pinned host memory"}
+        del eng4, m4
+
+        # ---- configs[3]: continual training step = EnhancementEngine(SR-only) fwd + MSE + EWC penalty + bwd + AdamW, with
+        #      8 replayed samples appended to the batch of 16 (train_continual.py's two strategies in one step) ----
+        engc = EnhancementEngine(EnhancementConfig(frame_recovery_enabled=False, sr_num_features=args.features,
+                                                   sr_num_residual_blocks=args.blocks)).to(dev).train()
+        src = engc.super_resolution
+        src.compute_dtype = torch.bfloat16
+        nd.data_parallel(src)
+        optc = FlatAdamW(src, lr=1e-4, weight_decay=0.0)
+        ewc = EWC(src, ewc_lambda=5000.0)
+        if world > 1:
+            ewc.process_group = dist.group.WORLD
+        ewc.register_task(0, [(lr_dev[:4], hr_dev[:4])])
+        engc.train()
+        lr_c = torch.cat([lr_dev, lr_dev[:8]])
+        hr_c = torch.cat([hr_dev, hr_dev[:8]])
+        l0 = ops.LAUNCHES[0]
+
+        def cont_step():
+            optc.zero_grad()
+            loss = torch.nn.functional.mse_loss(engc(lr_c)["enhanced"], hr_c) + ewc.penalty()
+            loss.backward()
+            optc.step()
+
+        cont_step()
+        cont_step()
+        l0 = ops.LAUNCHES[0]
+        ms = timed(cont_step, args.steps)
+        cfg4 = {"metric": "continual_train_frames_per_sec", "value": 24 * world * args.steps / (ms / 1e3), "unit": UNIT,
+                "ms_per_step": ms / args.steps, "batch": "16 new + 8 replayed windows per GPU",
+                "launches_per_step": (ops.LAUNCHES[0] - l0) / args.steps,
+                "note": "EnhancementEngine(SR-only)['enhanced'] + MSE + EWC penalty (lambda 5000, online) + bwd + fused AdamW"}
+        del engc, src, optc, ewc, lr_c, hr_c
+        torch.cuda.empty_cache()
+
+        # ---- configs[4]: full pipeline, FrameRecoveryNet inpainting -> x2 SR, 540p -> 1080p, host to host ----
+        eng5 = EnhancementEngine(EnhancementConfig()).to(dev).eval()
+        eng5.super_resolution.compute_dtype = torch.bfloat16
+        eng5.frame_recovery.compute_dtype = torch.bfloat16
+        n5 = 16
+        clip5 = torch.rand(n5, 3, 540, 960).pin_memory()
+        mask5 = torch.zeros(n5, 1, 540, 960)
+        mask5[::2, :, 100:300, 200:600] = 1
+        mask5 = mask5.pin_memory()
+        out5 = torch.empty(n5, 3, 1080, 1920).pin_memory()
+
+        def pipe_step():
+            v, m = clip5.to(dev, non_blocking=True), mask5.to(dev, non_blocking=True)
+            out5.copy_(eng5.enhance_video(v, m, batch_size=8), non_blocking=True)
+
+        pipe_step()
+        ms = timed(pipe_step, max(args.steps // 2, 1))
+        cfg5 = {"metric": "enhance_pipeline_frames_per_sec", "value": n5 * world * max(args.steps // 2, 1) / (ms / 1e3),
+                "unit": UNIT, "ms_per_clip": ms / max(args.steps // 2, 1), "frames_per_clip": n5,
+                "note": "EnhancementEngine.enhance_video: FrameRecoveryNet (4 reference frames, mask on every 2nd frame) + "
+                        "SuperResolutionNet x2, 960x540 -> 1920x1080, host frames in, HR frames back in pinned host memory"}
+        del eng5
+        torch.cuda.empty_cache()
 
     divergence = nd.param_divergence(model)       # max |theta_rank - theta_0| after all the steps above (must be 0)
     if rank != 0:
@@ -570,6 +649,9 @@ def run_native(args):
                       "unit": UNIT, "ms_per_batch": ms_x4 / args.steps,
                       "note": "BASELINE configs[2]: scale 4, T=5, 320x180 -> 1280x720, B=16/GPU, eval forward, inputs in HBM"}
                      if ms_x4 else None),
+        "infer_x4_e2e": x4_e2e,
+        "continual_train": cfg4,
+        "enhance_pipeline": cfg5,
         "hbm_kernels": {"peak_GBs": hbm_peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk['_source']})",
                         "kernels": hbm_kernels},
         "loss_last": losses[-1] if losses else None,

@@ -492,6 +492,25 @@ upfinish_bwd_kernel(const float* __restrict__ conv, const float* __restrict__ lr
   }
 }
 
+// EnhancementEngine strength blend (enhancement_engine.py:172-182): out = strength * out + (1 - strength) * bicubic(lr)
+__global__ void __launch_bounds__(256)
+bicubic_blend_kernel(float* __restrict__ out, const float* __restrict__ lr, int64_t sN, int64_t sC, int64_t sH, int N, int C,
+                     int H, int W, int s, float rscale, float strength) {
+  const int HO = H * s, WO = W * s;
+  const int64_t total = (int64_t)N * C * HO * WO;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int X = (int)(i % WO);
+    int64_t r = i / WO;
+    int Y = (int)(r % HO);
+    r /= HO;
+    int c = (int)(r % C);
+    int n = (int)(r / C);
+    const float b = bicubic_sample(lr + n * sN + c * sC, sH, H, W, Y, X, rscale);
+    out[i] = strength * out[i] + (1.f - strength) * b;
+  }
+}
+
 inline int ew_blocks(int64_t work) { return (int)imax(1, imin(cdiv(work, 256), kSMs * 16)); }
 inline bool group_ok(int C) {
   int cg = C >> 3;
@@ -630,5 +649,14 @@ NV_API int nervecl_upfinish_bwd(const float* conv_out, const float* lr, int64_t 
   float rscale = (float)(1.0 / (double)s);
   upfinish_bwd_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(conv_out, lr, sN, sC, sH, dout, dconv, N, C,
                                                                        H, W, s, rscale);
+  return launch_status();
+}
+
+NV_API int nervecl_bicubic_blend(float* out, const float* lr, int64_t sN, int64_t sC, int64_t sH, int N, int C, int H, int W,
+                                 int s, float strength, nervecl_stream_t stream) {
+  if (!out || !lr || N <= 0 || C <= 0 || H <= 0 || W <= 0 || s < 1 || s > 8) return NERVECL_EINVAL;
+  int64_t total = (int64_t)N * C * H * s * W * s;
+  float rscale = (float)(1.0 / (double)s);
+  bicubic_blend_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(out, lr, sN, sC, sH, N, C, H, W, s, rscale, strength);
   return launch_status();
 }

@@ -90,6 +90,15 @@ _SIGNATURES = {
                             c_i64, c_i32, c_vp],
     "nervecl_upfinish_fwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_upfinish_bwd": [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "nervecl_bicubic_blend": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp],
+    "nervecl_conv2d_direct": [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                              c_i32, c_i32, c_i32, c_vp],
+    "nervecl_maxpool2d": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "nervecl_depth_to_space": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "nervecl_resize_bilinear": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "nervecl_fusion_blend": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32,
+                             c_i64, c_vp],
+    "nervecl_recovery_finish": [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_axpy": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_f32, c_i32, c_vp],
     "nervecl_relu_bwd": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp],
     "nervecl_fill_zero": [c_vp, C.c_size_t, c_vp],

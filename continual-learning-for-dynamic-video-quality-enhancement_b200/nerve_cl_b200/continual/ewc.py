@@ -123,9 +123,9 @@ class EWC:
         # Data-parallel runs: the Fisher is sum over LOCAL batches of (local batch-mean gradient)^2, summed over ranks
         # below.  A gradient all-reduce inside backward would square the rank-AVERAGED
         # gradient instead (and hang when ranks see different batch counts), so it is switched off for this pass.
-        saved_sync = getattr(self.model, "_grad_sync", None)
-        if saved_sync is not None:
-            self.model._grad_sync = None
+        synced = [(m, m._grad_sync) for m in self.model.modules() if getattr(m, "_grad_sync", None) is not None]
+        for m, _ in synced:
+            m._grad_sync = None
         try:
             for batch in dataloader:
                 if num_samples is not None and used >= num_samples:
@@ -149,8 +149,8 @@ class EWC:
                 nv.ewc_fisher_accum(fisher.flat, grads, numels, 1.0)
                 used += inputs.size(0)
         finally:
-            if saved_sync is not None:
-                self.model._grad_sync = saved_sync
+            for m, sync in synced:
+                m._grad_sync = sync
         if self.process_group is not None:
             import torch.distributed as dist
             cnt = torch.tensor([float(used)], device=dev)

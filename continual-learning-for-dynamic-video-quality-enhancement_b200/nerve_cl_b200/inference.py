@@ -17,7 +17,6 @@ from __future__ import annotations
 from typing import List, Optional
 
 import torch
-import torch.nn.functional as F
 
 Tensor = torch.Tensor
 
@@ -55,10 +54,19 @@ def enhance_video(model: torch.nn.Module, video: Tensor, batch_size: int = 16, r
     idx = sr_window_indices(T, model.temporal_window, recovery_temporal_window).to(video.device)
     windows = video[:, idx]                                                   # (B, T, T', C, H, W), one device gather
     windows = windows.reshape(B * T, idx.shape[1], C, H, W)
-    outs = [model(windows[i:i + batch_size]) for i in range(0, B * T, batch_size)]
+    # inference means eval mode: in train mode BatchNorm would normalise with the statistics of whichever windows share
+    # a batch (and update the running statistics), so the result would depend on batch_size -- the reference calls the
+    # network per window.  The mode is restored afterwards.  (The tail batch, if smaller, gets its own shape plan.)
+    was_training = model.training
+    model.eval()
+    try:
+        outs = [model(windows[i:i + batch_size]) for i in range(0, B * T, batch_size)]
+    finally:
+        model.train(was_training)
     out = torch.cat(outs, 0)
-    out = out.view(B, T, *out.shape[1:])
     if enhancement_strength is not None and enhancement_strength < 1.0:
-        bic = F.interpolate(video.reshape(B * T, C, H, W).float(), size=out.shape[-2:], mode="bicubic", align_corners=False)
-        out = enhancement_strength * out + (1.0 - enhancement_strength) * bic.view_as(out)
+        from . import ops as _ops
+        _ops.nv.bicubic_blend(out, video.reshape(B * T, C, H, W).float().contiguous(), out.shape[-1] // W,
+                              float(enhancement_strength))
+    out = out.view(B, T, *out.shape[1:])
     return out.squeeze(0) if squeeze else out

@@ -171,3 +171,40 @@ def warp_indices(flow: Tensor, div_mode: int = 0) -> Tensor:
     idx = torch.empty((b, h, w, 2), device=flow.device, dtype=torch.int32)
     nv.warp_fwd(dummy, fl, out, div_mode, idx)
     return idx
+
+
+class ResidualBlock(_Holder):
+    """dw-separable residual block (efficient_layers.py:109-151): conv1 = DepthwiseSeparableConv, conv2 = dw 3x3 ->
+    pw 1x1 -> BN, ``relu(conv2(conv1(x)) + x)``.  Holder: the arithmetic runs in ``frame_recovery._Runner``."""
+
+    def __init__(self, channels: int, use_efficient: bool = True):
+        super().__init__()
+        if not use_efficient:
+            raise ValueError("nerve_cl_b200.ResidualBlock implements the reference default use_efficient=True only")
+        self.conv1 = DepthwiseSeparableConv(channels, channels)
+        self.conv2 = nn.Sequential(
+            nn.Conv2d(channels, channels, 3, 1, 1, groups=channels, bias=False),
+            nn.Conv2d(channels, channels, 1, 1, 0, bias=False),
+            nn.BatchNorm2d(channels),
+        )
+        self.relu = nn.ReLU(inplace=True)
+
+
+class TemporalConv3D(_Holder):
+    """(2+1)D factorised 3-D convolution (efficient_layers.py:231-294): (1,3,3) spatial conv -> BN3d -> ReLU ->
+    (k,1,1) temporal conv -> BN3d -> ReLU, with the reference's intermediate width formula."""
+
+    def __init__(self, in_channels: int, out_channels: int, temporal_kernel: int = 3):
+        super().__init__()
+        if temporal_kernel != 3:
+            raise ValueError("nerve_cl_b200.TemporalConv3D implements temporal_kernel=3 (the only value the reference uses)")
+        mid = (in_channels * out_channels * 3 * 3 * temporal_kernel) // (in_channels * 3 * 3 + out_channels * temporal_kernel)
+        mid = max(mid, out_channels // 2)
+        self.mid_channels = mid
+        self.spatial = nn.Sequential(
+            nn.Conv3d(in_channels, mid, kernel_size=(1, 3, 3), stride=1, padding=(0, 1, 1), bias=False),
+            nn.BatchNorm3d(mid), nn.ReLU(inplace=True))
+        self.temporal = nn.Sequential(
+            nn.Conv3d(mid, out_channels, kernel_size=(temporal_kernel, 1, 1), stride=1, padding=(temporal_kernel // 2, 0, 0),
+                      bias=False),
+            nn.BatchNorm3d(out_channels), nn.ReLU(inplace=True))

@@ -305,11 +305,41 @@ class SuperResolutionNet(nn.Module):
         self._grad_sync = sync
 
 
-class LightweightSuperResolution(nn.Module):
-    """Reference ``LightweightSuperResolution`` (super_resolution.py:434-470) -- parameter-compatible holder.
+class _LightFunction(torch.autograd.Function):
+    """forward + backward of LightweightSuperResolution as one autograd node (same scheme as ``_SRFunction``)."""
 
-    SURVEY.md section 8f ranks this network as a *next* row; its kernels are not built yet, so forward
-    raises instead of silently running a non-native path."""
+    @staticmethod
+    def forward(ctx, module: "LightweightSuperResolution", x: Tensor, *params: Tensor):
+        names = module._param_names
+        P = {n: p.detach() for n, p in zip(names, params)}
+        need_bwd = module._grad_mode and any(ctx.needs_input_grad[2:])
+        out, saved = module._run_forward(x.detach(), P, need_bwd)
+        if need_bwd:
+            ctx.module, ctx.P, ctx.saved = module, P, saved
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Optional[Tensor]):
+        module, P, saved = ctx.module, ctx.P, ctx.saved
+        names = module._param_names
+        if dout is None:
+            return (None, None) + (None,) * len(names)
+        G = {n: torch.zeros_like(P[n]) for n in names}
+        module._run_backward(saved, dout.contiguous().float(), P, G)
+        ctx.saved = None
+        return (None, None) + tuple(G[n] for n in names)
+
+
+class LightweightSuperResolution(nn.Module):
+    """Ultra-light single-frame SR (reference super_resolution.py:434-470): conv 3->32 + ReLU, four depthwise-separable
+    blocks (dw 3x3 -> pw 1x1 -> BatchNorm -> ReLU), conv 32 -> 3*s^2, PixelShuffle, + bicubic(x), clamp(0, 1).
+
+    Same constructor / ``net`` Sequential / ``state_dict`` keys as the reference; the arithmetic runs on the kernels the
+    SuperResolutionNet extractor and output stage use (9 868 parameters: every layer is bandwidth-bound): the 3-channel
+    head as a 1x1 over 3x3-unfolded pixels, TMA-free generic depthwise / BatchNorm kernels at 32 channels, pointwise
+    convs through ``conv2d_fwd`` (BatchNorm folded into them on the pure-inference path), PixelShuffle + bicubic skip +
+    clamp in ``upfinish``.  Training (batch-statistics BatchNorm, running-stat updates, full backward) is supported."""
 
     def __init__(self, scale_factor: int = 2):
         super().__init__()
@@ -319,7 +349,131 @@ class LightweightSuperResolution(nn.Module):
             *[DepthwiseSeparableConv(32, 32) for _ in range(4)],
             nn.Conv2d(32, 3 * scale_factor ** 2, 3, 1, 1), nn.PixelShuffle(scale_factor))
         self.bicubic = nn.Upsample(scale_factor=scale_factor, mode="bicubic", align_corners=False)
+        self.compute_dtype: Optional[torch.dtype] = None
+        self.conv_engine = _ops.CONV_AUTO
+        self._grad_mode = True
+        self._param_names: List[str] = [n for n, _ in self.named_parameters()]
+
+    def get_num_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def _dtype_now(self) -> torch.dtype:
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
 
     def forward(self, x: Tensor) -> Tensor:
-        raise NotImplementedError("LightweightSuperResolution is outside the B200 hot path built so far "
-                                  "(SURVEY.md section 8f, rank 3)")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected (B, 3, H, W) frames, got shape {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("nerve_cl_b200.LightweightSuperResolution runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the input frames are not produced by the kernel engine")
+        self._grad_mode = torch.is_grad_enabled()
+        return _LightFunction.apply(self, x.float(), *self.parameters())
+
+    # ---- engine -----------------------------------------------------------------------------------------------
+    C, BN_EPS, BN_MOMENTUM = 32, 1e-5, 0.1
+
+    def _pack(self, w: Tensor, adt, flip: bool, rows: int, cols: int) -> Tensor:
+        k = w.shape[-1]
+        dst = torch.empty((k * k, rows, (cols + 7) // 8 * 8), device=w.device, dtype=adt)
+        _ops.nv.pack_conv_weight(w.contiguous().float(), dst, flip)
+        return dst
+
+    def _run_forward(self, x: Tensor, P: Dict[str, Tensor], need_bwd: bool):
+        nv, eng = _ops.nv, self.conv_engine
+        B, _, H, W = x.shape
+        C, s, adt, dev, f32 = self.C, self.scale_factor, self._dtype_now(), x.device, torch.float32
+        training = self.training
+        fold = (not training) and (not need_bwd)
+        BUF = dict(self.named_buffers())
+
+        def act(c, dtype=adt):
+            return torch.empty((B, H, W, c), device=dev, dtype=dtype)
+
+        S: Dict[str, object] = {"x": x, "training": training, "adt": adt}
+        x_in = act(32)
+        nv.pack_frames_unfold3(x.unsqueeze(1), x_in)                       # (B,1,3,H,W): one "frame" per sample
+        head = act(C)
+        w0 = P["net.0.weight"]
+        nv.conv2d_fwd(x_in, self._pack(w0.view(C, 27, 1, 1), adt, False, C, 32), P["net.0.bias"], None, None, None, head, C,
+                      1, False, 0, 0, 1.0, eng)
+        S["x_in"], S["head"] = x_in, head
+        cur = head
+        S["dwo"], S["pwo"], S["act"], S["stat"] = [], [], [], []
+        for j in range(4):
+            pre = f"net.{2 + j}."
+            dwo = act(C)
+            nv.dwconv3x3_fwd(cur, P[pre + "depthwise.weight"], dwo, False, False)
+            y = act(C)
+            if fold:
+                sc = P[pre + "bn.weight"] * torch.rsqrt(BUF[pre + "bn.running_var"] + self.BN_EPS)
+                bias = (P[pre + "bn.bias"] - BUF[pre + "bn.running_mean"] * sc).contiguous()
+                wf = self._pack(P[pre + "pointwise.weight"] * sc.view(-1, 1, 1, 1), adt, False, C, C)
+                nv.conv2d_fwd(dwo, wf, bias, None, None, None, y, C, 1, False, 0, 0, 1.0, eng)
+            else:
+                pwo = act(C)
+                nv.conv2d_fwd(dwo, self._pack(P[pre + "pointwise.weight"], adt, False, C, C), None, None, None, None, pwo, C,
+                              0, False, 0, 0, 1.0, eng)
+                stat = torch.empty((1, C, 2), device=dev, dtype=f32)
+                sums = None
+                if training:
+                    sums = torch.zeros((1, C, 2), device=dev, dtype=torch.float64)
+                    nv.bn_stats(pwo, 1, sums)
+                nv.bn_finalize(sums, stat, BUF[pre + "bn.running_mean"], BUF[pre + "bn.running_var"],
+                               BUF[pre + "bn.num_batches_tracked"], B * H * W, 1, self.BN_MOMENTUM, self.BN_EPS, training)
+                nv.bn_relu_fwd(pwo, stat, P[pre + "bn.weight"], P[pre + "bn.bias"], None, y, 1)
+                S["pwo"].append(pwo); S["stat"].append(stat)
+            S["dwo"].append(dwo); S["act"].append(y)
+            cur = y
+        ncs = 3 * s * s
+        up = act(ncs, f32)
+        nv.conv2d_fwd(cur, self._pack(P["net.6.weight"], adt, False, ncs, C), P["net.6.bias"], None, None, None, up, ncs, 0,
+                      False, 0, 0, 1.0, eng)
+        out = torch.empty((B, 3, H * s, W * s), device=dev, dtype=f32)
+        nv.upfinish_fwd(up, x, out, s)
+        S["up"] = up
+        return out, (S if need_bwd else None)
+
+    def _run_backward(self, S, dout: Tensor, P: Dict[str, Tensor], G: Dict[str, Tensor]) -> None:
+        nv, eng = _ops.nv, self.conv_engine
+        x, adt, training = S["x"], S["adt"], S["training"]
+        B, _, H, W = x.shape
+        C, s, dev, f32 = self.C, self.scale_factor, x.device, torch.float32
+        ncs = 3 * s * s
+
+        def act(c, dtype=adt):
+            return torch.empty((B, H, W, c), device=dev, dtype=dtype)
+
+        dup = act(ncs, f32)
+        nv.upfinish_bwd(S["up"], x, dout, dup, s)
+        dup_a = torch.zeros((B, H, W, (ncs + 15) // 16 * 16), device=dev, dtype=adt)
+        nv.axpy(dup, dup_a[..., :ncs], 1.0, False)
+        last = S["act"][3]
+        nv.conv2d_wgrad(last, dup_a[..., :ncs], G["net.6.weight"], G["net.6.bias"], 1.0, eng)
+        dy = act(C)
+        wb = self._pack(P["net.6.weight"], adt, True, C, dup_a.shape[-1])
+        nv.conv2d_fwd(dup_a, wb, None, None, None, None, dy, C, 0, False, 0, 0, 1.0, eng)
+        for j in reversed(range(4)):
+            pre = f"net.{2 + j}."
+            gamma, beta = P[pre + "bn.weight"], P[pre + "bn.bias"]
+            bsums = torch.zeros((1, C, 2), device=dev, dtype=torch.float64)
+            nv.bn_relu_bwd_reduce(S["pwo"][j], dy, S["stat"][j], gamma, beta, 1, bsums)
+            s0 = act(C)
+            nv.bn_relu_bwd_apply(S["pwo"][j], dy, S["stat"][j], gamma, beta, bsums, s0, G[pre + "bn.weight"],
+                                 G[pre + "bn.bias"], 1, training)
+            nv.conv2d_wgrad(S["dwo"][j], s0, G[pre + "pointwise.weight"], None, 1.0, eng)
+            s1 = act(C)
+            nv.conv2d_fwd(s0, self._pack(P[pre + "pointwise.weight"], adt, True, C, C), None, None, None, None, s1, C, 0,
+                          False, 0, 0, 1.0, eng)
+            x_in = S["act"][j - 1] if j > 0 else S["head"]
+            nv.dwconv3x3_wgrad(x_in, s1, G[pre + "depthwise.weight"])
+            dy = act(C)
+            nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], dy, True, False)
+        t0 = act(C)
+        nv.relu_bwd(dy, S["head"], None, t0)
+        gw = G["net.0.weight"]
+        nv.conv2d_wgrad(S["x_in"][..., :27], t0, gw.view(C, 27, 1, 1), G["net.0.bias"], 1.0, eng)

@@ -191,7 +191,7 @@ def _pack_conv_weights_batched(w, dst, transpose_flip) -> None:
 # dense convolution
 # --------------------------------------------------------------------------------------------
 @_op("conv2d_fwd(Tensor x, Tensor w, Tensor? bias, Tensor? res, Tensor? mask, Tensor? mask_sub, "
-     "Tensor(a!) out, int cout, bool relu, bool accumulate, int res_channels, int mask_c0, float alpha, "
+     "Tensor(a!) out, int cout, int relu, bool accumulate, int res_channels, int mask_c0, float alpha, "
      "int engine, Tensor? x2=None, bool x2_center=False, Tensor(b!)? colsum=None) -> ()")
 def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, res_channels, mask_c0, alpha,
                 engine, x2=None, x2_center=False, colsum=None) -> None:
@@ -535,6 +535,86 @@ def _upfinish_bwd(conv_out, lr, dout, dconv, scale) -> None:
     lp, sn, sc, sh = _lr_view(lr)
     _lib.check(_lib.load().nervecl_upfinish_bwd(_flat(conv_out, "conv_out"), lp, sn, sc, sh, _flat(dout, "dout"),
                                                _flat(dconv, "dconv"), n, c, h, w, scale, _stream()), "upfinish_bwd")
+
+
+@_op("bicubic_blend(Tensor(a!) out, Tensor lr, int scale, float strength) -> ()")
+def _bicubic_blend(out, lr, scale, strength) -> None:
+    """out = strength * out + (1 - strength) * bicubic(lr) (``nervecl_bicubic_blend``)."""
+    n, c, h, w = lr.shape
+    lp, sn, sc, sh = _lr_view(lr)
+    if tuple(out.shape) != (n, c, h * scale, w * scale):
+        raise RuntimeError("nervecl.bicubic_blend: out must be (N,C,s*H,s*W)")
+    _lib.check(_lib.load().nervecl_bicubic_blend(_flat(out, "out"), lp, sn, sc, sh, n, c, h, w, scale, strength, _stream()),
+               "bicubic_blend")
+
+
+# --------------------------------------------------------------------------------------------
+# FrameRecoveryNet trunk
+# --------------------------------------------------------------------------------------------
+@_op("conv2d_direct(Tensor x, Tensor w, Tensor? bias, Tensor(a!) out, int stride, int pad, bool relu) -> ()")
+def _conv2d_direct(x, w, bias, out, stride, pad, relu) -> None:
+    """Strided direct convolution, OIHW fp32 weights (``nervecl_conv2d_direct``)."""
+    xp, ldx, n, h, wd, cin = _nhwc(x, "x")
+    op, ldo, on, oh, ow, oc = _nhwc(out, "out")
+    o, i, kh, kw = w.shape
+    if i != cin or o != oc or kh != kw or on != n:
+        raise RuntimeError("nervecl.conv2d_direct: weight / tensor shapes do not match")
+    if (oh, ow) != ((h + 2 * pad - kh) // stride + 1, (wd + 2 * pad - kh) // stride + 1):
+        raise RuntimeError("nervecl.conv2d_direct: out has the wrong spatial size")
+    _lib.check(_lib.load().nervecl_conv2d_direct(xp, ldx, _dt(x), _flat(w, "w"), _flat(bias, "bias") if bias is not None else None,
+                                                op, ldo, _dt(out), n, h, wd, cin, o, kh, stride, pad, int(relu), _stream()),
+               "conv2d_direct")
+
+
+@_op("maxpool2d(Tensor x, Tensor(a!) y, int k, int stride, int pad) -> ()")
+def _maxpool2d(x, y, k, stride, pad) -> None:
+    xp, ldx, n, h, w, c = _nhwc(x, "x")
+    yp, ldy, yn, oh, ow, yc = _nhwc(y, "y")
+    if (yn, yc) != (n, c) or (oh, ow) != ((h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1) or x.dtype != y.dtype:
+        raise RuntimeError("nervecl.maxpool2d: output shape / dtype mismatch")
+    _lib.check(_lib.load().nervecl_maxpool2d(xp, ldx, yp, ldy, _dt(x), n, h, w, c, k, stride, pad, _stream()), "maxpool2d")
+
+
+@_op("depth_to_space(Tensor x, Tensor(a!) y, int s) -> ()")
+def _depth_to_space(x, y, s) -> None:
+    xp, ldx, n, h, w, cs = _nhwc(x, "x")
+    yp, ldy, yn, oh, ow, c = _nhwc(y, "y")
+    if (yn, oh, ow) != (n, h * s, w * s) or cs != c * s * s or x.dtype != y.dtype:
+        raise RuntimeError("nervecl.depth_to_space: output shape / dtype mismatch")
+    _lib.check(_lib.load().nervecl_depth_to_space(xp, ldx, yp, ldy, _dt(x), n, h, w, c, s, _stream()), "depth_to_space")
+
+
+@_op("resize_bilinear(Tensor x, Tensor(a!) y) -> ()")
+def _resize_bilinear(x, y) -> None:
+    xp, ldx, n, h, w, c = _nhwc(x, "x")
+    yp, ldy, yn, oh, ow, yc = _nhwc(y, "y")
+    if (yn, yc) != (n, c) or x.dtype != y.dtype:
+        raise RuntimeError("nervecl.resize_bilinear: output shape / dtype mismatch")
+    _lib.check(_lib.load().nervecl_resize_bilinear(xp, ldx, yp, ldy, _dt(x), n, h, w, c, oh, ow, _stream()), "resize_bilinear")
+
+
+@_op("fusion_blend(Tensor aligned, Tensor logits, Tensor spatial, Tensor temporal, Tensor(a!) out) -> ()")
+def _fusion_blend(aligned, logits, spatial, temporal, out) -> None:
+    ap, lda, n, h, w, c = _nhwc(aligned, "aligned")
+    lp, ldl, *_ = _nhwc(logits, "logits")
+    sp, lds, _, _, _, cs = _nhwc(spatial, "spatial")
+    tp, ldt, _, _, _, ct = _nhwc(temporal, "temporal")
+    op, ldo, *_ = _nhwc(out, "out")
+    if logits.dtype != torch.float32 or logits.shape[-1] < 2:
+        raise RuntimeError("nervecl.fusion_blend: logits must be float32 [N,H,W,>=2]")
+    _lib.check(_lib.load().nervecl_fusion_blend(ap, lda, lp, ldl, sp, lds, cs, tp, ldt, ct, op, ldo, _dt(aligned), c, n * h * w,
+                                               _stream()), "fusion_blend")
+
+
+@_op("recovery_finish(Tensor conv_out, Tensor frame, Tensor? mask, Tensor(a!) out) -> ()")
+def _recovery_finish(conv_out, frame, mask, out) -> None:
+    cp, ldc, n, hd, wd, c = _nhwc(conv_out, "conv_out")
+    fn, fc, h, w = frame.shape
+    if conv_out.dtype != torch.float32 or (fn, fc) != (n, c) or out.shape != frame.shape:
+        raise RuntimeError("nervecl.recovery_finish: shape / dtype mismatch")
+    _lib.check(_lib.load().nervecl_recovery_finish(cp, ldc, hd, wd, _flat(frame, "frame"),
+                                                  _flat(mask, "mask") if mask is not None else None, _flat(out, "out"), n, c,
+                                                  h, w, _stream()), "recovery_finish")
 
 
 # --------------------------------------------------------------------------------------------

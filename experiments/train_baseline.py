@@ -74,6 +74,7 @@ def train(args):
             opt.step()
             loss_sum += loss.detach()                                     # no host sync inside the loop
         train_loss = float(loss_sum) / steps_per_epoch
+        nd.sync_buffers(model)       # validation / checkpoint use rank 0's BatchNorm statistics on every rank (DDP semantics)
         if rank == 0:
             model.eval()
             vl, vp, nb = 0.0, 0.0, 0

@@ -3,9 +3,14 @@
 `experiments/train_continual.py` flow (4 content-type tasks, Adam 1e-4, 5 epochs per task, EWC lambda 5000,
 online consolidation) with torchrun data parallelism.
 
+The model is the drop-in `EnhancementEngine` in the reference launcher's configuration (`frame_recovery_enabled=False`,
+train_continual.py:125-128); the loss is taken on `engine(frames)['enhanced']` and `EWC` / the optimiser see the
+engine's parameters under their `super_resolution.*` names.
+
 Deviation from the reference launcher, documented in SURVEY.md section 3.3: the reference registers a task by
 feeding raw 4-D batches to `EnhancementEngine`, which raises at the end of task 0; here the Fisher pass gets the
-same (B,T,C,H,W) windows the training loop uses and the bare SR network, i.e. what the reference intended.
+same (B,T,C,H,W) windows the training loop uses (through a thin module that returns `['enhanced']`), i.e. what the
+reference intended.
 
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 experiments/train_continual.py --strategy ewc
 """
@@ -79,20 +84,33 @@ def main():
     ap.add_argument("--epochs", type=int, default=5)
     ap.add_argument("--batch-size", type=int, default=16)
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--features", type=int, default=64)
+    ap.add_argument("--blocks", type=int, default=8)
     args = ap.parse_args()
 
     from nerve_cl_b200 import distributed as nd
     from nerve_cl_b200.continual import EWC
-    from nerve_cl_b200.models import SuperResolutionNet
+    from nerve_cl_b200.models import EnhancementConfig, EnhancementEngine
     from nerve_cl_b200.optim import FlatAdamW
     rank, local_rank, world, device = _common.setup_distributed()
     torch.manual_seed(0)
-    model = SuperResolutionNet(scale_factor=2).to(device)          # the engine's SR branch (64 feat, 8 blocks)
+    engine = EnhancementEngine(EnhancementConfig(frame_recovery_enabled=False, super_resolution_enabled=True,
+                                                 sr_num_features=args.features, sr_num_residual_blocks=args.blocks)).to(device)
+    model = engine.super_resolution                                 # the only trainable branch (64 feat, 8 blocks)
     model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     nd.data_parallel(model)
-    opt = FlatAdamW(model, lr=1e-4, weight_decay=0.0)              # Adam(lr=1e-4)
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=0.0)              # Adam(lr=1e-4); enhancement_strength never gets a gradient
     tasks = [(ct, create_task_data(ct, args.samples, args.size, 100 + i)) for i, ct in enumerate(OFFSETS)]
-    ewc = EWC(model, ewc_lambda=args.ewc_lambda) if args.strategy == "ewc" else None
+
+    class Enhanced(torch.nn.Module):                                # what EWC differentiates: engine(x)['enhanced']
+        def __init__(self, eng):
+            super().__init__()
+            self.engine = eng
+
+        def forward(self, x):
+            return self.engine(x)["enhanced"]
+
+    ewc = EWC(Enhanced(engine), ewc_lambda=args.ewc_lambda) if args.strategy == "ewc" else None
     if ewc is not None and world > 1:
         ewc.process_group = torch.distributed.group.WORLD      # Fisher: local sum of g^2, then one all-reduce
     memory = ReplayBuffer(args.memory_size, 7 + rank) if args.strategy == "replay" else None
@@ -101,7 +119,7 @@ def main():
         _common.log(rank, f"\n=== Training on Task {task_id}: {name} ===")
         loader = WindowLoader(lr, hr, _common.shard(len(lr), rank, world), args.batch_size, device, task_id)
         for epoch in range(args.epochs):
-            model.train()
+            engine.train()
             total = torch.zeros((), device=device)
             steps = 0
             for lr_w, hr_b in loader:
@@ -110,7 +128,7 @@ def main():
                     lr_w = torch.cat([lr_w, r_lr.unsqueeze(1).expand(-1, 3, -1, -1, -1)])
                     hr_b = torch.cat([hr_b, r_hr])
                 opt.zero_grad()
-                loss = torch.nn.functional.mse_loss(model(lr_w), hr_b)
+                loss = torch.nn.functional.mse_loss(engine(lr_w)["enhanced"], hr_b)
                 if ewc is not None:
                     loss = loss + ewc.penalty()          # Python 0.0 before the first task, as in the reference
                 loss.backward()
@@ -127,9 +145,10 @@ def main():
             for i in list(_common.shard(len(lr), rank, world))[:50]:
                 memory.store(lr[i], hr[i])
             _common.log(rank, f"  Memory size: {len(memory)}")
+    nd.sync_buffers(engine)                               # rank 0's BatchNorm statistics everywhere, like DDP's buffer broadcast
     if rank == 0:
         Path("checkpoints").mkdir(exist_ok=True)
-        torch.save(model.state_dict(), "checkpoints/continual_model.pt")
+        torch.save(engine.state_dict(), "checkpoints/continual_model.pt")
     _common.log(rank, "\nTraining complete!")
 
 

@@ -116,10 +116,11 @@ int nervecl_pack_conv_weights_batched(int n, const float* const* w_host, void* c
  *
  *   v = sum_taps sum_ci x[p+tap, ci] * w[tap, co, ci]   (+ sum over the x2 channels when x2 != NULL)
  *   v += bias[co]                      (bias != NULL)
- *   v  = max(v, 0)                     (relu)
+ *   v  = max(v, 0)                     (relu == 1)
  *   v *= alpha
  *   v += res[p, co]                    (res != NULL and co < res_channels)
  *   v += out[p, co]                    (accumulate)
+ *   v  = max(v, 0)                     (relu == 2: ReLU after the residual, efficient_layers.py:148-150)
  *   v  = 0 if mask[p, co] - (mask_sub ? mask_sub[p, co] : 0) <= 0   (mask != NULL and co >= mask_c0)
  *   out[p, co] = v
  * ---------------------------------------------------------------------------------------- */
@@ -318,6 +319,45 @@ int nervecl_upfinish_fwd(const float* conv_out, const float* lr, int64_t sN, int
 int nervecl_upfinish_bwd(const float* conv_out, const float* lr, int64_t sN, int64_t sC,
                          int64_t sH, const float* dout, float* dconv, int N, int C, int H, int W,
                          int s, nervecl_stream_t stream);
+
+/* out (N,C,sH,sW fp32, in place) = strength * out + (1 - strength) * bicubic(lr)  -- the EnhancementEngine's
+ * strength blend, nerve_cl/models/enhancement_engine.py:172-182 (ATen bicubic, A = -0.75, align_corners=False);
+ * lr is (N,C,H,W) fp32 with element strides sN, sC, sH and unit column stride. */
+int nervecl_bicubic_blend(float* out, const float* lr, int64_t sN, int64_t sC, int64_t sH, int N, int C,
+                          int H, int W, int s, float strength, nervecl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FrameRecoveryNet trunk (nerve_cl/models/frame_recovery.py), inference path.  Its stride-1 3x3 / 1x1
+ * convolutions (94 % of the FLOPs: TemporalConv3D's (1,3,3) spatial and (3,1,1) temporal convs,
+ * efficient_layers.py:231-294, the pointwise convs of ResidualBlock :109-151, FusionModule.align, and
+ * ConvTranspose2d(4,2,1) rewritten as a 3x3 conv with 4*Cout outputs) run through nervecl_conv2d_fwd with
+ * the eval-mode BatchNorm folded into weights and bias; the entry points below are the rest.
+ * ---------------------------------------------------------------------------------------- */
+/* Direct convolution with stride / padding, OIHW fp32 weights read as they are (no packing), + bias, ReLU:
+ * the encoder stem Conv2d(4,64,7,2,3) + folded BN + ReLU (frame_recovery.py:43-47) and the 1x1 stride-2
+ * shortcuts of SpatialEncoder._make_stage (:70-74).  out is [N][OH][OW][ldo], OH = (H + 2 pad - K)/stride + 1. */
+int nervecl_conv2d_direct(const void* x, int64_t ldx, int dtype, const float* w_oihw, const float* bias,
+                          void* out, int64_t ldo, int out_dtype, int N, int H, int W, int Cin, int Cout,
+                          int K, int stride, int pad, int relu, nervecl_stream_t stream);
+/* nn.MaxPool2d(k, stride, pad) (frame_recovery.py:47) and F.max_pool3d(x, (1,2,2)) (:150,153) over NHWC frames */
+int nervecl_maxpool2d(const void* x, int64_t ldx, void* y, int64_t ldy, int dtype, int N, int H, int W,
+                      int C, int k, int stride, int pad, nervecl_stream_t stream);
+/* y[n][s*h+i][s*w+j][c] = x[n][h][w][(i*s+j)*C + c]: second half of ConvTranspose2d(4,2,1) (:281-303) */
+int nervecl_depth_to_space(const void* x, int64_t ldx, void* y, int64_t ldy, int dtype, int N, int H, int W,
+                           int C, int s, nervecl_stream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=False) to (OH, OW) (frame_recovery.py:224-230) */
+int nervecl_resize_bilinear(const void* x, int64_t ldx, void* y, int64_t ldy, int dtype, int N, int H, int W,
+                            int C, int OH, int OW, nervecl_stream_t stream);
+/* FusionModule (:232-256): a = softmax(logits[p][0:2]); out[p][c] = aligned[p][c] + a0 * mean_c spatial[p] +
+ * a1 * mean_c temporal[p]  (the two all-ones/C 1x1 convolutions of :243-250 are channel means). */
+int nervecl_fusion_blend(const void* aligned, int64_t lda, const float* logits, int64_t ldl,
+                         const void* spatial, int64_t lds, int Cs, const void* temporal, int64_t ldt, int Ct,
+                         void* out, int64_t ldo, int dtype, int C, int64_t npix, nervecl_stream_t stream);
+/* Tail (:425-442): recovered = tanh(conv_out [N][Hd][Wd][ldc] fp32), bilinearly resized to (H, W) when the sizes
+ * differ; out = frame * (1 - mask) + recovered * mask.  frame / out (N,C,H,W) fp32, mask (N,1,H,W) fp32 or NULL. */
+int nervecl_recovery_finish(const float* conv_out, int64_t ldc, int Hd, int Wd, const float* frame,
+                            const float* mask, float* out, int N, int C, int H, int W,
+                            nervecl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise helpers (gradient routing that autograd does implicitly in the reference)
