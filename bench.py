@@ -373,7 +373,10 @@ def run_native(args):
             barrier()
             wall = (time.perf_counter() - t0) * 1e3
             dev_ms = e0.elapsed_time(e1)
-            if abs(wall - dev_ms) <= 0.05 * wall + 2.0:
+            bad = torch.tensor([0.0 if abs(wall - dev_ms) <= 0.05 * wall + 2.0 else 1.0], device=dev)
+            if world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX)       # every rank takes the same decision (collectives must pair)
+            if float(bad.item()) == 0.0:
                 break
             timing_notes.append({"attempt": attempt, "event_ms": dev_ms, "wall_ms": wall})
         ms = torch.tensor([dev_ms], device=dev)
