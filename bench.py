@@ -566,6 +566,7 @@ def run_native(args):
     eager = None if args.no_gpu_eager else gpu_eager(dev, args)
     pk = peaks()
     hbm_peak = pk.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
+    peak = pk.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
 
     # ---- bandwidth-bound kernels against the measured HBM copy bandwidth --------------------------------
     # (a) from the per-launch CUDA-event spans of the timed steps: algorithmic bytes per LR pixel (SURVEY.md 8d,
@@ -627,6 +628,20 @@ def run_native(args):
     conv_launches = sum(d["launches"] for k, d in ksum.items() if k.startswith("conv"))
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+    # Which roofline binds each conv launch?  Per shape: t_tensor = algorithmic FLOPs / measured bf16 peak, t_hbm =
+    # algorithmic bytes (input + output channels of the launch, bf16) / measured copy bandwidth; the launch cannot
+    # finish before max(t_tensor, t_hbm).  Many launches of this network are 1x1 or narrow convolutions whose
+    # t_hbm exceeds t_tensor, so the family's distance to the TENSOR roofline alone overstates the headroom.
+    bind_ms, hbm_bound_ms, hbm_bound_launch_ms = 0.0, 0.0, 0.0
+    for k, d in kdetail.items():
+        if not k.startswith("conv") or d["ms"] <= 0:
+            continue
+        t_t = d["flops"] / (peak * 1e12) * 1e3
+        t_h = d["bytes"] / (hbm_peak * 1e9) * 1e3
+        bind_ms += max(t_t, t_h)
+        if t_h > t_t:
+            hbm_bound_ms += t_h
+            hbm_bound_launch_ms += d["ms"]
     # DRAM bytes per conv-family launch from the committed ncu pass (profiles/conv_traffic.json, written by
     # scripts/summarize_profile.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one step)
     traffic, traffic_src = None, None
@@ -653,6 +668,10 @@ def run_native(args):
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['_source']})",
             "launches_timed": conv_launches, "avg_launch_ms": conv_ms / max(conv_launches, 1),
             "share_of_step": conv_ms / ms_spans if ms_spans else None,
+            "binding": {"note": "sum over launches of max(algorithmic FLOPs / bf16 peak, algorithmic bytes / HBM peak) / measured time",
+                        "frac": bind_ms / conv_ms if conv_ms else None, "lower_bound_ms_per_step": bind_ms / args.steps,
+                        "measured_ms_per_step": conv_ms / args.steps,
+                        "hbm_bound_share_of_conv_time": hbm_bound_launch_ms / conv_ms if conv_ms else None},
             "span_pass_ms_per_step": ms_spans / args.steps,
             "by_kind": {k: {"launches": d["launches"], "ms": round(d["ms"], 3),
                             "tflops": d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0}

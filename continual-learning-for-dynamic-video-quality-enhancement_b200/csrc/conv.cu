@@ -24,17 +24,24 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   int engine = p->engine;
-  if (p->x2) {                                   // second input: row-streaming engine only
+  const bool pair_ok = engine != NERVECL_CONV_TC_ROWS1;      // (ROWS1: the 1-CTA row kernel, for A/B comparisons and tests)
+  if (engine == NERVECL_CONV_TC_ROWS1) engine = NERVECL_CONV_TC;
+  if (p->x2) {                                   // second input: row-streaming engines only
     if (p->Cin2 <= 0 || p->ldx2 < p->Cin2) return NERVECL_EINVAL;
-    if ((engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) || !conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
+    if (engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) return NERVECL_EUNSUPPORTED;
+    if (pair_ok && conv_rows2_supported(*p)) return conv_rows2_fwd(*p, s);
+    if (!conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
     return conv_rows_fwd(*p, s);
   }
-  if (p->colsum) {                               // fused column sums: row-streaming engine only
-    if ((engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) || !conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
+  if (p->colsum) {                               // fused column sums: row-streaming engines only
+    if (engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) return NERVECL_EUNSUPPORTED;
+    if (pair_ok && conv_rows2_supported(*p)) return conv_rows2_fwd(*p, s);
+    if (!conv_rows_supported(*p)) return NERVECL_EUNSUPPORTED;
     return conv_rows_fwd(*p, s);
   }
   if (engine == NERVECL_CONV_AUTO) engine = conv_tc_fwd_supported(*p) ? NERVECL_CONV_TC : NERVECL_CONV_SIMT;
   if (engine == NERVECL_CONV_TC) {               // best tcgen05 kernel for the shape
+    if (pair_ok && conv_rows2_supported(*p)) return conv_rows2_fwd(*p, s);
     // (1x1: the row kernel wins while the per-row MMA count stays small; wide inputs are at the HBM roofline
     //  with the per-tap kernel already)
     static const int k1_max_cin = nv::tune_env("NERVECL_ROWS_K1_MAXCIN") ? atoi(nv::tune_env("NERVECL_ROWS_K1_MAXCIN")) : 128;

@@ -22,6 +22,9 @@ int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s);
 // row-streaming 3x3 tcgen05 kernel (conv_tc_rows.cu)
 bool conv_rows_supported(const nervecl_conv_params& a);
 int conv_rows_fwd(const nervecl_conv_params& a, cudaStream_t s);
+// CTA-pair (cta_group::2) row-streaming 3x3 kernel for bf16 outputs with a lean epilogue (conv_tc_rows2.cu)
+bool conv_rows2_supported(const nervecl_conv_params& a);
+int conv_rows2_fwd(const nervecl_conv_params& a, cudaStream_t s);
 bool conv_tc_wgrad_supported(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H,
                              int W, int Cin, int Cout, int K);
 int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float* dw, float* db, int N, int H,

@@ -29,7 +29,7 @@ constexpr int PW = 80;               // pixels of a ring row including the zero 
 constexpr int ROWCH = PW * 8;        // 16-byte chunks per ring row (gradient kernel)
 constexpr int ROWCH_F = PWU * 8;     // forward kernel: no pad needed (k < 24)
 constexpr int RING = 9;
-constexpr int NT = 128;
+constexpr int NT = 256;                // forward: 8 warps = 4 pixel groups x 2 halves of the vertical displacements
 // Staged gradient row G[px][i][j] (gradient kernels): 10 half-words per vertical displacement i (9 + 1 unused)
 // and an ODD pixel pitch, so that the two band entries (j0, j0+1) an A-fragment register needs are ALWAYS one
 // aligned 32-bit word: (px*GP + i*GS + k - px) has the parity of k = 2*tig + {0,8,16,24}.  Entries outside the
@@ -99,7 +99,8 @@ corr_fwd_mma_kernel(const bf16* __restrict__ x1, int64_t ld1, const bf16* __rest
   const int strip = item % strips;
   const int n = item / strips;
   const int x0 = strip * TW, y0 = seg * TH, y1 = min(H, y0 + TH);
-  const int px0 = warp * 16;                                          // this warp's pixels within the strip
+  const int px0 = (warp & 3) * 16;                                    // this warp's pixels within the strip
+  const int i_lo = (warp >> 2) ? 5 : 0, i_hi = (warp >> 2) ? ND : 5;  // ... and its vertical displacements
 
   zero_ring<ROWCH_F>(ring);
   for (int e = t; e < TW * cout_pad; e += NT) stage[e] = __float2bfloat16_rn(0.f);   // pad channels stay zero
@@ -133,7 +134,7 @@ corr_fwd_mma_kernel(const bf16* __restrict__ x1, int64_t ld1, const bf16* __rest
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) ldsm4(af[ks], x1row + swz(a_px, 2 * ks + a_ch));
 #pragma unroll 1
-    for (int i = 0; i < ND; ++i) {
+    for (int i = i_lo; i < i_hi; ++i) {
       const int yy = y + i - RAD;
       const uint4* row = ring + (((yy % RING) + RING) % RING) * ROWCH_F;
       float acc[3][4];
@@ -192,11 +193,12 @@ corr_fwd_mma_kernel(const bf16* __restrict__ x1, int64_t ld1, const bf16* __rest
 // gradient gather:  dx[p, c] (+)= (1/C) sum_{i,j} G[p, i*9+j] * X[p + (i-4, j-4), c]
 // MODE 0: G[p,d] = g[p,d].   MODE 1: G[p,(i,j)] = g[p + (i-4, j-4), (8-i)*9 + (8-j)]  (zero outside the image).
 // ---------------------------------------------------------------------------------------
-// Threads 0..127 (4 warps) run the MMAs of output row y; threads 128..255 stage everything row y+1 needs while
+// Threads 0..255 (8 warps = 4 pixel groups x 2 halves of the 64 output channels) run the MMAs of output row y;
+// threads 256..383 stage everything row y+1 needs while
 // they do: the next X row into registers (installed in the ring slot row y-4 frees) and the next G row straight
 // into the other half of a double-buffered G (all of a loader thread's global loads are issued before its first
 // store, so one row costs ~one memory latency, hidden behind the MMAs).
-constexpr int GNT = 256;
+constexpr int GNT = 384, GMMA = 256;
 constexpr int GQ = (ND * PWU + 127) / 128;        // (i, source pixel) items per loader thread in MODE 1 (6)
 constexpr int GV = (TW * 11 + 127) / 128;         // 16-byte chunks per loader thread in MODE 0 (6)
 constexpr int GXP = (PWU * 8 + 127) / 128;        // X-row chunks per loader thread (5)
@@ -318,8 +320,9 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
   bf16* Gbuf = reinterpret_cast<bf16*>(ring + RING * ROWCH_F);       // [2][GBUF]: staged gradient rows (see GS / GP)
   constexpr int OP = 32 + 4;                                         // fp32 output staging pitch (aliases the G in use)
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool loader = t >= 128;
-  const int lt = t & 127;
+  const bool loader = t >= GMMA;
+  const int lt = t - GMMA;                                           // loader thread index (0..127)
+  const int chalf = (warp >> 2) & 1;                                 // MMA warps: which 32 output channels
   const int gid = lane >> 2, tig = lane & 3;
   int item = blockIdx.x;
   const int seg = item % segs; item /= segs;
@@ -369,9 +372,9 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
         stage_G<MODE>(Gbuf + ((y + 1) & 1) * GBUF, g, ldg, n, y + 1, x0, H, W, lt, vec_g);
       }
     } else {
-      float acc[8][4];
+      float acc[4][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
       const uint8_t* Gb = reinterpret_cast<const uint8_t*>(G);
@@ -390,30 +393,32 @@ corr_grad_mma_kernel(const bf16* __restrict__ X, int64_t ldX, const bf16* __rest
           // row instead of padding it: the operand only has to be finite
           const int kpx = min(px0 + ks * 16 + b_k, PWU - 1);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {                               // n-tiles 2q, 2q+1
+          for (int q = 0; q < 2; ++q) {                               // this warp's n-tiles 2q, 2q+1 (of its channel half)
             uint32_t bf[4];
-            ldsm4_t(bf, row + swz(kpx, 2 * q + b_ch));
+            ldsm4_t(bf, row + swz(kpx, 2 * (2 * chalf + q) + b_ch));
             mma16816(acc[2 * q], af, bf[0], bf[1]);
             mma16816(acc[2 * q + 1], af, bf[2], bf[3]);
           }
         }
       }
-      // stage the 16 x 64 result of every warp (two halves of 32 channels, over this row's G), then one coalesced
-      // (read-modify-)write per half; only the 4 MMA warps take part (named barrier 1)
+      // stage the 16 x 32 results of the four warps of one channel half (over this row's G), then one coalesced
+      // (read-modify-)write of that half by all 256 MMA threads; only the MMA warps take part (named barrier 1)
       float* ost = reinterpret_cast<float*>(G);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (chalf == half) {
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+          for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r = gid + (q >> 1) * 8, c = nt * 8 + 2 * tig + (q & 1);
-            ost[(px0 + r) * OP + c] = acc[half * 4 + nt][q] * inv_c;
-          }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int e = lt; e < TW * 4; e += 128) {
-          const int px = e >> 2, ch = e & 3;
+            for (int q = 0; q < 4; ++q) {
+              const int r = gid + (q >> 1) * 8, c = nt * 8 + 2 * tig + (q & 1);
+              ost[(px0 + r) * OP + c] = acc[nt][q] * inv_c;
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        {
+          const int px = t >> 2, ch = t & 3;                            // TW * 4 = 256 items: one per MMA thread
           const int x = x0 + px;
           if (x < W) {
             bf16* dp = dx + (((int64_t)n * H + y) * W + x) * lddx + 32 * half + 8 * ch;

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnervecl.so")
 
 F32, BF16 = 0, 1
-CONV_AUTO, CONV_SIMT, CONV_TC, CONV_TC_TAPS = 0, 1, 2, 3
+CONV_AUTO, CONV_SIMT, CONV_TC, CONV_TC_TAPS, CONV_TC_ROWS1 = 0, 1, 2, 3, 4
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 

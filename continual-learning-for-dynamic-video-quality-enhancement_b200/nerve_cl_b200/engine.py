@@ -288,11 +288,12 @@ class Plan:
         return self.timer.span(f"{kind}|{cin}>{cout}k{k}", 2.0 * npix * cin * cout * k * k,
                                float(npix) * (cin + cout) * x.element_size())
 
-    def _span_flops(self, kind: str, x: Tensor, flops_per_px: float):
+    def _span_flops(self, kind: str, x: Tensor, flops_per_px: float, channels_moved: int = 0):
+        """``channels_moved``: activation channels read + written per pixel (algorithmic bytes = that x element size)."""
         if self.timer is None:
             return _NOSPAN
         npix = x.shape[0] * x.shape[1] * x.shape[2]
-        return self.timer.span(kind, flops_per_px * npix, 0.0)
+        return self.timer.span(kind, flops_per_px * npix, float(npix) * channels_moved * x.element_size())
 
     def conv(self, name: str, x: Tensor, out: Tensor, P, *, relu=False, res=None, res_channels=0, alpha=1.0,
              bias=True) -> None:
@@ -516,14 +517,17 @@ class Plan:
             x_lo = F + (0 if s == 0 else s) * GROWTH          # first channel of the later layers' gradients
             w = self.wslice[s][:, k * rows:(k + 1) * rows, :]
             mask = buf[..., c_lo:c_lo + rows] if s > 0 else None
-            with self._span_flops(f"conv_dgrad|slice{s}", buf, 2.0 * rows * (9 * (CT - x_lo) + F)):
+            # bytes: later layers' gradients + the block gradient (1x1 branch; + once more as the x slice's residual) in,
+            # the slice's ReLU mask in (s > 0), the slice out
+            moved = (CT - x_lo) + F + (F if s == 0 else rows) + rows
+            with self._span_flops(f"conv_dgrad|slice{s}", buf, 2.0 * rows * (9 * (CT - x_lo) + F), moved):
                 # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
                 nv.conv2d_fwd(g[..., x_lo:CT], w, None, dblock if s == 0 else None, mask, None,
                               g[..., c_lo:c_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,
                               dblock, True, G[names[s - 1] + ".bias"] if s > 0 else None)
         cx = F + (RDB_LAYERS - 1) * GROWTH
         with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
-                                                                for i in range(RDB_LAYERS))):
+                                                                for i in range(RDB_LAYERS)), cx + RDB_LAYERS * GROWTH):
             nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names], [],
                                      [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
 

@@ -17,7 +17,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BF16, CONV_AUTO, CONV_SIMT, CONV_TC, CONV_TC_TAPS, F32, ConvParams  # noqa: F401
+from ._lib import BF16, CONV_AUTO, CONV_SIMT, CONV_TC, CONV_TC_ROWS1, CONV_TC_TAPS, F32, ConvParams  # noqa: F401
 
 Tensor = torch.Tensor
 

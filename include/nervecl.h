@@ -46,9 +46,11 @@ enum {
 enum {
   NERVECL_CONV_AUTO = 0, /* tcgen05 when the shape qualifies, else SIMT */
   NERVECL_CONV_SIMT = 1, /* fp32-accumulate CUDA-core direct conv (any shape, f32 or bf16) */
-  NERVECL_CONV_TC = 2,   /* tcgen05/TMEM/TMA implicit GEMM (bf16, Cin%8==0, Cout <= 256): the row-streaming
-                            kernel for 3x3 / Cin%16==0 / W>=64, else the per-tap kernel */
-  NERVECL_CONV_TC_TAPS = 3 /* force the per-tap tcgen05 kernel */
+  NERVECL_CONV_TC = 2,   /* tcgen05/TMEM/TMA implicit GEMM (bf16, Cin%8==0, Cout <= 256): the CTA-pair row-streaming
+                            kernel for 3x3 / bf16 out / lean epilogue, the 1-CTA row kernel for other 3x3 / narrow
+                            1x1 with Cin%16==0 and W>=64, else the per-tap kernel */
+  NERVECL_CONV_TC_TAPS = 3, /* force the per-tap tcgen05 kernel */
+  NERVECL_CONV_TC_ROWS1 = 4 /* like TC, but never the CTA-pair (cta_group::2) row kernel: A/B comparisons */
 };
 
 int nervecl_abi_version(void);

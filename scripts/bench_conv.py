@@ -70,6 +70,19 @@ if __name__ == "__main__":
         fwd_case(192, 64, 3, 192, 64, engines)
         fwd_case(64, 64, 3, 64, 64, engines)
         fwd_case(224, 64, 1, 224, 64, engines)
+    if which == "pair":
+        # CTA-pair (cta_group::2) row kernel vs the 1-CTA row kernel on the dense-block / flow / attention shapes
+        print("engines: pair (auto) | rows1")
+        eng2 = [ops.CONV_TC, ops.CONV_TC_ROWS1]
+        for cin in (64, 96, 128, 160, 192):
+            fwd_case(cin, 32, 3, 256, 256, eng2)
+        for cin in (32, 64, 96, 128):
+            fwd_case(cin, 32, 3, 256, 256, eng2, mask=True)
+        fwd_case(160, 64, 3, 256, 256, eng2)
+        fwd_case(96, 128, 3, 96, 128, eng2)
+        fwd_case(128, 64, 3, 128, 64, eng2)
+        fwd_case(192, 64, 3, 192, 64, eng2)
+        fwd_case(64, 64, 3, 64, 64, eng2)
     if which == "layout":
         # same conv, input/output pixel pitch 64/32 (contiguous pixels) vs 256 (channel slices of a wide buffer)
         for cin in (64, 128, 192):
