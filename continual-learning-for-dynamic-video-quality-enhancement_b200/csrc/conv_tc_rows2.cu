@@ -98,6 +98,9 @@ __device__ __forceinline__ void unpack8(const uint4& a, const uint4& b, float (&
   }
 }
 
+// NC = 16-channel chunks per epilogue thread (1: NOUT <= 32, 2: NOUT <= 64, 3: NOUT <= 80): a compile-time bound keeps
+// the single-chunk epilogue of the dense-block launches small enough for a three-row operand prefetch queue.
+template <int NC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                   const __grid_constant__ CUtensorMap tmap_w, const Pair2Args a) {
@@ -306,10 +309,10 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (rank == 0) mbar_arrive(&acc_empty[sl]); else mbar_arrive_cluster(empty0 + 8u * sl);
       }
 
-    bool has[3];
-    int ch[3];
+    bool has[NC];
+    int ch[NC];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NC; ++i) {
       has[i] = part + 2 * i < nch_all;
       ch[i] = c_lo + (part + 2 * i) * 16;
     }
@@ -347,11 +350,17 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const bf16* ep = has_e ? a.eop + p0 * a.ldeop : nullptr;
       const int64_t estride = (int64_t)a.W * a.ldeop;
       // first operand row in flight before anything is waited on
-      uint4 pre[3][2];
+      uint4 pre[NC][2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < NC; ++i) {
         pre[i][0] = pre[i][1] = make_uint4(0, 0, 0, 0);
         if (has_e && valid && has[i]) load32B(ep + ch[i], pre[i][0], pre[i][1], vi);
+      }
+      uint4 q1[2], q2[2];                           // NC == 1: rows oi + 1 and oi + 2 of the operand are in flight as well
+      q1[0] = q1[1] = q2[0] = q2[1] = make_uint4(0, 0, 0, 0);
+      if (NC == 1 && has_e && valid && has[0]) {
+        if (rows > 1) load32B(ep + estride + ch[0], q1[0], q1[1], vi);
+        if (rows > 2) load32B(ep + 2 * estride + ch[0], q2[0], q2[1], vi);
       }
       // the two gap slots in front of the item: drained and re-zeroed, nothing stored
       for (int gslot = 0; gslot < 2; ++gslot) {
@@ -359,7 +368,7 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tc_fence_after();
         const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT);
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < NC; ++i)
           if (has[i]) {
             tmem_st16_zero(tcol + (uint32_t)((part + 2 * i) * 16));
             if (slot < 2) tmem_st16_zero(tcol + mirror + (uint32_t)((part + 2 * i) * 16));
@@ -367,26 +376,30 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         release();
       }
       for (int oi = 0; oi < rows; ++oi) {
-        uint4 cur[3][2];
+        uint4 cur[NC][2];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { cur[i][0] = pre[i][0]; cur[i][1] = pre[i][1]; }
-        if (has_e && valid && oi + 1 < rows) {
+        for (int i = 0; i < NC; ++i) { cur[i][0] = pre[i][0]; cur[i][1] = pre[i][1]; }
+        if (NC == 1) {
+          pre[0][0] = q1[0]; pre[0][1] = q1[1];
+          q1[0] = q2[0]; q1[1] = q2[1];
+          if (has_e && valid && has[0] && oi + 3 < rows) load32B(ep + (int64_t)(oi + 3) * estride + ch[0], q2[0], q2[1], vi);
+        } else if (has_e && valid && oi + 1 < rows) {
           const bf16* en = ep + (int64_t)(oi + 1) * estride;
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+          for (int i = 0; i < NC; ++i)
             if (has[i]) load32B(en + ch[i], pre[i][0], pre[i][1], vi);
         }
         mbar_wait(&acc_full[slot], par);
         tc_fence_after();
         const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT);
-        uint32_t v[3][16];
+        uint32_t v[NC][16];
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < NC; ++i)
           if (has[i]) tmem_ld16(tcol + (uint32_t)((part + 2 * i) * 16), v[i]);
         tmem_ld_wait();
         if (slot < 2) {                               // this output row's first taps were written to the mirror slot
 #pragma unroll 1
-          for (int i = 0; i < 3; ++i)                 // (two rows per lap of the ring: one chunk at a time, few registers)
+          for (int i = 0; i < NC; ++i)                 // (two rows per lap of the ring: one chunk at a time, few registers)
             if (has[i]) {
               uint32_t m[16];
               tmem_ld16(tcol + mirror + (uint32_t)((part + 2 * i) * 16), m);
@@ -396,17 +409,17 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               for (int j = 0; j < 16; ++j) {
                 const float t = __uint_as_float(m[j]);
                 if (i == 0) v[0][j] = __float_as_uint(__uint_as_float(v[0][j]) + t);
-                else if (i == 1) v[1][j] = __float_as_uint(__uint_as_float(v[1][j]) + t);
-                else v[2][j] = __float_as_uint(__uint_as_float(v[2][j]) + t);
+                else if (NC > 1 && i == 1) v[NC > 1 ? 1 : 0][j] = __float_as_uint(__uint_as_float(v[NC > 1 ? 1 : 0][j]) + t);
+                else if (NC > 2) v[NC > 2 ? 2 : 0][j] = __float_as_uint(__uint_as_float(v[NC > 2 ? 2 : 0][j]) + t);
               }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < NC; ++i)
           if (has[i]) tmem_st16_zero(tcol + (uint32_t)((part + 2 * i) * 16));
         if (valid) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
+          for (int i = 0; i < NC; ++i) {
             if (!has[i]) continue;
             float f[16], e[16];
             if (has_e) unpack8(cur[i][0], cur[i][1], e);
@@ -599,9 +612,16 @@ int conv_rows2_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   t.ksteps2_last = p.ksteps2_last; t.x2_center = a.x2 ? a.x2_center : 0;
   t.strips = p.strips; t.cps = p.cps; t.stages = p.stages; t.slots = p.slots; t.R = p.R;
 
-  cudaError_t e = cudaFuncSetAttribute(conv_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e != cudaSuccess) return (int)e;
-  conv_rows2_kernel<<<dim3((unsigned)(2 * p.pairs), (unsigned)p.nsplit, 1), kThreads, p.smem, s>>>(tx, tx2, tw, t);
+  const dim3 grid((unsigned)(2 * p.pairs), (unsigned)p.nsplit, 1);
+  cudaError_t e = cudaSuccess;
+#define NV_LAUNCH_PAIR(NCV)                                                                                          \
+  do {                                                                                                               \
+    e = cudaFuncSetAttribute(conv_rows2_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);       \
+    if (e != cudaSuccess) return (int)e;                                                                             \
+    conv_rows2_kernel<NCV><<<grid, kThreads, p.smem, s>>>(tx, tx2, tw, t);                                            \
+  } while (0)
+  if (p.NOUT <= 32) NV_LAUNCH_PAIR(1); else if (p.NOUT <= 64) NV_LAUNCH_PAIR(2); else NV_LAUNCH_PAIR(3);
+#undef NV_LAUNCH_PAIR
   return launch_status();
 }
 
