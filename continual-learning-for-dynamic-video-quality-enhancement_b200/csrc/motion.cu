@@ -5,6 +5,11 @@
 using namespace nv;
 
 namespace nv {   // motion_mma.cu
+// tcgen05 2-D tile Gram kernel (motion_tc.cu)
+bool corr_fwd_tc_supported(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* out, int64_t ldo, int H, int W,
+                           int cout_pad);
+int corr_fwd_tc(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* out, int64_t ldo, int N, int H, int W,
+                int cout_pad, cudaStream_t s);
 int corr_fwd_mma(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* out, int64_t ldo, int N, int H, int W,
                  int cout_pad, cudaStream_t s);
 int corr_bwd_mma(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* g, int64_t ldg, void* dx1,
@@ -341,6 +346,9 @@ NV_API int nervecl_corr_fwd(const void* x1, int64_t ld1, const void* x2, int64_t
   if (!x1 || !x2 || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if (cout_pad < NDISP || ldo < cout_pad) return NERVECL_EINVAL;
   if ((C & 7) || (ld1 & 7) || (ld2 & 7) || !aligned(x1, 16) || !aligned(x2, 16)) return NERVECL_EALIGN;
+  if (dtype == NERVECL_BF16 && C == 64 && !nv::tune_env("NERVECL_CORR_MMA") &&
+      corr_fwd_tc_supported(x1, ld1, x2, ld2, out, ldo, H, W, cout_pad))
+    return corr_fwd_tc(x1, ld1, x2, ld2, out, ldo, N, H, W, cout_pad, as_stream(stream));
   if (corr_tiled_supported(dtype, C, ld1, ld2, x1, x2) && !(cout_pad & 7) && !(ldo & 7) && aligned(out, 16) && cout_pad <= 128)
     return (nv::tune_env("NERVECL_CORR_SIMT") ? corr_fwd_tiled : corr_fwd_mma)(x1, ld1, x2, ld2, out, ldo, N, H, W, cout_pad,
                                                                             as_stream(stream));
