@@ -10,6 +10,10 @@ bool corr_fwd_tc_supported(const void* x1, int64_t ld1, const void* x2, int64_t 
                            int cout_pad);
 int corr_fwd_tc(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* out, int64_t ldo, int N, int H, int W,
                 int cout_pad, cudaStream_t s);
+bool corr_bwd_tc_supported(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* g, int64_t ldg, const void* dx1,
+                           int64_t lddx1, const void* dx2, int64_t lddx2, const void* ws, int64_t ws_bytes, int N, int H, int W);
+int corr_bwd_tc(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* g, int64_t ldg, void* dx1, int64_t lddx1,
+                int acc1, void* dx2, int64_t lddx2, int acc2, void* ws, int N, int H, int W, cudaStream_t s);
 int corr_fwd_mma(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* out, int64_t ldo, int N, int H, int W,
                  int cout_pad, cudaStream_t s);
 int corr_bwd_mma(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* g, int64_t ldg, void* dx1,
@@ -361,9 +365,13 @@ NV_API int nervecl_corr_fwd(const void* x1, int64_t ld1, const void* x2, int64_t
 
 NV_API int nervecl_corr_bwd(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* dout,
                             int64_t lddo, void* dx1, int64_t lddx1, int acc1, void* dx2, int64_t lddx2, int acc2,
-                            int dtype, int N, int H, int W, int C, nervecl_stream_t stream) {
+                            int dtype, int N, int H, int W, int C, void* workspace, int64_t workspace_bytes,
+                            nervecl_stream_t stream) {
   if (!x1 || !x2 || !dout || !dx1 || !dx2 || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
   if ((C & 7) || (ld1 & 7) || (ld2 & 7) || (lddx1 & 7) || (lddx2 & 7)) return NERVECL_EALIGN;
+  if (dtype == NERVECL_BF16 && C == 64 && !nv::tune_env("NERVECL_CORR_MMA") &&
+      corr_bwd_tc_supported(x1, ld1, x2, ld2, dout, lddo, dx1, lddx1, dx2, lddx2, workspace, workspace_bytes, N, H, W))
+    return corr_bwd_tc(x1, ld1, x2, ld2, dout, lddo, dx1, lddx1, acc1, dx2, lddx2, acc2, workspace, N, H, W, as_stream(stream));
   if (corr_tiled_supported(dtype, C, ld1, ld2, x1, x2) && aligned(dx1, 16) && aligned(dx2, 16))
     return (nv::tune_env("NERVECL_CORR_SIMT") ? corr_bwd_tiled : corr_bwd_mma)(x1, ld1, x2, ld2, dout, lddo, dx1, lddx1, acc1, dx2,
                                                                             lddx2, acc2, N, H, W, as_stream(stream));

@@ -183,6 +183,279 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradients.  dx[p, c] = (1/C) sum_{i,j} G[p, i*9+j] * X[p + (i-4, j-4), c]  with (G, X) = (g, x2) for dx1 and
+// (g~, x1) for dx2, g~[q, i*9+j] = g[q + (i-4, j-4), (8-i)*9 + (8-j)] (corr_transpose_kernel below).
+//
+// Per 8 x 16 pixel tile this is ONE GEMM  D[128 px, 64 ch] = A[128, 384] * B[384, 64]:  B = the 16 x 24 pixel region of
+// X exactly as its TMA box lands in shared memory (region pixel = K row, 64 channels contiguous: the MN-major operand
+// layout), A = the tile's gradients scattered onto the region (A[p, q] = G[p, d(q - p)], zero where q is out of reach).
+// The sparsity pattern of A depends only on the position inside the tile, so A is zeroed once per CTA and every tile
+// overwrites the same 81 entries per row with 2-byte stores in the K-major 128B-swizzled layout.  24 k-steps of
+// N = 64 are shared-memory fed (6 KB per MMA): ~1150 cycles per tile, against ~9000 per 128 pixels for the
+// mma.sync version; the 128 builder threads prefetch the next tile's gradients while the MMAs of this one run and
+// drain the previous tile's accumulator (two 64-column TMEM buffers) after they have rebuilt A.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t GA_CHUNK = TY * TX * ROWB;        // one 64-wide K chunk of A: 128 rows x 128 B = 16 KB
+constexpr uint32_t GA_BYTES = (RY * RX / 64) * GA_CHUNK;   // 6 chunks = 96 KB
+constexpr int kGradStages = 2;
+
+struct GradArgs {
+  const bf16* g;
+  int64_t ldg;
+  bf16* dx;
+  int64_t lddx;
+  int accumulate;
+  int N, H, W, tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr) {     // MN-major, 128-byte K rows, SBO = 8 rows
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((B_BYTES >> 4) & 0x3FFF) << 16;                      // LBO: next 64-channel block (there is none: N = 64)
+  d |= (uint64_t)((8u * ROWB) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+corr_grad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                                  // [6][128 rows][128 B]
+  uint8_t* sB = smem + GA_BYTES;                                       // [kGradStages][384 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kGradStages * B_BYTES);
+  uint64_t* b_full = bars;                       // [2] TMA -> MMA
+  uint64_t* b_empty = b_full + kGradStages;      // [2] MMA -> TMA
+  uint64_t* a_full = b_empty + kGradStages;      // builders -> MMA
+  uint64_t* a_free = a_full + 1;                 // MMA -> builders
+  uint64_t* acc_full = a_free + 1;               // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (int64_t)a.N * a.tiles_y * a.tiles_x;
+
+  for (uint32_t e = threadIdx.x; e < GA_BYTES / 16; e += kThreads) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0, 0, 0, 0);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < kGradStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(a_full, kEpiWarps);
+    mbar_init(a_free, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  fence_proxy_async();                              // the zero fill of A is visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tx = (int)(t % a.tiles_x);
+        const int64_t r = t / a.tiles_x;
+        const int ty = (int)(r % a.tiles_y), n = (int)(r / a.tiles_y);
+        mbar_wait(&b_empty[stage], phase ^ 1);
+        mbar_expect_tx(&b_full[stage], B_BYTES);
+        tma_load_4d(sB + (size_t)stage * B_BYTES, &tmap_x, &b_full[stage], 0, tx * TX - 4, ty * TY - 4, n);
+        if (++stage == kGradStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // A K-major (bit 15 clear), B MN-major (bit 16), D fp32, M = 128, N = 64
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const uint32_t ab = it & 1u;
+      mbar_wait(&acc_empty[ab], ((it >> 1) & 1u) ^ 1u);
+      mbar_wait(&b_full[stage], phase);
+      mbar_wait(a_full, it & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(sA), sb = smem_u32(sB + (size_t)stage * B_BYTES);
+#pragma unroll 4
+        for (int ks = 0; ks < RY * RX / 16; ++ks) {
+          const uint64_t da = make_kmajor_desc(sa + (uint32_t)(ks >> 2) * GA_CHUNK, ROWB) + 2u * (uint32_t)(ks & 3);
+          const uint64_t db = make_mn_desc(sb + (uint32_t)ks * 16u * ROWB);
+          umma_bf16(tmem_base + ab * 64u, da, db, idesc, ks > 0);
+        }
+        umma_commit(&b_empty[stage]);
+        umma_commit(a_free);
+        umma_commit(&acc_full[ab]);
+      }
+      __syncwarp();
+      if (++stage == kGradStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ================= builders + epilogue: thread <-> tile pixel p = TMEM lane =================
+    const int q = warp & 3;
+    const int p = q * 32 + lane;
+    const int py = p >> 4, px = p & 15;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float inv_c = 1.f / (float)C;
+    // byte address of A[p][k] (K-major, 128B swizzle): chunk k/64, 16-byte unit ((k%64)/8) ^ (p%8)
+    uint8_t* arow = sA + (uint32_t)p * ROWB;
+    const int k0 = py * RX + px;
+    auto drain = [&](uint32_t jt, int tx, int ty, int n) {
+      const uint32_t ab = jt & 1u;
+      mbar_wait(&acc_full[ab], (jt >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(lane_addr + ab * 64u + 16u * c, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      const int y = ty * TY + py, x = tx * TX + px;
+      if (y < a.H && x < a.W) {
+        bf16* dp = a.dx + (((int64_t)n * a.H + y) * a.W + x) * a.lddx;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          f16v o;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) o.v[k] = __uint_as_float(v[c][k]) * inv_c;
+          if (a.accumulate) {
+            const f8 lo = ld8(dp + 16 * c), hi = ld8(dp + 16 * c + 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { o.v[k] += lo.v[k]; o.v[8 + k] += hi.v[k]; }
+          }
+          st16(dp + 16 * c, o);
+        }
+      }
+    };
+    // this pixel's 81 gradients of a tile (96-channel rows: eleven 16-byte loads); the NEXT tile's are requested as soon
+    // as this tile's operand is built, so their latency hides behind the accumulator drain and the MMAs
+    uint4 gq[11];
+    auto fetch = [&](int64_t t) {
+      const int tx = (int)(t % a.tiles_x);
+      const int64_t r = t / a.tiles_x;
+      const int ty = (int)(r % a.tiles_y), n = (int)(r / a.tiles_y);
+      const int y = ty * TY + py, x = tx * TX + px;
+      const bool ok = t < ntiles && y < a.H && x < a.W;
+      const uint4* src = reinterpret_cast<const uint4*>(a.g + (((int64_t)n * a.H + y) * a.W + x) * a.ldg);
+#pragma unroll
+      for (int c = 0; c < 11; ++c) gq[c] = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    };
+    uint32_t it = 0;
+    int ptx = 0, pty = 0, pn = 0;
+    fetch(blockIdx.x);
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int tx = (int)(t % a.tiles_x);
+      const int64_t r = t / a.tiles_x;
+      const int ty = (int)(r % a.tiles_y), n = (int)(r / a.tiles_y);
+      uint32_t w[44];
+#pragma unroll
+      for (int c = 0; c < 11; ++c) { w[4 * c] = gq[c].x; w[4 * c + 1] = gq[c].y; w[4 * c + 2] = gq[c].z; w[4 * c + 3] = gq[c].w; }
+      mbar_wait(a_free, (it & 1u) ^ 1u);              // the MMAs of the previous tile have read A
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          const int d = i * ND + j;
+          const uint16_t hv = (uint16_t)((d & 1) ? (w[d >> 1] >> 16) : (w[d >> 1] & 0xFFFFu));
+          const int k = k0 + i * RX + j;
+          const int kk = k & 63;
+          *reinterpret_cast<uint16_t*>(arow + (uint32_t)(k >> 6) * GA_CHUNK + ((uint32_t)((kk >> 3) ^ (p & 7)) << 4) + (uint32_t)(kk & 7) * 2u) = hv;
+        }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+      fetch(t + gridDim.x);
+      if (it > 0) drain(it - 1, ptx, pty, pn);
+      ptx = tx; pty = ty; pn = n;
+    }
+    if (it > 0) drain(it - 1, ptx, pty, pn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// g~[q, i*9+j] = g[q + (i-4, j-4), (8-i)*9 + (8-j)]  (zero outside the image; channels 81..95 zero): the gradient of the
+// correlation seen from the SECOND operand's pixels.  One CTA per 8 x 16 tile: the 16 x 24 source region is staged in
+// shared memory at a 49-word pixel pitch (odd: the 2-byte diagonal gathers of a warp hit 32 different banks).
+constexpr int GT_PITCH = 49;                         // 32-bit words per staged pixel (96 bf16 = 48 words + 1)
+constexpr int GT_THREADS = 256;
+
+__global__ void __launch_bounds__(GT_THREADS)
+corr_transpose_kernel(const bf16* __restrict__ g, int64_t ldg, bf16* __restrict__ gt, int64_t ldt, int N, int H, int W, int tiles_x,
+                      int tiles_y) {
+  extern __shared__ __align__(16) uint32_t st[];     // [RY*RX][GT_PITCH]
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int n = t / tiles_y;
+  const int y0 = ty * TY - 4, x0 = tx * TX - 4;
+  // 384 pixels x 12 chunks = 4608 chunks = 18 per thread, requested six at a time before anything is stored (a plain
+  // load-store loop pays one global-memory latency per chunk)
+  constexpr int PER = RY * RX * 12 / GT_THREADS;       // 18
+  static_assert(PER * GT_THREADS == RY * RX * 12 && PER % 6 == 0, "chunk split");
+#pragma unroll 1
+  for (int b = 0; b < PER; b += 6) {
+    uint4 u[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int e = threadIdx.x + (b + k) * GT_THREADS;
+      const int rp = e / 12, c = e - rp * 12;
+      const int ry = rp / RX, rx = rp - ry * RX;
+      const int y = y0 + ry, x = x0 + rx;
+      u[k] = make_uint4(0, 0, 0, 0);
+      if (y >= 0 && y < H && x >= 0 && x < W) u[k] = __ldg(reinterpret_cast<const uint4*>(g + (((int64_t)n * H + y) * W + x) * ldg) + c);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int e = threadIdx.x + (b + k) * GT_THREADS;
+      const int rp = e / 12, c = e - rp * 12;
+      uint32_t* dst = st + rp * GT_PITCH + c * 4;
+      dst[0] = u[k].x; dst[1] = u[k].y; dst[2] = u[k].z; dst[3] = u[k].w;
+    }
+  }
+  __syncthreads();
+  const int p = threadIdx.x & 127, half = threadIdx.x >> 7;        // pixel of the tile, which 48 output channels
+  const int py = p >> 4, px = p & 15;
+  const int y = ty * TY + py, x = tx * TX + px;
+  const uint16_t* sh = reinterpret_cast<const uint16_t*>(st);
+  uint32_t o[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int d = half * 48 + 2 * k + hf;                          // output channel i*9+j (d >= 81: zero padding)
+      uint16_t v = 0;
+      if (d < NDISP) {
+        const int i = d / ND, j = d - i * ND;
+        v = sh[((py + i) * RX + px + j) * (GT_PITCH * 2) + (NDISP - 1 - d)];
+      }
+      word |= (uint32_t)v << (16 * hf);
+    }
+    o[k] = word;
+  }
+  if (y < H && x < W) {
+    uint4* dst = reinterpret_cast<uint4*>(gt + (((int64_t)n * H + y) * W + x) * ldt + half * 48);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  }
+}
+
 }  // namespace
 
 namespace nv {
@@ -221,6 +494,60 @@ int corr_fwd_tc(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* 
   const unsigned grid = (unsigned)imin(ntiles, sm_count());
   corr_fwd_tc_kernel<<<grid, kThreads, smem, s>>>(ta, tb, a);
   return launch_status();
+}
+
+}  // namespace nv
+
+namespace nv {
+
+bool corr_bwd_tc_supported(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* g, int64_t ldg, const void* dx1,
+                           int64_t lddx1, const void* dx2, int64_t lddx2, const void* ws, int64_t ws_bytes, int N, int H, int W) {
+  if ((ld1 & 7) || (ld2 & 7) || !aligned(x1, 16) || !aligned(x2, 16)) return false;
+  if (ldg < 88 || (ldg & 7) || !aligned(g, 16)) return false;                  // eleven 16-byte loads per pixel
+  if ((lddx1 & 15) || (lddx2 & 15) || !aligned(dx1, 32) || !aligned(dx2, 32)) return false;
+  if (!ws || !aligned(ws, 16) || ws_bytes < (int64_t)N * H * W * 96 * 2) return false;
+  if (H < 8 || W < 16) return false;
+  return encode_fn() != nullptr;
+}
+
+static int corr_grad_tc(const void* X, int64_t ldX, const void* g, int64_t ldg, void* dx, int64_t lddx, int accumulate, int N,
+                        int H, int W, cudaStream_t s) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return NERVECL_EUNSUPPORTED;
+  CUtensorMap tx;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ldX * 2, (cuuint64_t)W * ldX * 2, (cuuint64_t)H * W * ldX * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)RX, (cuuint32_t)RY, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(X), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return NERVECL_EUNSUPPORTED;
+  GradArgs a;
+  a.g = (const bf16*)g; a.ldg = ldg; a.dx = (bf16*)dx; a.lddx = lddx; a.accumulate = accumulate;
+  a.N = N; a.H = H; a.W = W;
+  a.tiles_x = (W + TX - 1) / TX;
+  a.tiles_y = (H + TY - 1) / TY;
+  const int64_t ntiles = (int64_t)N * a.tiles_x * a.tiles_y;
+  const size_t smem = 1024 + GA_BYTES + (size_t)kGradStages * B_BYTES + 16 * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(corr_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  corr_grad_tc_kernel<<<(unsigned)imin(ntiles, sm_count()), kThreads, smem, s>>>(tx, a);
+  return launch_status();
+}
+
+int corr_bwd_tc(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* g, int64_t ldg, void* dx1, int64_t lddx1,
+                int acc1, void* dx2, int64_t lddx2, int acc2, void* ws, int N, int H, int W, cudaStream_t s) {
+  int rc = corr_grad_tc(x2, ld2, g, ldg, dx1, lddx1, acc1, N, H, W, s);
+  if (rc) return rc;
+  const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+  const size_t smem = (size_t)RY * RX * GT_PITCH * 4;
+  cudaError_t e = cudaFuncSetAttribute(corr_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  corr_transpose_kernel<<<(unsigned)((int64_t)N * tiles_x * tiles_y), GT_THREADS, smem, s>>>((const bf16*)g, ldg, (bf16*)ws, 96, N, H, W,
+                                                                                       tiles_x, tiles_y);
+  rc = launch_status();
+  if (rc) return rc;
+  return corr_grad_tc(x1, ld1, ws, 96, dx2, lddx2, acc2, N, H, W, s);
 }
 
 }  // namespace nv

@@ -69,7 +69,7 @@ _SIGNATURES = {
                                   c_i32, c_i32, c_i64, c_i32, c_i32, c_vp],
     "nervecl_corr_fwd": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_corr_bwd": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32,
-                         c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+                         c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp],
     "nervecl_warp_fwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp],
     "nervecl_warp_bwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                          c_i32, c_vp],

@@ -472,6 +472,7 @@ class Plan:
             ws["wg_tmp"] = torch.zeros(32 * 64 + 32, device=dev, dtype=f32)         # their 1x1 weight / bias gradients
             ws["dfn3"], ws["dfn2"], ws["dfn1"] = act(B, 32), act(B, 64), act(B, 128)
             ws["dcorr"] = act(B, CORR_PAD)
+            ws["dcorr_t"] = act(B, CORR_PAD)          # the centre frame's view of the correlation gradient (corr_bwd workspace)
             ws["t"] = [act(T * B, F) for _ in range(3)]
             ws["bsums"] = torch.zeros((T, F, 2), device=dev, dtype=torch.float64)
             self._bwd_ws = ws
@@ -625,7 +626,7 @@ class Plan:
             self.dgrad("motion_estimator.flow_net.2", ws["dfn2"], ws["dfn1"], mask=A.fn1[t])
             self.wgrad("motion_estimator.flow_net.0", A.corr[t][..., :CORR_CH], ws["dfn1"], G)
             self.dgrad("motion_estimator.flow_net.0", ws["dfn1"], ws["dcorr"])
-            nv.corr_bwd(feat[t], centre, ws["dcorr"], dfeat[t], True, dfeat[self.mid], True)
+            nv.corr_bwd(feat[t], centre, ws["dcorr"], dfeat[t], True, dfeat[self.mid], True, ws["dcorr_t"])
         ready("motion_estimator.")
 
         # ---- feature extractor (all T*B frames at once, BN per frame group) ----

@@ -371,15 +371,23 @@ def _corr_fwd(x1, x2, out) -> None:
                "corr_fwd")
 
 
-@_op("corr_bwd(Tensor x1, Tensor x2, Tensor dout, Tensor(a!) dx1, bool acc1, Tensor(b!) dx2, bool acc2) -> ()")
-def _corr_bwd(x1, x2, dout, dx1, acc1, dx2, acc2) -> None:
+@_op("corr_bwd(Tensor x1, Tensor x2, Tensor dout, Tensor(a!) dx1, bool acc1, Tensor(b!) dx2, bool acc2, "
+     "Tensor(c!)? workspace=None) -> ()")
+def _corr_bwd(x1, x2, dout, dx1, acc1, dx2, acc2, workspace=None) -> None:
+    """``workspace``: optional [N,H,W,96] buffer of the activation dtype (enables the tcgen05 gradient kernels)."""
     p1, ld1, n, h, w, c = _nhwc(x1, "x1")
     p2, ld2, *_ = _nhwc(x2, "x2")
     pg, ldg, *_ = _nhwc(dout, "dout")
     q1, l1, *_ = _nhwc(dx1, "dx1")
     q2, l2, *_ = _nhwc(dx2, "dx2")
+    wp, wb = (None, 0)
+    if workspace is not None:
+        _cuda(workspace, "workspace")
+        if not workspace.is_contiguous() or workspace.dtype != x1.dtype:
+            raise RuntimeError("nervecl.corr_bwd: workspace must be contiguous and of the activation dtype")
+        wp, wb = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     _lib.check(_lib.load().nervecl_corr_bwd(p1, ld1, p2, ld2, pg, ldg, q1, l1, int(acc1), q2, l2, int(acc2),
-                                           _dt(x1), n, h, w, c, _stream()), "corr_bwd")
+                                           _dt(x1), n, h, w, c, wp, wb, _stream()), "corr_bwd")
 
 
 @_op("warp_fwd(Tensor feat, Tensor flow, Tensor(a!) out, int div_mode, Tensor(b!)? idx_out) -> ()")

@@ -232,10 +232,14 @@ int nervecl_bn_relu_bwd_apply(const void* x, int64_t ldx, const void* dy, int64_
 int nervecl_corr_fwd(const void* x1, int64_t ld1, const void* x2, int64_t ld2, void* out,
                      int64_t ldo, int dtype, int N, int H, int W, int C, int cout_pad,
                      nervecl_stream_t stream);
-/* dx1 / dx2 are fp32-accumulated and then stored (acc1/acc2 = 0) or added (= 1) in dtype. */
+/* dx1 / dx2 are fp32-accumulated and then stored (acc1/acc2 = 0) or added (= 1) in dtype.
+ * workspace (nullable, ABI v6): N*H*W*96 elements of dtype, 16-byte aligned, for the second operand's view of the
+ * gradient (dout gathered from the neighbouring pixels); with it the bf16 / C = 64 case runs both gradients as
+ * tcgen05 GEMMs over 8 x 16 pixel tiles, without it as banded mma.sync products. */
 int nervecl_corr_bwd(const void* x1, int64_t ld1, const void* x2, int64_t ld2, const void* dout,
                      int64_t lddo, void* dx1, int64_t lddx1, int acc1, void* dx2, int64_t lddx2,
-                     int acc2, int dtype, int N, int H, int W, int C, nervecl_stream_t stream);
+                     int acc2, int dtype, int N, int H, int W, int C, void* workspace,
+                     int64_t workspace_bytes, nervecl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Flow warp = grid build + bilinear grid_sample(zeros, align_corners=True)

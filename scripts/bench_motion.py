@@ -42,11 +42,13 @@ flow = (torch.rand(N, H, W, 2, device=dev) - 0.5) * 6
 out = torch.empty_like(x1)
 dfeat = torch.zeros_like(x1)
 dflow = torch.empty_like(flow)
+ws = torch.empty_like(corr)
 px = N * H * W
 e = 2
 rows = {
     "corr_fwd": ((2 * C * e + 96 * e) * px, lambda: nv.corr_fwd(x1, x2, corr)),
-    "corr_bwd": ((96 * e + 4 * C * e) * px, lambda: nv.corr_bwd(x1, x2, g, d1, False, d2, False)),
+    "corr_bwd": ((96 * e + 4 * C * e) * px, lambda: nv.corr_bwd(x1, x2, g, d1, False, d2, False, ws)),
+    "corr_bwd_mma": ((96 * e + 4 * C * e) * px, lambda: nv.corr_bwd(x1, x2, g, d1, False, d2, False)),
     "warp_fwd": ((2 * C * e + 8) * px, lambda: nv.warp_fwd(x1, flow, out, 0, None)),
     "warp_bwd_lp": ((3 * C * e + 16) * px, lambda: nv.warp_bwd_lp(x1, flow, g[..., :C], dfeat, dflow, 0)),
 }

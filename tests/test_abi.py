@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert name in _lib._SIGNATURES, f"{name} has no ctypes signature"
         assert len(_lib._SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, binding {len(_lib._SIGNATURES[name])}"
     assert set(_lib._SIGNATURES) == set(decls)
-    assert lib.nervecl_abi_version() == 5
+    assert lib.nervecl_abi_version() == 6
     assert lib.nervecl_error_string(-2).decode().startswith("misaligned")
 
 

@@ -204,6 +204,37 @@ def test_correlation_tiled_bf16(shape):
     assert relerr(nchw(d1), a.grad + p1) <= 8e-3 and relerr(nchw(d2), b.grad) <= 8e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 150), (1, 8, 16), (1, 50, 70), (3, 64, 128), (1, 21, 333)])
+def test_correlation_tcgen05_tiles(shape):
+    """The tcgen05 2-D tile correlation kernels (csrc/motion_tc.cu: dense Gram product per 8 x 16 tile, diagonal
+    extraction through shared memory; gradients as one GEMM per tile over the scattered gradient operand, the second
+    operand's gradient through the transposed-gradient workspace): ragged tiles in both directions, accumulate flags."""
+    from oracle import sr_oracle
+    n, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 3)
+    x1 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    x2 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    a, b = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    ref = sr_oracle.correlation(a, b)
+    out = torch.full((n, h, w, 96), 7.0, device="cuda", dtype=torch.bfloat16)
+    nv().corr_fwd(nhwc(x1, torch.bfloat16, pad_to=72), nhwc(x2, torch.bfloat16), out)
+    assert relerr(nchw(out[..., :81]), ref) <= 6e-3
+    assert float(out[..., 81:].float().abs().max()) == 0.0
+    dy = torch.randn(n, 81, h, w, generator=g).bfloat16().float()
+    ref.backward(dy)
+    p1 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    d1 = nhwc(p1, torch.bfloat16)
+    d2 = torch.full((n, h, w, 64), 3.0, device="cuda", dtype=torch.bfloat16)
+    ws = torch.empty((n, h, w, 96), device="cuda", dtype=torch.bfloat16)
+    gy = nhwc(dy, torch.bfloat16, pad_to=96)
+    nv().corr_bwd(nhwc(x1, torch.bfloat16), nhwc(x2, torch.bfloat16), gy, d1, True, d2, False, ws)
+    assert relerr(nchw(d1), a.grad + p1) <= 8e-3 and relerr(nchw(d2), b.grad) <= 8e-3
+    # the workspace path and the banded mma.sync path (no workspace) agree
+    e1, e2 = torch.empty_like(d2), torch.empty_like(d2)
+    nv().corr_bwd(nhwc(x1, torch.bfloat16), nhwc(x2, torch.bfloat16), gy, e1, False, e2, False)
+    assert relerr(e2, d2.float()) <= 8e-3 and relerr(nchw(e1), a.grad) <= 8e-3
+
+
 def test_warp_indices_bit_exact_vs_cpu_golden():
     """div_mode=1 replays ATen-CPU's division: indices must equal the golden (CPU reference) ones exactly."""
     from nerve_cl_b200.models import warp_indices, warp_features
