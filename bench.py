@@ -394,8 +394,9 @@ def run_native(args):
     # three back-to-back passes of K steps; `value` is their MEDIAN, all three are reported
     value_passes = [timed(lambda: step(lr_dev, hr_dev), args.steps)]
     launches = ops.LAUNCHES[0] - launches0
-    value_passes += [timed(lambda: step(lr_dev, hr_dev), args.steps) for _ in range(2)]
-    ms = sorted(value_passes)[1]
+    if not args.value_only:                      # (the ncu passes run --value-only: one pass keeps them short)
+        value_passes += [timed(lambda: step(lr_dev, hr_dev), args.steps) for _ in range(2)]
+    ms = sorted(value_passes)[len(value_passes) // 2]
     clocks = sampler.stop()
 
     if args.value_only:
@@ -491,17 +492,33 @@ def run_native(args):
         # EnhancementEngine.enhance_video (sliding windows batched 16 per network call) -> HR frames back in pinned host memory
         clip_frames = 32
         clip_host = torch.rand(clip_frames, 3, 180, 320).pin_memory()
-        hr_host4 = torch.empty(clip_frames, 3, 720, 1280).pin_memory()
+        hr_host4 = [torch.empty(clip_frames, 3, 720, 1280).pin_memory() for _ in range(2)]
+        d2h_stream = torch.cuda.Stream(device=dev)
+        d2h_state = {"k": 0}
 
         def infer4_e2e():
+            # the loop a user writes: clip k+1 is enhanced while clip k's HR frames travel back on a side stream
             v = clip_host.to(dev, non_blocking=True)
-            hr_host4.copy_(eng4.enhance_video(v, batch_size=x4_batch), non_blocking=True)
+            hr = eng4.enhance_video(v, batch_size=x4_batch)
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                hr_host4[d2h_state["k"] & 1].copy_(hr, non_blocking=True)
+                hr.record_stream(d2h_stream)
+            d2h_state["k"] += 1
+
+        def run_clips():
+            for _ in range(args.steps):
+                infer4_e2e()
+            torch.cuda.current_stream().wait_stream(d2h_stream)      # the last clip's frames are back before the clock stops
 
         infer4_e2e()
-        ms_c3 = timed(infer4_e2e, args.steps)
+        torch.cuda.synchronize()
+        ms_c3 = timed(run_clips, 1)
         x4_e2e = {"metric": "sr_x4_infer_frames_per_sec", "value": clip_frames * world * args.steps / (ms_c3 / 1e3), "unit": UNIT,
                   "ms_per_clip": ms_c3 / args.steps, "frames_per_clip": clip_frames,
-                  "h2d_bytes_per_step": clip_host.numel() * 4, "d2h_bytes_per_step": hr_host4.numel() * 4,
+                  "h2d_bytes_per_step": clip_host.numel() * 4, "d2h_bytes_per_step": hr_host4[0].numel() * 4,
                   "note": "host frames -> EnhancementEngine.enhance_video (16 windows per call) -> HR frames in pinned host memory"}
         del eng4, m4
 
@@ -562,6 +579,37 @@ def run_native(args):
                         "SuperResolutionNet x2, 960x540 -> 1920x1080, host frames in, HR frames back in pinned host memory"}
         del eng5
         torch.cuda.empty_cache()
+
+    # ---- the reference launcher's own configuration (train_baseline.py: 32 features / 4 dense blocks, 64x64 crops, batch
+    #      16; README "~5 s/epoch estimated on CUDA" for 512 samples): launch-bound, so the step is replayed as a CUDA graph
+    small = None
+    if full_cfg and world == 1:
+        from nerve_cl_b200.graphs import GraphedTrainStep
+        torch.manual_seed(0)
+        ms_small = {}
+        lr_s, hr_s = synth_batch(16, 3, 64, 64, 2, 99, dev)
+        for tag in ("eager", "cuda_graph"):
+            m_s = SuperResolutionNet(scale_factor=2, num_features=32, num_residual_blocks=4).to(dev).train()
+            m_s.compute_dtype = torch.bfloat16
+            o_s = FlatAdamW(m_s, lr=1e-3, weight_decay=1e-5)
+            if tag == "eager":
+                def s_step():
+                    o_s.zero_grad()
+                    torch.nn.functional.mse_loss(m_s(lr_s), hr_s).backward()
+                    o_s.step()
+            else:
+                g_step = GraphedTrainStep(m_s, o_s)
+
+                def s_step():
+                    g_step(lr_s, hr_s)
+            for _ in range(3):
+                s_step()
+            ms_small[tag] = timed(s_step, 32) / 32
+            del m_s, o_s
+        small = {"config": "SuperResolutionNet x2, 32 feat / 4 dense blocks, 64x64 -> 128x128, T=3, B=16, bf16 (train_baseline.py defaults)",
+                 "ms_per_step_eager": ms_small["eager"], "ms_per_step_cuda_graph": ms_small["cuda_graph"],
+                 "epoch_512_samples_s": 32 * ms_small["cuda_graph"] / 1e3,
+                 "frames_per_s_cuda_graph": 16 / (ms_small["cuda_graph"] / 1e3)}
 
     divergence = nd.param_divergence(model)       # max |theta_rank - theta_0| after all the steps above (must be 0)
     if rank != 0:
@@ -689,6 +737,7 @@ def run_native(args):
         "infer_x4_e2e": x4_e2e,
         "continual_train": cfg4,
         "enhance_pipeline": cfg5,
+        "launcher_config": small,
         "hbm_kernels": {"peak_GBs": hbm_peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk['_source']})",
                         "kernels": hbm_kernels},
         "loss_last": losses[-1] if losses else None,

@@ -159,7 +159,12 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                     float lr, float b1, float b2, float eps, float wd, float bc1,
-                                                    float bc2_sqrt, float gscale) {
+                                                    float bc2_sqrt, float gscale, const int32_t* __restrict__ step_dev) {
+  if (step_dev) {          // step count kept on the device (CUDA-graph replays): bias corrections computed here
+    const float st = (float)__ldg(step_dev);
+    bc1 = 1.f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  }
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok(p, g, m) && vec_ok(v, nullptr, nullptr)) {
     const int64_t n4 = n >> 2;
@@ -360,13 +365,13 @@ NV_API int nervecl_si_register(const float* const* theta_host, const int64_t* nu
 
 NV_API int nervecl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                              float grad_scale, nervecl_stream_t stream) {
-  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return NERVECL_EINVAL;
+                              float grad_scale, const int32_t* step_dev, nervecl_stream_t stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || (step < 1 && !step_dev)) return NERVECL_EINVAL;
   float bc1 = 1.f - powf(beta1, (float)step);
   float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   // one resident wave: 8 blocks of 256 threads per SM, every thread streams two 128-bit vectors per array per trip
   int blocks = (int)imax(1, imin(cdiv(n, 256 * 8), kSMs * 8));
   adamw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                      weight_decay, bc1, bc2_sqrt, grad_scale);
+                                                      weight_decay, bc1, bc2_sqrt, grad_scale, step_dev);
   return launch_status();
 }

@@ -111,7 +111,7 @@ _SIGNATURES = {
     "nervecl_flat_gather": [C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64), c_i32, c_vp, c_vp],
     "nervecl_si_update": [C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_i64), c_i32, c_vp, c_vp, c_vp],
     "nervecl_si_register": [C.POINTER(c_vp), C.POINTER(c_i64), c_i32, c_vp, c_vp, c_vp, c_f32, c_vp],
-    "nervecl_adamw_step": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp],
+    "nervecl_adamw_step": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp, c_vp],
 }
 _RESTYPES = {"nervecl_error_string": C.c_char_p}
 

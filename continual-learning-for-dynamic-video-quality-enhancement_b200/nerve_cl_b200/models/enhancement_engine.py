@@ -149,6 +149,27 @@ class EnhancementEngine(nn.Module):
             rows.append((start, end, t - start))
         return rows
 
+    def _video_plan(self, T: int, per_call: int, device) -> List[Tuple[int, Tensor, Tensor]]:
+        """[(centre index, source-frame table (n, L), output frame ids (n,))] per network call for a T-frame clip, built once
+        per (T, batch size, device) and kept on the device: the loop itself issues no host->device copies."""
+        key = (T, per_call, str(device), self.config.recovery_temporal_window, self.config.sr_temporal_window)
+        cache = self.__dict__.setdefault("_video_plans", {})
+        if key not in cache:
+            table = self.window_table(T)
+            groups: Dict[Tuple[int, int], List[int]] = {}
+            for t, (start, end, c) in enumerate(table):
+                groups.setdefault((end - start, c), []).append(t)
+            plan = []
+            for (length, c), ts in groups.items():
+                for i in range(0, len(ts), per_call):
+                    chunk = ts[i:i + per_call]
+                    idx = torch.tensor([[table[t][0] + j for j in range(length)] for t in chunk], device=device)
+                    plan.append((c, idx, torch.tensor(chunk, device=device)))
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = plan
+        return cache[key]
+
     @torch.no_grad()
     def enhance_video(self, video: Tensor, corruption_masks: Optional[Tensor] = None, batch_size: int = 4) -> Tensor:
         """video (T,C,H,W) or (B,T,C,H,W) [+ masks (T,1,H,W)] -> enhanced video (reference :186-248).
@@ -161,26 +182,20 @@ class EnhancementEngine(nn.Module):
         if video.dim() != 5:
             raise RuntimeError("enhance_video: video must be (T,C,H,W) or (B,T,C,H,W)")
         B, T, C, H, W = video.shape
-        table = self.window_table(T)
-        groups: Dict[Tuple[int, int], List[int]] = {}
-        for t, (start, end, c) in enumerate(table):
-            groups.setdefault((end - start, c), []).append(t)
-        out: Optional[Tensor] = None
         per_call = max(1, batch_size)
-        for (length, c), ts in groups.items():
-            for i in range(0, len(ts), per_call):
-                chunk = ts[i:i + per_call]
-                idx = torch.tensor([[table[t][0] + j for j in range(length)] for t in chunk], device=video.device)
-                win = video[:, idx]                                       # (B, n, L, C, H, W): one device gather
-                win = win.transpose(0, 1).reshape(len(chunk) * B, length, C, H, W)
-                mask = None
-                if corruption_masks is not None:
-                    m = corruption_masks[torch.tensor(chunk, device=corruption_masks.device)]          # (n, 1, H, W)
-                    mask = m.unsqueeze(1).expand(-1, B, -1, -1, -1).reshape(len(chunk) * B, *m.shape[1:])
-                enh = self.forward(win, center_idx=c, corruption_mask=mask)["enhanced"]
-                if out is None:
-                    out = torch.empty((B, T) + tuple(enh.shape[1:]), device=enh.device, dtype=enh.dtype)
-                out[:, torch.tensor(chunk, device=enh.device)] = enh.view(len(chunk), B, *enh.shape[1:]).transpose(0, 1)
+        out: Optional[Tensor] = None
+        for c, idx, frames_t in self._video_plan(T, per_call, video.device):
+            n, length = idx.shape
+            win = video[:, idx]                                           # (B, n, L, C, H, W): one device gather
+            win = win.transpose(0, 1).reshape(n * B, length, C, H, W)
+            mask = None
+            if corruption_masks is not None:
+                m = corruption_masks[frames_t.to(corruption_masks.device)]                          # (n, 1, H, W)
+                mask = m.unsqueeze(1).expand(-1, B, -1, -1, -1).reshape(n * B, *m.shape[1:])
+            enh = self.forward(win, center_idx=c, corruption_mask=mask)["enhanced"]
+            if out is None:
+                out = torch.empty((B, T) + tuple(enh.shape[1:]), device=enh.device, dtype=enh.dtype)
+            out[:, frames_t] = enh.view(n, B, *enh.shape[1:]).transpose(0, 1)
         return out.squeeze(0) if squeeze else out
 
     # ------------------------------------------------------------------------------------------------------------

@@ -752,11 +752,15 @@ def _si_register(theta, W, p_old, omega, damping) -> None:
 
 
 @_op("adamw_step(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, "
-     "float beta2, float eps, float weight_decay, int step, float grad_scale) -> ()")
-def _adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale) -> None:
+     "float beta2, float eps, float weight_decay, int step, float grad_scale, Tensor? step_dev=None) -> ()")
+def _adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                step_dev=None) -> None:
+    """``step_dev``: optional device int32 scalar holding the step count (CUDA-graph replays), see ``nervecl_adamw_step``."""
     _lib.check(_lib.load().nervecl_adamw_step(_flat(param, "param"), _flat(grad, "grad"), _flat(exp_avg, "exp_avg"),
                                              _flat(exp_avg_sq, "exp_avg_sq"), param.numel(), lr, beta1, beta2, eps,
-                                             weight_decay, step, grad_scale, _stream()), "adamw_step")
+                                             weight_decay, step,
+                                             grad_scale, _flat(step_dev, "step_dev", torch.int32) if step_dev is not None else None,
+                                             _stream()), "adamw_step")
 
 
 nv = torch.ops.nervecl

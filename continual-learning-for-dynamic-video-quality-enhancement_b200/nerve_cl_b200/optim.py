@@ -58,6 +58,10 @@ class FlatAdamW:
                               "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
                               "fused": None, "decoupled_weight_decay": True, "params": list(module.parameters())}]
         self._gather: Optional[torch.Tensor] = None
+        # step count on the device as well (incremented by a captured kernel): lets graphs.GraphedTrainStep replay
+        # the optimiser step with the right bias corrections
+        self.step_dev = torch.zeros(1, device=self.flat.device, dtype=torch.int32)
+        self.device_step = False
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.module.parameters():
@@ -81,6 +85,9 @@ class FlatAdamW:
     def step(self) -> None:
         self._check_aliasing()
         self.step_count += 1
+        if self.device_step:
+            self.step_dev.add_(1)
+        sd = self.step_dev if self.device_step else None
         grp = self.param_groups[0]
         lr, (b1, b2), eps, wd = grp["lr"], grp["betas"], grp["eps"], grp["weight_decay"]
         g: Optional[torch.Tensor] = self.module.last_flat_grad()
@@ -93,14 +100,14 @@ class FlatAdamW:
                                [self.module._flat_layout[n][0] for n, _ in named], self._gather)
                 g = self._gather
         if g is not None:
-            nv.adamw_step(self.flat, g, self.exp_avg, self.exp_avg_sq, lr, b1, b2, eps, wd, self.step_count, 1.0)
+            nv.adamw_step(self.flat, g, self.exp_avg, self.exp_avg_sq, lr, b1, b2, eps, wd, self.step_count, 1.0, sd)
             return
         for n, p in self.module.named_parameters():
             if p.grad is None:
                 continue
             off, k, _ = self.module._flat_layout[n]
             nv.adamw_step(self.flat[off:off + k], p.grad.contiguous().view(-1), self.exp_avg[off:off + k],
-                          self.exp_avg_sq[off:off + k], lr, b1, b2, eps, wd, self.step_count, 1.0)
+                          self.exp_avg_sq[off:off + k], lr, b1, b2, eps, wd, self.step_count, 1.0, sd)
 
     # ---- torch.optim.AdamW-compatible checkpoints -------------------------------------------------------------
     def state_dict(self):
@@ -135,3 +142,4 @@ class FlatAdamW:
             self.exp_avg[off:off + k].view(shape).copy_(st["exp_avg"])
             self.exp_avg_sq[off:off + k].view(shape).copy_(st["exp_avg_sq"])
             self.step_count = max(self.step_count, int(st["step"]))
+        self.step_dev.fill_(self.step_count)

@@ -427,10 +427,13 @@ int nervecl_si_register(const float* const* theta_host, const int64_t* numel_hos
                         nervecl_stream_t stream);
 
 /* Fused AdamW over a flat fp32 parameter buffer (torch.optim.AdamW semantics,
- * experiments/train_baseline.py:62).  step is 1-based. */
+ * experiments/train_baseline.py:62).  step is 1-based; step_dev (nullable, ABI v6) is a device int32 holding the
+ * step count instead -- the bias corrections are then computed in the kernel, so a CUDA graph that contains the
+ * launch (and the increment of that counter) replays correctly. */
 int nervecl_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                        int64_t n, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, int step, float grad_scale, nervecl_stream_t stream);
+                       float weight_decay, int step, float grad_scale, const int32_t* step_dev,
+                       nervecl_stream_t stream);
 
 #ifdef __cplusplus
 }

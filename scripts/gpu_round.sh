@@ -6,7 +6,7 @@ tag=${1:-r01}
 mkdir -p gpurun_out
 timeout ${PYTEST_TIMEOUT:-600} python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 cp gpurun_out/bench_detail.json gpurun_out/${tag}_bench_detail.json 2>/dev/null
 CMD="timeout ${NCU_TIMEOUT:-420} python bench.py --steps 1 --warmup 3 --value-only"
 $CMD > gpurun_out/${tag}_plain.log 2>&1 &&

@@ -17,6 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+NSTEPS_IN_RUN = int(sys.argv[2]) if len(sys.argv) > 2 else 4     # steps the ncu'd command ran (3 warm-up + timed)
 src = os.path.join(ROOT, "gpurun_out")
 dst = os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
@@ -51,7 +52,7 @@ if os.path.exists(launches):
     tot = sum(v[1] for v in agg.values())
     out += ["## ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare SHARES)",
             "", f"total {tot:.1f} ms over {sum(v[0] for v in agg.values())} launches "
-            "(`python bench.py --steps 1 --warmup 3 --value-only`: 3 warm-up + 1 timed step)", "",
+            f"(`python bench.py --steps 1 --warmup 3 --value-only`: {NSTEPS_IN_RUN} steps in the run)", "",
             "| kernel | launches | ms | share |", "|---|---:|---:|---:|"]
     with open(os.path.join(dst, f"{tag}_launch_shares.csv"), "w") as f:
         f.write("kernel,launches,ms,share\n")
@@ -98,7 +99,7 @@ if os.path.exists(traffic):
         e = per.setdefault(r[ii], [r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", ""), 0.0])
         e[1] += v
     ids = list(per)
-    nstep = len(ids) // 4                         # 3 warm-up + 1 timed step, identical launch sequences
+    nstep = len(ids) // NSTEPS_IN_RUN             # identical launch sequences per step; the last one is summarised
     last = [per[i] for i in ids[len(ids) - nstep:]]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for k, b in last:
