@@ -29,9 +29,20 @@ namespace {
 constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 drain
 constexpr int KC = 64;
 constexpr uint32_t ROWB = 128;
-constexpr int PXB = BM + 2;
-constexpr uint32_t XCHUNK = (PXB * ROWB + 1023u) & ~1023u;    // 17408: one 64-channel chunk of a halo'd X row
-constexpr uint32_t YCHUNK = BM * ROWB;                          // 16384: one 64-channel chunk of a dY row
+// One pipeline stage = KPX pixels of a row (the GEMM's K extent per stage).  Measured at the cfg-2 dense block
+// (profiles/r02h_wgrad.md): 128 px x 2 stages 1.65 ms, 64 x 5 1.99 ms, 32 x 10 3.17 ms -- smaller stages spread the
+// classes over more rows at a time and the L2 hit rate drops (40 % -> 26 %), so the deeper pipeline loses.
+#ifndef WG_KPX
+#define WG_KPX 128
+#endif
+#ifndef WG_STAGES
+#define WG_STAGES 2
+#endif
+constexpr int KPX = WG_KPX;
+constexpr int PXB = KPX + 2;
+constexpr uint32_t XCHUNK = (PXB * ROWB + 1023u) & ~1023u;    // 17408: one 64-channel chunk of a halo'd X row piece
+constexpr uint32_t YCHUNK = KPX * ROWB;                         // 16384: one 64-channel chunk of a dY row piece
+constexpr int kStages = WG_STAGES;
 constexpr int kMaxGroups = 8;
 constexpr int kMaxClasses = 12;
 
@@ -161,19 +172,22 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // channel chunks of this M tile that exist (the second one may lie entirely beyond Cx: not loaded; its
-      // accumulator rows are never drained)
-      const int nxc = (mt * 128 + KC < a.Cx || ky2 >= 0) ? 2 : 1;
-      const uint32_t bytes = (uint32_t)nxc * (PXB * ROWB) + (uint32_t)nby * YCHUNK;
-      for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
+    int stage = 0;
+    uint32_t phase = 0;
+    // channel chunks of this M tile that exist (the second one may lie entirely beyond Cx: not loaded; its
+    // accumulator rows are never drained)
+    const int nxc = (mt * 128 + KC < a.Cx || ky2 >= 0) ? 2 : 1;
+    const uint32_t bytes = (uint32_t)nxc * (PXB * ROWB) + (uint32_t)nby * YCHUNK;
+    for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
+      if (lane == 0) {
         const int strip = (int)(rt % a.strips);
         const int64_t r = rt / a.strips;
         const int y = (int)(r % a.H), n = (int)(r / a.H);
-        const int x0 = strip * BM;
+        const int x0 = strip * KPX;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+#ifdef WG_NO_LOAD
+        mbar_arrive(&full_bar[stage]);
+#else
         mbar_expect_tx(&full_bar[stage], bytes);
         uint8_t* sx = smem + (size_t)stage * stage_bytes;
         uint8_t* sy = sx + 2 * XCHUNK;
@@ -182,8 +196,9 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                       y + (ky2 >= 0 && c ? ky2 : ky) - 1, n);
         for (int c = 0; c < nby; ++c)
           tma_load_4d(sy + (size_t)c * YCHUNK, &tmap_dy, &full_bar[stage], col0 + c * KC, x0, y, n);
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+#endif
       }
+      if (++stage == a.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     const uint32_t idesc = idesc_mn((uint32_t)n16);
@@ -202,11 +217,13 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int kx = 0; kx < 3; ++kx) {
           const uint32_t d = tmem_base + (uint32_t)(kx * n16);
 #pragma unroll
-          for (int ks = 0; ks < BM / 16; ++ks) {
+          for (int ks = 0; ks < KPX / 16; ++ks) {
             // K step = 16 pixel rows of 128 B; tap kx starts kx pixel rows into the halo'd X row
             const uint64_t da = hi | (uint64_t)(lbo_a | (sx + (uint32_t)((kx + 16 * ks) * 8)));
             const uint64_t db = hi | (uint64_t)(lbo_b | (sy + (uint32_t)(16 * ks * 8)));
+#ifndef WG_NO_MMA
             umma_bf16(d, da, db, idesc, started | (uint32_t)ks);
+#endif
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -281,7 +298,7 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
   if (!enc) return NERVECL_EUNSUPPORTED;
   if (ngroups < 1 || ngroups > kMaxGroups) return NERVECL_EINVAL;
   WgrArgs a;
-  a.N = N; a.H = H; a.W = W; a.Cx = Cx; a.strips = (W + BM - 1) / BM;
+  a.N = N; a.H = H; a.W = W; a.Cx = Cx; a.strips = (W + KPX - 1) / KPX;
   a.ngroups = ngroups;
   a.scale = scale;
   for (int g = 0; g < ngroups; ++g) {
@@ -310,9 +327,16 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
       const int c = a.nclasses++;
       a.c_ky2[c] = half && ky == 0 ? 1 : -1;
       a.c_mt[c] = mt; a.c_ky[c] = ky; a.c_col0[c] = lo; a.c_n16[c] = n16; a.c_nby[c] = (n16 + KC - 1) / KC;
-      const double mma = 24.0 * n16 / 2.0;
+      const double mma = (3.0 * KPX / 16.0) * n16 / 2.0;
       const double ld = (2.0 * PXB * ROWB + a.c_nby[c] * YCHUNK) / 48.0;
       cost[c] = mma > ld ? mma : ld;
+      // Narrow classes (N <= 64) run 1.45x slower than this model says: their MMAs are shared-memory bound and nothing
+      // they load is shared with a class in step with them.  Measured at the cfg-2 dense block (the share of SMs
+      // they get, launch time): x1.0 1.70 ms, x1.2 1.51, x1.4 1.41, x1.6 1.52, x1.8 1.51, x2.1 1.62.
+#ifndef WG_SMALL_SCALE
+#define WG_SMALL_SCALE 1.45
+#endif
+      if (n16 <= 64) cost[c] *= WG_SMALL_SCALE;
       total_cost += cost[c];
     }
   }
@@ -343,14 +367,14 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cy, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)W * ldy * 2, (cuuint64_t)H * W * ldy * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)BM, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)KPX, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return NERVECL_EUNSUPPORTED;
   }
-  a.stages = 2;
+  a.stages = kStages;
   const size_t smem = 1024 + (size_t)a.stages * (2 * XCHUNK + 3 * YCHUNK) + (2 * a.stages + 1) * sizeof(uint64_t) + 16;
   cudaError_t e = cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

@@ -58,6 +58,16 @@ def wgrad_case(cin, cout, k, ld_in, ld_dy):
     print(f"wgrad {cin:3d}->{cout:3d} k{k}: {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF", flush=True)
 
 
+def grouped_case():
+    """The dense block's five 3x3 weight gradients as ONE grouped launch (engine._rdb_backward_fused)."""
+    x = torch.randn((B, H, W, 256), device=dev, dtype=torch.bfloat16)
+    g = torch.randn((B, H, W, 256), device=dev, dtype=torch.bfloat16)
+    dws = [torch.zeros((32, 64 + 32 * i, 3, 3), device=dev) for i in range(5)]
+    flops = sum(2.0 * B * H * W * 9 * (64 + 32 * i) * 32 for i in range(5))
+    ms = bench(lambda: nv.conv3x3_wgrad_grouped(x[..., :192], g[..., 64:224], dws, [], [32 * i for i in range(5)], 1.0))
+    print(f"wgrad grouped dense block: {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
     engines = [ops.CONV_TC, ops.CONV_TC_TAPS]
@@ -110,6 +120,8 @@ if __name__ == "__main__":
         for cout in (64, 96, 128, 160, 192):
             fwd_case(32, cout, 3, 224, 224, engines, accumulate=True, mask=True)
         fwd_case(64, 224, 1, 64, 224, engines)
+    if which in ("grouped", "wgrad", "all"):
+        grouped_case()
     if which in ("wgrad", "all"):
         for cin in (64, 96, 128, 160, 192):
             wgrad_case(cin, 32, 3, 224, 224)
