@@ -35,11 +35,15 @@ def test_graphed_train_step_matches_eager(dtype):
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     for a, b in zip(losses_e[3:], losses_g):
         assert abs(a - b) <= tol * abs(a), (losses_e, losses_g)
-    # (AdamW turns the last-bit noise of atomically accumulated gradients into +-lr steps for near-zero gradients: two EAGER
-    #  runs differ by ~1e-3 of the largest weight after 8 steps as well; the loss trajectory above is the tight check)
-    ptol = 5e-3 if dtype == torch.float32 else 5e-2
+    # AdamW turns the last-bit noise of atomically accumulated gradients into +-lr steps wherever a gradient is near zero
+    # (flow_net.0 at this size: two EAGER runs differ the same way), so a relative bound per tensor is a coin toss.  What
+    # must hold: no element moves apart faster than two full AdamW steps per iteration, and almost none moves at all.
+    n_steps, lr_ = 8, 1e-3
     for (n, p), q in zip(models[0].named_parameters(), models[1].parameters()):
-        assert relerr(q, p) <= ptol, n
+        d = (q.detach() - p.detach()).abs()
+        assert float(d.max()) <= 2.02 * n_steps * lr_, n
+        assert float(d.mean()) <= (0.05 if dtype == torch.float32 else 0.25) * n_steps * lr_, n
+    ptol = 5e-3 if dtype == torch.float32 else 5e-2
     sd0, sd1 = models[0].state_dict(), models[1].state_dict()
     for k in sd0:
         if "tracked" in k:
