@@ -262,7 +262,8 @@ class Plan:
     def pack_rdb_slice_weights(self, P: Dict[str, Tensor]) -> None:
         """Assemble (in fp32, batched over the blocks) and pack the slice-gradient operators described in
         ``__init__``:  W_s[c, (i,o), tap] = W_i[o, c_lo+c, 8-tap] for the later layers i, and for the LFF columns
-        the centre tap 0.2 * W_lff[d, c_lo+c]."""
+        the centre tap 0.2 * W_lff[d, c_lo+c].  The later layers' column groups are in DESCENDING layer order, the
+        order of their gradients in the gradient buffer (``_rdb_backward_fused``)."""
         F, NB = self.F, self.NB
         Wl = [torch.stack([P[f"residual_blocks.{k}.layers.{i}.0.weight"] for k in range(NB)]) for i in range(RDB_LAYERS)]
         Wf = torch.stack([P[f"residual_blocks.{k}.lff.weight"] for k in range(NB)])[..., 0, 0]      # [NB, F, CT]
@@ -273,7 +274,7 @@ class Plan:
             cmain = GROWTH * (RDB_LAYERS - first)
             cols = _align(cmain, 64) + F
             comb = torch.zeros((NB, rows, cols, 3, 3), device=self.device, dtype=torch.float32)
-            for j, i in enumerate(range(first, RDB_LAYERS)):
+            for j, i in enumerate(range(RDB_LAYERS - 1, first - 1, -1)):
                 blk = Wl[i][:, :, c_lo:c_lo + rows]          # [NB, o, c, 3, 3]
                 comb[:, :, j * GROWTH:(j + 1) * GROWTH] = blk.permute(0, 2, 1, 3, 4).flip(3, 4)
             comb[:, :, _align(cmain, 64):, 1, 1] = 0.2 * Wf[:, :, c_lo:c_lo + rows].permute(0, 2, 1)    # [NB, c, d]
@@ -500,37 +501,50 @@ class Plan:
 
     def _rdb_backward_fused(self, k: int, buf: Tensor, g: Tensor, dblock: Tensor, G: Dict[str, Tensor]) -> None:
         """Dense-block backward as 1 + 5 convolutions that each WRITE one slice of the gradient buffer once
-        (no read-modify-write accumulation) followed by one grouped weight-gradient GEMM."""
+        (no read-modify-write accumulation) followed by one grouped weight-gradient GEMM.
+
+        Gradient-buffer layout (differs from the forward buffer's): ``[x | layer 4 | layer 3 | ... | layer 0]``.  The
+        gradient of a slice reads the gradients of ALL LATER layers; in descending order those are the channels
+        ``[F, F + 32 n)`` for every slice, so each 64-channel TMA box row is one aligned 128-byte line (in forward
+        order the later layers of slices 1 and 3 start 64 bytes into a line: 0.05-0.07 ms more per launch,
+        ``scripts/bench_conv.py align``)."""
         F = self.F
         CT = F + RDB_LAYERS * GROWTH
+
+        def gpos(i):                                          # first channel of layer i's output gradient
+            return F + (RDB_LAYERS - 1 - i) * GROWTH
+
         lff = f"residual_blocks.{k}.lff"
         # last slice: only the LFF reaches it.  dy_4 = relu'(o_4) * 0.2 * W_lff[:, slice]^T dblock
         c4 = F + (RDB_LAYERS - 1) * GROWTH
         # (every slice gradient g is the previous layer's output gradient: its per-channel sum, taken in the conv
         #  epilogue, is that layer's bias gradient -- no reduction pass over the gradient buffer)
         names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
+        g4 = gpos(RDB_LAYERS - 1)
         with self._span("conv_dgrad", dblock, F, GROWTH, 1):
-            nv.conv2d_fwd(dblock, self.wb[lff][:, c4:CT, :], None, None, buf[..., c4:CT], None, g[..., c4:CT], GROWTH,
-                          False, False, 0, 0, 0.2, self.engine, None, False, G[names[RDB_LAYERS - 1] + ".bias"])
+            nv.conv2d_fwd(dblock, self.wb[lff][:, c4:CT, :], None, None, buf[..., c4:CT], None, g[..., g4:g4 + GROWTH],
+                          GROWTH, False, False, 0, 0, 0.2, self.engine, None, False, G[names[RDB_LAYERS - 1] + ".bias"])
         for s in range(RDB_LAYERS - 1, -1, -1):              # slices F+(s-1)G .. (s >= 1), then the x slice (s = 0)
             rows = F if s == 0 else GROWTH
-            c_lo = 0 if s == 0 else F + (s - 1) * GROWTH
-            x_lo = F + (0 if s == 0 else s) * GROWTH          # first channel of the later layers' gradients
+            c_lo = 0 if s == 0 else F + (s - 1) * GROWTH      # the slice in the FORWARD buffer (its ReLU mask)
+            first = 0 if s == 0 else s                        # first later layer
+            n_later = GROWTH * (RDB_LAYERS - first)           # their gradients: channels [F, F + n_later)
+            o_lo = 0 if s == 0 else gpos(s - 1)               # where this slice's gradient goes (== F + n_later)
             w = self.wslice[s][:, k * rows:(k + 1) * rows, :]
             mask = buf[..., c_lo:c_lo + rows] if s > 0 else None
             # bytes: later layers' gradients + the block gradient (1x1 branch; + once more as the x slice's residual) in,
             # the slice's ReLU mask in (s > 0), the slice out
-            moved = (CT - x_lo) + F + (F if s == 0 else rows) + rows
-            with self._span_flops(f"conv_dgrad|slice{s}", buf, 2.0 * rows * (9 * (CT - x_lo) + F), moved):
+            moved = n_later + F + (F if s == 0 else rows) + rows
+            with self._span_flops(f"conv_dgrad|slice{s}", buf, 2.0 * rows * (9 * n_later + F), moved):
                 # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
-                nv.conv2d_fwd(g[..., x_lo:CT], w, None, dblock if s == 0 else None, mask, None,
-                              g[..., c_lo:c_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,
+                nv.conv2d_fwd(g[..., F:F + n_later], w, None, dblock if s == 0 else None, mask, None,
+                              g[..., o_lo:o_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,
                               dblock, True, G[names[s - 1] + ".bias"] if s > 0 else None)
         cx = F + (RDB_LAYERS - 1) * GROWTH
         with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
                                                                 for i in range(RDB_LAYERS)), cx + RDB_LAYERS * GROWTH):
             nv.conv3x3_wgrad_grouped(buf[..., :cx], g[..., F:CT], [G[n + ".weight"] for n in names], [],
-                                     [i * GROWTH for i in range(RDB_LAYERS)], 1.0)
+                                     [gpos(i) - F for i in range(RDB_LAYERS)], 1.0)
 
     def backward(self, A: Activations, dout: Tensor, P: Dict[str, Tensor], G: Dict[str, Tensor],
                  on_grads_ready=None) -> None:

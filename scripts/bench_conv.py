@@ -28,7 +28,7 @@ def bench(fn, iters=5):
     return e0.elapsed_time(e1) / iters
 
 
-def fwd_case(cin, cout, k, ld_in, ld_out, engines, accumulate=False, mask=False):
+def fwd_case(cin, cout, k, ld_in, ld_out, engines, accumulate=False, mask=False, c0=0):
     x = torch.randn((B, H, W, ld_in), device=dev, dtype=torch.bfloat16)
     out = torch.zeros((B, H, W, ld_out), device=dev, dtype=torch.bfloat16)
     w = torch.randn((k * k, cout, (cin + 7) // 8 * 8), device=dev, dtype=torch.bfloat16) * 0.05
@@ -39,13 +39,13 @@ def fwd_case(cin, cout, k, ld_in, ld_out, engines, accumulate=False, mask=False)
     for eng in engines:
         try:
             plain = not accumulate and not mask
-            ms = bench(lambda: nv.conv2d_fwd(x[..., :cin], w, bias if plain else None, None,
+            ms = bench(lambda: nv.conv2d_fwd(x[..., c0:c0 + cin], w, bias if plain else None, None,
                                              m[..., :cout] if mask else None, None, out[..., :cout], cout,
                                              plain, accumulate, 0, 0, 1.0, eng))
             res.append(f"{ms:7.3f} ms {flops / ms / 1e9:7.1f} TF")
         except RuntimeError as e:
             res.append(f"unsupported ({str(e)[-30:]})")
-    print(f"fwd {cin:3d}->{cout:3d} k{k} acc={int(accumulate)}: " + " | ".join(res), flush=True)
+    print(f"fwd {cin:3d}->{cout:3d} k{k} acc={int(accumulate)} c0={c0}: " + " | ".join(res), flush=True)
 
 
 def wgrad_case(cin, cout, k, ld_in, ld_dy):
@@ -93,6 +93,10 @@ if __name__ == "__main__":
         fwd_case(128, 64, 3, 128, 64, eng2)
         fwd_case(192, 64, 3, 192, 64, eng2)
         fwd_case(64, 64, 3, 64, 64, eng2)
+    if which == "align":
+        # input channel slice starting on / off a 128-byte line of the 256-channel-pitch buffer (slice gradients)
+        for cin, c0 in ((64, 128), (64, 160), (64, 96), (128, 64), (128, 96), (128, 32)):
+            fwd_case(cin, 32, 3, 256, 256, [ops.CONV_TC], mask=True, c0=c0)
     if which == "layout":
         # same conv, input/output pixel pitch 64/32 (contiguous pixels) vs 256 (channel slices of a wide buffer)
         for cin in (64, 128, 192):

@@ -635,10 +635,12 @@ def test_conv_wgrad_tcgen05(shape):
     assert relerr(db, 0.5 * b.grad) <= 1e-3
 
 
+@pytest.mark.parametrize("descending", [False, True])
 @pytest.mark.parametrize("shape", [(1, 20, 200), (2, 33, 128), (1, 9, 640), (1, 360, 640)])
-def test_conv3x3_wgrad_grouped_dense_block(shape):
+def test_conv3x3_wgrad_grouped_dense_block(shape, descending):
     """One GEMM for the weight/bias gradients of the five dense-block layers (channel-prefix inputs of one
-    buffer, adjacent output-gradient slices) == five separate ATen convolution_backward calls."""
+    buffer, adjacent output-gradient slices) == five separate ATen convolution_backward calls.  ``descending``: the
+    layers' gradient slices in descending layer order (the engine's gradient-buffer layout)."""
     n, h, w = shape
     g = torch.Generator().manual_seed(sum(shape) + 31)
     buf = bf(torch.randn(n, 224, h, w, generator=g))
@@ -646,8 +648,10 @@ def test_conv3x3_wgrad_grouped_dense_block(shape):
     dws = [torch.zeros(32, 64 + 32 * i, 3, 3, device="cuda") for i in range(5)]
     dbs = [torch.zeros(32, device="cuda") for _ in range(5)]
     xb = nhwc(buf, torch.bfloat16, pad_to=256)
-    gb = nhwc(torch.cat([torch.zeros(n, 64, h, w), dy], 1), torch.bfloat16, pad_to=256)
-    nv().conv3x3_wgrad_grouped(xb[..., :192], gb[..., 64:224], dws, dbs, [32 * i for i in range(5)], 0.5)
+    col0 = [32 * (4 - i) if descending else 32 * i for i in range(5)]
+    dy_buf = torch.cat([dy[:, 32 * i:32 * i + 32] for i in sorted(range(5), key=lambda i: col0[i])], 1)
+    gb = nhwc(torch.cat([torch.zeros(n, 64, h, w), dy_buf], 1), torch.bfloat16, pad_to=256)
+    nv().conv3x3_wgrad_grouped(xb[..., :192], gb[..., 64:224], dws, dbs, col0, 0.5)
     for i in range(5):
         cin = 64 + 32 * i
         wt = torch.zeros(32, cin, 3, 3, requires_grad=True)
