@@ -73,6 +73,7 @@ struct WgArgs {
   int stages;
   float scale;
   float* dw;
+  float* db;         // bias gradient taken in-kernel from the dY tiles (drain warps of M group 0), or nullptr
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -109,7 +110,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&dyfull_bar[s], 1);
-      mbar_init(&dyempty_bar[s], 1);
+      mbar_init(&dyempty_bar[s], a.db ? 5 : 1);      // the MMA commit (+ the four column-sum warps)
     }
     mbar_init(done_bar, 1);
     fence_barrier_init();
@@ -190,6 +191,33 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int row = q * 32 + lane;
     const int half = row >> 6, ci_local = row & 63;
     const bool any_tile = split < num_tiles;
+    if (a.db) {
+      // Bias gradient db[co] = scale * sum_p dY[p, co] while the main loop runs: these warps are idle until the drain,
+      // and every dY tile passes through shared memory anyway (128 pixel rows of 64 channels, 128B swizzle) -- a
+      // separate reduction pass would read dY from HBM a second time.  Lane <-> channel pair, warp <-> 32 pixel rows.
+      float s0 = 0.f, s1 = 0.f;
+      int it = 0;
+      for (int tile = split; tile < num_tiles; tile += nsplit, ++it) {
+        const int db = it & 1;
+        mbar_wait(&dyfull_bar[db], (it >> 1) & 1);
+        if (mg == 0) {
+          const uint8_t* t = dy_smem + (size_t)db * dy_bytes;
+#pragma unroll 8
+          for (int r = q * 32; r < q * 32 + 32; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(t + r * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) +
+                                                                   (((uint32_t)lane & 3u) << 2));
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dyempty_bar[db]);
+      }
+      if (mg == 0 && any_tile) {
+        if (2 * lane < a.Cout) atomicAdd(a.db + 2 * lane, a.scale * s0);
+        if (2 * lane + 1 < a.Cout) atomicAdd(a.db + 2 * lane + 1, a.scale * s1);
+      }
+    }
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int KK = a.K * a.K;
@@ -257,6 +285,8 @@ int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float
   a.tiles_y = (H + BH - 1) / BH;
   a.scale = scale;
   a.dw = dw;
+  // in-kernel bias gradient: one 128-byte dY box per tile (Cout in (32, 64]); out-of-image pixels are zero-filled
+  a.db = (db && a.dy_row_bytes == 128 && a.nb_blocks == 1) ? db : nullptr;
 
   CUtensorMap tx, td;
   {
@@ -297,7 +327,7 @@ int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float
   conv_tc_wgrad_kernel<<<grid, kThreads, smem, s>>>(tx, td, a);
   int rc = launch_status();
   if (rc) return rc;
-  if (!db) return NERVECL_OK;
+  if (!db || a.db) return NERVECL_OK;
   if (Cout % 4 == 0)
     return nervecl_chan_sum(dy, ldy, NERVECL_BF16, 1, (int64_t)N * H * W, Cout, scale, db, (nervecl_stream_t)s);
   const int64_t npix = (int64_t)N * H * W;
