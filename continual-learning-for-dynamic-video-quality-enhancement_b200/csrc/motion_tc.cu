@@ -191,15 +191,9 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // Per 8 x 16 pixel tile this is ONE GEMM  D[128 px, 64 ch] = A[128, 384] * B[384, 64]:  B = the 16 x 24 pixel region of
 // X exactly as its TMA box lands in shared memory (region pixel = K row, 64 channels contiguous: the MN-major operand
 // layout), A = the tile's gradients scattered onto the region (A[p, q] = G[p, d(q - p)], zero where q is out of reach).
-// The sparsity pattern of A depends only on the position inside the tile, so A is zeroed once per CTA and every tile
-// overwrites the same 81 entries per row with 2-byte stores in the K-major 128B-swizzled layout.  24 k-steps of
-// N = 64 are shared-memory fed (6 KB per MMA): ~1150 cycles per tile, against ~9000 per 128 pixels for the
-// mma.sync version; the 128 builder threads prefetch the next tile's gradients while the MMAs of this one run and
-// drain the previous tile's accumulator (two 64-column TMEM buffers) after they have rebuilt A.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr uint32_t GA_CHUNK = TY * TX * ROWB;        // one 64-wide K chunk of A: 128 rows x 128 B = 16 KB
-constexpr uint32_t GA_BYTES = (RY * RX / 64) * GA_CHUNK;   // 6 chunks = 96 KB
-constexpr int kGradStages = 2;
+// Row i of a pixel's 9 x 9 gradient block is NINE CONSECUTIVE K entries of its A row (k = k0 + 24 i + j, j = 0..8), and
+// 24 i is a multiple of 8, so every run starts at element px % 8 of a 16-byte "unit" (8 bf16): the nine values are
+// shifted into place in registers and occupy two units; no other row of the pixel touches those units.
 
 struct GradArgs {
   const bf16* g;
@@ -220,29 +214,54 @@ __device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr) {     // MN-maj
   return d;
 }
 
-// Builders / drainers of the gradient kernel.  Thread <-> tile pixel p = TMEM lane; two warps share a lane quarter:
-// warp group H builds the displacement rows [5H, 5 + 4H) of A and drains the accumulator columns [32H, 32H + 32).
+// A lives in TENSOR MEMORY (tcgen05.mma with a TMEM A operand: lane = row, two bf16 per 32-bit column): the builders write
+// their pixel's row of A with tcgen05.st -- no shared-memory round trip, no swizzle, no proxy fence -- A is double
+// buffered (2 x 192 columns next to the two 64-column accumulators = all 512 columns), so the build of tile t + 1
+// overlaps the MMAs of tile t, and the MMAs read only B from shared memory (2 KB instead of 6 KB per k-step), which
+// leaves room for four B stages.
 //
-// Row i of a pixel's 9 x 9 gradient block is NINE CONSECUTIVE K entries of its A row (k = k0 + 24 i + j, j = 0..8), and
-// 24 i is a multiple of 8, so the run starts at element px % 8 of a 16-byte unit in every row i: the nine bf16 are
-// shifted into place in registers (16 halfword slots = two units; the other seven stay zero, and no other row of the
-// pixel touches those units) and leave as TWO 16-byte stores -- 18 per pixel and tile instead of 81 2-byte stores whose
-// 4-way bank conflicts and address arithmetic made the build 3x longer than the MMAs it feeds.  The eight lanes of a
-// quarter warp write the same logical unit of eight consecutive rows, which the 128B swizzle spreads over all banks.
+// tcgen05.st writes the SAME columns for all 32 lanes of a warp, but a pixel's runs start at unit 3 py + px / 8, which
+// takes four values c = 3 (lane / 16) + (lane % 16) / 8 in {0, 1, 3, 4} (+ 6 q) inside a warp.  Every lane therefore
+// assembles a 15-unit (60-column) image of its part of the row in registers -- each run OR-ed in at each of the four
+// candidate positions under a lane mask -- and the warp stores the image at a warp-uniform address.  Warp group H owns
+// the units [15 H, 15 H + 15) relative to 6 q (no run straddles a multiple of 3 because c = 2 does not occur):
+// displacement rows 0..4 (row 4 only for c <= 1) for H = 0, rows 4 (c >= 3)..8 for H = 1.
+//
+// Measured (clock64, cfg-2 shape): the build is bound by the integer pipe's THROUGHPUT (~450 SEL / LOP3 / SHF per
+// pixel and tile, two builder warps per scheduler: ~1900 cycles per tile); four groups per quarter (16 warps, 12
+// instead of 10 shifted rows) were 28 % slower.  MMAs (24 x 32 cycles) and the 48 KB of TMA per tile hide behind it.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTsStages = 4;
+constexpr int kTsBuild = 8;                          // builder / drain warps (two per TMEM lane quarter)
+constexpr int kTsThreads = 32 * (2 + kTsBuild);
+constexpr uint32_t TS_D = 0, TS_A = 128, TS_ACOLS = RY * RX / 2;      // TMEM columns: accumulators, A buffers (192 each)
+
 template <int H>
-__device__ __forceinline__ void corr_grad_builder(const GradArgs& a, uint8_t* sA, uint64_t* a_full, uint64_t* a_free,
-                                                  uint64_t* acc_full, uint64_t* acc_empty, uint32_t tmem_base, int q, int lane,
-                                                  int64_t ntiles) {
-  constexpr int I0 = H ? 5 : 0, I1 = H ? ND : 5;
-  constexpr int Q0 = (I0 * ND / 2) / 4;              // first 16-byte chunk of the pixel's gradient row this group reads
-  constexpr int NQ = 6;                              // H = 0: halfwords 0..44 (chunks 0..5); H = 1: 45..80 (chunks 5..10)
+__device__ __forceinline__ void corr_grad_ts_builder(const GradArgs& a, uint64_t* a_full, uint64_t* a_free, uint64_t* acc_full,
+                                                     uint64_t* acc_empty, uint32_t tmem_base, int q, int lane, int64_t ntiles) {
+  constexpr int U0 = 15 * H, U1 = U0 + 15;
+  constexpr int NW = (U1 - U0) * 4;                  // image words (TMEM columns): 60
+  constexpr int I0 = H ? 4 : 0, I1 = H ? ND : 5;     // displacement rows this group touches
+  constexpr int Q0 = H ? 4 : 0, NQ = H ? 7 : 6;      // 16-byte chunks of the pixel's gradient row it reads
   const int p = q * 32 + lane;
   const int py = p >> 4, px = p & 15;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + 32u * H;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t img_col = TS_A + (uint32_t)(6 * q + U0) * 4u;         // first column of this group's image (buffer 0)
   const float inv_c = 1.f / (float)C;
-  uint8_t* arow = sA + (uint32_t)p * ROWB;
-  const uint32_t u0 = (uint32_t)(py * RX + px) >> 3;  // first 16-byte unit of displacement row 0
   const bool b0 = px & 1, b1 = px & 2, b2 = px & 4;
+  const int cl = 3 * (lane >> 4) + ((lane & 15) >> 3);
+  const uint32_t mk[4] = {cl == 0 ? ~0u : 0u, cl == 1 ? ~0u : 0u, cl == 3 ? ~0u : 0u, cl == 4 ? ~0u : 0u};
+  // The units outside [6q, 6q + 30) of this quarter's lanes are never written: zero them once in both buffers (group 0
+  // the ones below, group 1 the ones above; everything inside the range is rewritten for every tile by its owner).
+  {
+    const uint32_t zero4[4] = {0u, 0u, 0u, 0u};
+    const int u_lo = H ? 6 * q + 30 : 0, u_hi = H ? RY * RX / 8 : 6 * q;
+    for (int u = u_lo; u < u_hi; ++u) {
+      tmem_st4(lane_base + TS_A + (uint32_t)u * 4u, zero4);
+      tmem_st4(lane_base + TS_A + TS_ACOLS + (uint32_t)u * 4u, zero4);
+    }
+    tmem_st_wait();
+  }
   uint4 gq[NQ];
   auto fetch = [&](int64_t t) {
     const int tx = (int)(t % a.tiles_x);
@@ -254,7 +273,6 @@ __device__ __forceinline__ void corr_grad_builder(const GradArgs& a, uint8_t* sA
 #pragma unroll
     for (int c = 0; c < NQ; ++c) gq[c] = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
   };
-  // the 32 output channels of the previous tile's pixel (accumulate mode): requested before the build, used after it
   uint4 accq[4];
   bf16* dp = nullptr;
   auto locate = [&](int tx, int ty, int n) {
@@ -270,17 +288,13 @@ __device__ __forceinline__ void corr_grad_builder(const GradArgs& a, uint8_t* sA
     mbar_wait(&acc_full[ab], (jt >> 1) & 1u);
     tc_fence_after();
     uint32_t v[2][16];
-    tmem_ld16(lane_addr + ab * 64u, v[0]);
-    tmem_ld16(lane_addr + ab * 64u + 16u, v[1]);
+    tmem_ld16(lane_base + TS_D + ab * 64u + 32u * H, v[0]);
+    tmem_ld16(lane_base + TS_D + ab * 64u + 32u * H + 16u, v[1]);
     tmem_ld_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&acc_empty[ab]);
-#ifdef CG_NO_DRAIN
-    if (dp && v[0][0] == 0x12345678u) {
-#else
     if (dp) {
-#endif
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         f16v o;
@@ -309,9 +323,11 @@ __device__ __forceinline__ void corr_grad_builder(const GradArgs& a, uint8_t* sA
     uint32_t w[NQ * 4];
 #pragma unroll
     for (int c = 0; c < NQ; ++c) { w[4 * c] = gq[c].x; w[4 * c + 1] = gq[c].y; w[4 * c + 2] = gq[c].z; w[4 * c + 3] = gq[c].w; }
+    fetch(t + gridDim.x);
     if (it > 0) locate(ptx, pty, pn);
-    mbar_wait(a_free, (it & 1u) ^ 1u);              // the MMAs of the previous tile have read A
-#ifndef CG_NO_BUILD
+    uint32_t img[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) img[m] = 0u;
 #pragma unroll
     for (int i = I0; i < I1; ++i) {
       // the nine halfwords 9i .. 9i+8 of the gradient row, right-aligned into five words
@@ -338,17 +354,27 @@ __device__ __forceinline__ void corr_grad_builder(const GradArgs& a, uint8_t* sA
       for (int m = 0; m < 7; ++m) y7[m] = b1 ? (m > 0 ? x6[m - 1] : 0u) : (m < 6 ? x6[m] : 0u);
 #pragma unroll
       for (int m = 0; m < 8; ++m) z[m] = b2 ? (m > 1 ? y7[m - 2] : 0u) : (m < 7 ? y7[m] : 0u);
-      const uint32_t ua = u0 + 3u * (uint32_t)i, ub = ua + 1u;
-      *reinterpret_cast<uint4*>(arow + (ua >> 3) * GA_CHUNK + (((ua & 7u) ^ (uint32_t)(p & 7)) << 4)) = make_uint4(z[0], z[1], z[2], z[3]);
-      *reinterpret_cast<uint4*>(arow + (ub >> 3) * GA_CHUNK + (((ub & 7u) ^ (uint32_t)(p & 7)) << 4)) = make_uint4(z[4], z[5], z[6], z[7]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = ci < 2 ? ci : ci + 1;             // 0, 1, 3, 4
+        const int unit = 3 * i + c - U0;                // relative to this group's image
+        if (unit < 0 || unit + 1 >= U1 - U0) continue;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) img[unit * 4 + m] |= z[m] & mk[ci];
+      }
     }
-#else
-    if (w[0] == 0x12345678u) arow[0] = 1;
-#endif
-    fence_proxy_async();
+    const uint32_t ab = it & 1u;
+    mbar_wait(&a_free[ab], ((it >> 1) & 1u) ^ 1u);    // the MMAs of tile it - 2 have read this A buffer
+    tc_fence_after();
+    const uint32_t dst = lane_base + img_col + ab * TS_ACOLS;
+    tmem_st32(dst, img);
+    tmem_st16(dst + 32u, img + 32);
+    tmem_st8(dst + 48u, img + 48);
+    tmem_st4(dst + 56u, img + 56);
+    tmem_st_wait();
+    tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(a_full);
-    fetch(t + gridDim.x);
+    if (lane == 0) mbar_arrive(&a_full[ab]);
     if (it > 0) drain(it - 1);
     ptx = tx; pty = ty; pn = n;
   }
@@ -358,43 +384,37 @@ __device__ __forceinline__ void corr_grad_builder(const GradArgs& a, uint8_t* sA
   }
 }
 
-constexpr int kGradBuild = 8;                        // builder / drain warps (two per TMEM lane quarter)
-constexpr int kGradThreads = 32 * (2 + kGradBuild);
-
-__global__ void __launch_bounds__(kGradThreads, 1)
-corr_grad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GradArgs a) {
+__global__ void __launch_bounds__(kTsThreads, 1)
+corr_grad_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const GradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                                                  // [6][128 rows][128 B]
-  uint8_t* sB = smem + GA_BYTES;                                       // [kGradStages][384 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kGradStages * B_BYTES);
-  uint64_t* b_full = bars;                       // [2] TMA -> MMA
-  uint64_t* b_empty = b_full + kGradStages;      // [2] MMA -> TMA
-  uint64_t* a_full = b_empty + kGradStages;      // builders -> MMA
-  uint64_t* a_free = a_full + 1;                 // MMA -> builders
-  uint64_t* acc_full = a_free + 1;               // [2] MMA -> epilogue
+  uint8_t* sB = smem;                                                  // [kTsStages][384 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTsStages * B_BYTES);
+  uint64_t* b_full = bars;                       // [kTsStages] TMA -> MMA
+  uint64_t* b_empty = b_full + kTsStages;        // [kTsStages] MMA -> TMA
+  uint64_t* a_full = b_empty + kTsStages;        // [2] builders -> MMA
+  uint64_t* a_free = a_full + 2;                 // [2] MMA -> builders
+  uint64_t* acc_full = a_free + 2;               // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = (int64_t)a.N * a.tiles_y * a.tiles_x;
 
-  for (uint32_t e = threadIdx.x; e < GA_BYTES / 16; e += kGradThreads) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
-    for (int s = 0; s < kGradStages; ++s) {
+    for (int s = 0; s < kTsStages; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    mbar_init(a_full, kGradBuild);
-    mbar_init(a_free, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], kTsBuild);
+      mbar_init(&a_free[s], 1);
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kGradBuild);
+      mbar_init(&acc_empty[s], kTsBuild);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
-  fence_proxy_async();                              // the zero fill of A is visible to the tensor core
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -409,17 +429,13 @@ corr_grad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GradArgs a
         const int64_t r = t / a.tiles_x;
         const int ty = (int)(r % a.tiles_y), n = (int)(r / a.tiles_y);
         mbar_wait(&b_empty[stage], phase ^ 1);
-#ifdef CG_NO_TMA
-        mbar_arrive(&b_full[stage]);
-#else
         mbar_expect_tx(&b_full[stage], B_BYTES);
         tma_load_4d(sB + (size_t)stage * B_BYTES, &tmap_x, &b_full[stage], 0, tx * TX - 4, ty * TY - 4, n);
-#endif
-        if (++stage == kGradStages) { stage = 0; phase ^= 1; }
+        if (++stage == kTsStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // A K-major (bit 15 clear), B MN-major (bit 16), D fp32, M = 128, N = 64
+    // A from tensor memory (K-major), B MN-major (bit 16), D fp32, M = 128, N = 64
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
@@ -428,35 +444,31 @@ corr_grad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const GradArgs a
       const uint32_t ab = it & 1u;
       mbar_wait(&acc_empty[ab], ((it >> 1) & 1u) ^ 1u);
       mbar_wait(&b_full[stage], phase);
-      mbar_wait(a_full, it & 1u);
+      mbar_wait(&a_full[ab], (it >> 1) & 1u);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sa = smem_u32(sA), sb = smem_u32(sB + (size_t)stage * B_BYTES);
+        const uint32_t sb = smem_u32(sB + (size_t)stage * B_BYTES);
+        const uint32_t ta = tmem_base + TS_A + ab * TS_ACOLS;
 #pragma unroll 4
-        for (int ks = 0; ks < RY * RX / 16; ++ks) {
-          const uint64_t da = make_kmajor_desc(sa + (uint32_t)(ks >> 2) * GA_CHUNK, ROWB) + 2u * (uint32_t)(ks & 3);
-          const uint64_t db = make_mn_desc(sb + (uint32_t)ks * 16u * ROWB);
-#ifndef CG_NO_MMA
-          umma_bf16(tmem_base + ab * 64u, da, db, idesc, ks > 0);
-#endif
-        }
+        for (int ks = 0; ks < RY * RX / 16; ++ks)
+          umma_bf16_ts(tmem_base + TS_D + ab * 64u, ta + 8u * (uint32_t)ks, make_mn_desc(sb + (uint32_t)ks * 16u * ROWB), idesc, ks > 0);
         umma_commit(&b_empty[stage]);
-        umma_commit(a_free);
+        umma_commit(&a_free[ab]);
         umma_commit(&acc_full[ab]);
       }
       __syncwarp();
-      if (++stage == kGradStages) { stage = 0; phase ^= 1; }
+      if (++stage == kTsStages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp & 3;
-    if (warp < 6) corr_grad_builder<0>(a, sA, a_full, a_free, acc_full, acc_empty, tmem_base, q, lane, ntiles);
-    else          corr_grad_builder<1>(a, sA, a_full, a_free, acc_full, acc_empty, tmem_base, q, lane, ntiles);
+    if (warp < 6) corr_grad_ts_builder<0>(a, a_full, a_free, acc_full, acc_empty, tmem_base, q, lane, ntiles);
+    else          corr_grad_ts_builder<1>(a, a_full, a_free, acc_full, acc_empty, tmem_base, q, lane, ntiles);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -599,10 +611,10 @@ static int corr_grad_tc(const void* X, int64_t ldX, const void* g, int64_t ldg, 
   a.tiles_x = (W + TX - 1) / TX;
   a.tiles_y = (H + TY - 1) / TY;
   const int64_t ntiles = (int64_t)N * a.tiles_x * a.tiles_y;
-  const size_t smem = 1024 + GA_BYTES + (size_t)kGradStages * B_BYTES + 16 * sizeof(uint64_t);
-  cudaError_t e = cudaFuncSetAttribute(corr_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = 1024 + (size_t)kTsStages * B_BYTES + 24 * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(corr_grad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  corr_grad_tc_kernel<<<(unsigned)imin(ntiles, sm_count()), kGradThreads, smem, s>>>(tx, a);
+  corr_grad_ts_kernel<<<(unsigned)imin(ntiles, sm_count()), kTsThreads, smem, s>>>(tx, a);
   return launch_status();
 }
 
