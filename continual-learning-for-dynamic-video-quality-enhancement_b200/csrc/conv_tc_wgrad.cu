@@ -71,6 +71,7 @@ struct WgArgs {
   int MG;            // number of M groups
   int bw_shift, tiles_x, tiles_y;
   int stages;
+  int ndy;           // dY tile buffers in flight (2 .. 6)
   float scale;
   float* dw;
   float* db;         // bias gradient taken in-kernel from the dY tiles (drain warps of M group 0), or nullptr
@@ -85,12 +86,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   const uint32_t dyblk_bytes = BM * (uint32_t)a.dy_row_bytes;
   const uint32_t dy_bytes = dyblk_bytes * (uint32_t)a.nb_blocks;
   uint8_t* dy_smem = smem + (size_t)a.stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dy_smem + 2 * (size_t)dy_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dy_smem + (size_t)a.ndy * dy_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + a.stages;
-  uint64_t* dyfull_bar = bars + 2 * a.stages;      // [2]
-  uint64_t* dyempty_bar = dyfull_bar + 2;          // [2]
-  uint64_t* done_bar = dyempty_bar + 2;            // [1]
+  uint64_t* dyfull_bar = bars + 2 * a.stages;      // [ndy]
+  uint64_t* dyempty_bar = dyfull_bar + a.ndy;      // [ndy]
+  uint64_t* done_bar = dyempty_bar + a.ndy;        // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,7 +109,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < a.ndy; ++s) {
       mbar_init(&dyfull_bar[s], 1);
       mbar_init(&dyempty_bar[s], a.db ? 5 : 1);      // the MMA commit (+ the four column-sum warps)
     }
@@ -133,8 +134,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         int ty = r % a.tiles_y;
         int n = r / a.tiles_y;
         int x0 = tx << a.bw_shift, y0 = ty * (BM >> a.bw_shift);
-        const int db = it & 1;
-        mbar_wait(&dyempty_bar[db], ((it >> 1) & 1) ^ 1);
+        const int db = it % a.ndy;
+        mbar_wait(&dyempty_bar[db], ((it / a.ndy) & 1) ^ 1);
         mbar_expect_tx(&dyfull_bar[db], dy_bytes);
         for (int b = 0; b < a.nb_blocks; ++b)
           tma_load_4d(dy_smem + (size_t)db * dy_bytes + (size_t)b * dyblk_bytes, &tmap_dy, &dyfull_bar[db], b * 64, x0,
@@ -163,8 +164,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       uint32_t phase = 0;
       int it = 0;
       for (int tile = split; tile < num_tiles; tile += nsplit, ++it) {
-        const int db = it & 1;
-        mbar_wait(&dyfull_bar[db], (it >> 1) & 1);
+        const int db = it % a.ndy;
+        mbar_wait(&dyfull_bar[db], (it / a.ndy) & 1);
         tc_fence_after();
         const uint32_t sb = smem_u32(dy_smem + (size_t)db * dy_bytes);
         for (int pl = 0; pl < npairs; ++pl) {
@@ -198,8 +199,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       float s0 = 0.f, s1 = 0.f;
       int it = 0;
       for (int tile = split; tile < num_tiles; tile += nsplit, ++it) {
-        const int db = it & 1;
-        mbar_wait(&dyfull_bar[db], (it >> 1) & 1);
+        const int db = it % a.ndy;
+        mbar_wait(&dyfull_bar[db], (it / a.ndy) & 1);
         if (mg == 0) {
           const uint8_t* t = dy_smem + (size_t)db * dy_bytes;
 #pragma unroll 8
@@ -312,11 +313,17 @@ int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float
   }
 
   const size_t dy_bytes = (size_t)BM * a.dy_row_bytes * a.nb_blocks;
-  int stages = (int)((208 * 1024 - 2 * dy_bytes) / (2 * XBOX_BYTES));
+  // X stages: one per (tap, chunk) pair in flight.  A CTA with ONE pair per tile (1x1 convs over <= 128 channels)
+  // runs through a tile per stage, so two dY buffers cap it at two tiles in flight: five there (0.53 -> 0.49 ms for the
+  // extractor's pointwise / head weight gradients); with two pairs per tile the extra X stage is worth more.
+  const int pairs_per_tile = a.G < a.pairs ? a.G : a.pairs;
+  a.ndy = pairs_per_tile == 1 ? 5 : 2;
+  int stages = (int)((208 * 1024 - a.ndy * dy_bytes) / (2 * XBOX_BYTES));
   if (stages > 6) stages = 6;
+  if (stages < 2) { a.ndy = 2; stages = (int)((208 * 1024 - 2 * dy_bytes) / (2 * XBOX_BYTES)); if (stages > 6) stages = 6; }
   if (stages < 2) return NERVECL_EUNSUPPORTED;
   a.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * 2 * XBOX_BYTES + 2 * dy_bytes + (2 * stages + 5) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + (size_t)stages * 2 * XBOX_BYTES + a.ndy * dy_bytes + (2 * stages + 2 * a.ndy + 1) * sizeof(uint64_t) + 16;
 
   const int64_t num_tiles = (int64_t)N * a.tiles_y * a.tiles_x;
   const int sms = sm_count();

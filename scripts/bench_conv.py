@@ -130,3 +130,11 @@ if __name__ == "__main__":
         for cin in (64, 96, 128, 160, 192):
             wgrad_case(cin, 32, 3, 224, 224)
         wgrad_case(224, 64, 1, 224, 64)
+    if which == "wgrad1":
+        # 1x1 weight gradients of the step: extractor pointwise and head conv (48 images), LFF (16 images)
+        B_save = B
+        globals()["B"] = 3 * B_save
+        wgrad_case(64, 64, 1, 64, 64)
+        wgrad_case(27, 64, 1, 32, 64)
+        globals()["B"] = B_save
+        wgrad_case(224, 64, 1, 256, 64)
