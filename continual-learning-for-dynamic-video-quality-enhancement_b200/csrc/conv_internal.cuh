@@ -34,7 +34,7 @@ int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float
 bool wgrad_rows_supported(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype, int N, int H, int W, int Cx,
                           int Cy);
 int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, int H, int W, int Cx, int Cy, int ngroups,
-               const int32_t* col0, const int32_t* ncols, const int32_t* cin, float* const* dw, float scale,
+               const int32_t* col0, const int32_t* ncols, const int32_t* cin, float* const* dw, float* const* db, float scale,
                cudaStream_t s);
 
 }  // namespace nv

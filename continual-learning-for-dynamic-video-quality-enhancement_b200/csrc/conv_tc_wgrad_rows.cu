@@ -21,9 +21,6 @@
 using namespace nv;
 using namespace nv::tc;
 
-extern "C" int nervecl_chan_sum(const void* x, int64_t ldx, int dtype, int N, int64_t pix_per_image, int C,
-                                float scale, float* out, nervecl_stream_t stream);
-
 namespace {
 
 constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 drain
@@ -46,7 +43,7 @@ constexpr int kStages = WG_STAGES;
 constexpr int kMaxGroups = 8;
 constexpr int kMaxClasses = 12;
 
-struct WgGroup { int col0, ncols, cin; float* dw; };
+struct WgGroup { int col0, ncols, cin; float* dw; float* db; };
 
 struct WgrArgs {
   int N, H, W, Cx, strips;
@@ -60,67 +57,9 @@ struct WgrArgs {
   // channels of input row y + ky2 - 1 (-1: none), so its three taps need two classes instead of three
   int c_ky2[kMaxClasses];
   int stages;
+  int bias;            // some group has a bias gradient: the drain warps of class 0 sum the dY tiles while the MMAs run
   float scale;
 };
-
-// bias gradient of a group whose column count / offset is not a multiple of 4 (<= 32 columns):
-// db[c] += scale * sum_p dy[p, c]
-__global__ void __launch_bounds__(256)
-colsum_any_kernel(const bf16* __restrict__ dy, int64_t ldy, int64_t npix, int ncols, float scale, float* __restrict__ db) {
-  float acc[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < ncols) acc[c] += ldf(dy + p * ldy + c);
-  }
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    if (c < ncols) {
-      const float v = warp_sum(acc[c]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(db + c, scale * v);
-    }
-  }
-}
-
-// All bias gradients of a grouped call in ONE pass over dy (Cy % 8 == 0): db_g[o] += scale * sum_p dy[p, col0_g + o].
-// A thread owns 8 channels of every (256 / (Cy/8))-th pixel; block partials go through shared memory.
-struct BiasTable { int ngroups; int col0[kMaxGroups], ncols[kMaxGroups]; float* db[kMaxGroups]; };
-
-__global__ void __launch_bounds__(256)
-colsum_scatter_kernel(const bf16* __restrict__ dy, int64_t ldy, int64_t npix, int Cy, float scale, const BiasTable tab) {
-  extern __shared__ float red[];          // [Cy]
-  const int cg = Cy >> 3;
-  const int lanes = 256 / cg;
-  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  if (lane < lanes) {
-    for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < npix; p += (int64_t)gridDim.x * lanes) {
-      const f8 v = ld8(dy + p * ldy + 8 * g);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
-    }
-  }
-  for (int i = threadIdx.x; i < Cy; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  if (lane < lanes) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&red[8 * g + k], acc[k]);
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < Cy; c += blockDim.x) {
-    for (int q = 0; q < tab.ngroups; ++q) {
-      const int o = c - tab.col0[q];
-      if (o >= 0 && o < tab.ncols[q]) {
-        if (tab.db[q]) atomicAdd(tab.db[q] + o, scale * red[c]);
-        break;
-      }
-    }
-  }
-}
 
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -160,7 +99,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     prefetch_tmap(&tmap_dy);
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (a.bias && cls == 0) ? 5 : 1);      // the MMA commit (+ the four column-sum warps)
     }
     mbar_init(done_bar, 1);
     fence_barrier_init();
@@ -241,6 +180,50 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int c = mt * 128 + q * 32 + lane - (upper ? 64 : 0);   // input channel of this lane
     const int kyl = upper ? ky2 : ky;
     const bool any = idx < row_tiles;
+    if (a.bias && cls == 0) {
+      // Bias gradients db_g[o] = scale * sum_p dY[p, col0_g + o]: class 0 (M tile 0: every group feeds it) walks over
+      // every dY row tile once, and these warps are idle until the drain -- so they sum the tiles in shared memory
+      // instead of a second pass over dY in HBM.  Lane <-> channel pair of each 64-channel chunk, warp <-> 32 pixel rows.
+      float bs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t rt = idx; rt < row_tiles; rt += nctas) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* sy = smem + (size_t)stage * stage_bytes + 2 * XCHUNK;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          if (cc < nby) {
+#pragma unroll 8
+            for (int r = q * (KPX / 4); r < (q + 1) * (KPX / 4); ++r) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(sy + (size_t)cc * YCHUNK + r * ROWB +
+                                                                     ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2));
+              bs[cc][0] += __uint_as_float(w << 16);
+              bs[cc][1] += __uint_as_float(w & 0xFFFF0000u);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      if (any) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          if (cc >= nby) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = col0 + cc * KC + 2 * lane + h;
+            for (int g = 0; g < a.ngroups; ++g) {
+              const int o = col - a.grp[g].col0;
+              if (o >= 0 && o < a.grp[g].ncols) {
+                if (a.grp[g].db) atomicAdd(a.grp[g].db + o, a.scale * bs[cc][h]);
+                break;
+              }
+            }
+          }
+        }
+      }
+    }
     mbar_wait(done_bar, 0);
     tc_fence_after();
     if (any) {
@@ -292,7 +275,7 @@ bool wgrad_rows_supported(const void* x, int64_t ldx, const void* dy, int64_t ld
 
 // groups must be sorted by ascending cin (so that the columns an M tile needs are a suffix)
 int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, int H, int W, int Cx, int Cy, int ngroups,
-               const int32_t* col0, const int32_t* ncols, const int32_t* cin, float* const* dw, float scale,
+               const int32_t* col0, const int32_t* ncols, const int32_t* cin, float* const* dw, float* const* db, float scale,
                cudaStream_t s) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return NERVECL_EUNSUPPORTED;
@@ -301,10 +284,12 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
   a.N = N; a.H = H; a.W = W; a.Cx = Cx; a.strips = (W + KPX - 1) / KPX;
   a.ngroups = ngroups;
   a.scale = scale;
+  a.bias = 0;
   for (int g = 0; g < ngroups; ++g) {
     if (g && cin[g] < cin[g - 1]) return NERVECL_EINVAL;
     if (col0[g] < 0 || col0[g] + ncols[g] > Cy || cin[g] > Cx || !dw[g]) return NERVECL_EINVAL;
-    a.grp[g] = WgGroup{col0[g], ncols[g], cin[g], dw[g]};
+    a.grp[g] = WgGroup{col0[g], ncols[g], cin[g], dw[g], db ? db[g] : nullptr};
+    a.bias = a.bias || (db && db[g]);
   }
   const int sms = sm_count();
   const int MT = (Cx + 127) / 128;
@@ -392,39 +377,5 @@ NV_API int nervecl_conv3x3_wgrad_grouped(const void* x, int64_t ldx, const void*
   if (N <= 0 || H <= 0 || W <= 0 || Cx <= 0 || Cy <= 0 || ldx < Cx || ldy < Cy) return NERVECL_EINVAL;
   if (!wgrad_rows_supported(x, ldx, dy, ldy, dtype, N, H, W, Cx, Cy)) return NERVECL_EUNSUPPORTED;
   cudaStream_t s = as_stream(stream);
-  int rc = wgrad_rows(x, ldx, dy, ldy, N, H, W, Cx, Cy, ngroups, col0_host, ncols_host, cin_host, dw_host, scale, s);
-  if (rc) return rc;
-  if (db_host && ngroups > 1 && Cy % 8 == 0 && Cy <= 256 && aligned(dy, 16) && ldy % 8 == 0) {
-    BiasTable tab;
-    tab.ngroups = ngroups;
-    bool any = false;
-    for (int g = 0; g < ngroups; ++g) {
-      tab.col0[g] = col0_host[g]; tab.ncols[g] = ncols_host[g]; tab.db[g] = db_host[g];
-      any = any || db_host[g];
-    }
-    if (!any) return NERVECL_OK;
-    const int64_t npix = (int64_t)N * H * W;
-    const int lanes = 256 / (Cy / 8);
-    const int blocks = (int)imax(1, imin(cdiv(npix, (int64_t)lanes * 32), sm_count() * 6));
-    colsum_scatter_kernel<<<blocks, 256, Cy * sizeof(float), s>>>(reinterpret_cast<const bf16*>(dy), ldy, npix, Cy, scale, tab);
-    return launch_status();
-  }
-  if (db_host) {
-    for (int g = 0; g < ngroups; ++g) {
-      if (!db_host[g]) continue;
-      if (ncols_host[g] % 4 || col0_host[g] % 4) {
-        if (ncols_host[g] > 32) return NERVECL_EALIGN;
-        const int64_t npix = (int64_t)N * H * W;
-        colsum_any_kernel<<<(int)imin(cdiv(npix, 256 * 8), sm_count() * 4), 256, 0, s>>>(
-            reinterpret_cast<const bf16*>(dy) + col0_host[g], ldy, npix, ncols_host[g], scale, db_host[g]);
-        rc = launch_status();
-        if (rc) return rc;
-        continue;
-      }
-      rc = nervecl_chan_sum(reinterpret_cast<const bf16*>(dy) + col0_host[g], ldy, NERVECL_BF16, 1, (int64_t)N * H * W,
-                            ncols_host[g], scale, db_host[g], stream);
-      if (rc) return rc;
-    }
-  }
-  return NERVECL_OK;
+  return wgrad_rows(x, ldx, dy, ldy, N, H, W, Cx, Cy, ngroups, col0_host, ncols_host, cin_host, dw_host, db_host, scale, s);
 }
