@@ -57,6 +57,7 @@ struct WgrArgs {
   // channels of input row y + ky2 - 1 (-1: none), so its three taps need two classes instead of three
   int c_ky2[kMaxClasses];
   int stages;
+  int nby_max;         // dY chunks per stage of the widest class (sizes the stage)
   int bias;            // some group has a bias gradient: the drain warps of class 0 sum the dY tiles while the MMAs run
   float scale;
 };
@@ -85,7 +86,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const int mt = a.c_mt[cls], ky = a.c_ky[cls], col0 = a.c_col0[cls], n16 = a.c_n16[cls], nby = a.c_nby[cls];
   const int ky2 = a.c_ky2[cls];
   const int idx = blockIdx.x - a.c_cta0[cls], nctas = a.c_ctas[cls];
-  const uint32_t stage_bytes = 2u * XCHUNK + 3u * YCHUNK;
+  const uint32_t stage_bytes = 2u * XCHUNK + (uint32_t)a.nby_max * YCHUNK;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + a.stages;
@@ -359,8 +360,20 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return NERVECL_EUNSUPPORTED;
   }
+  // Stages sized for the widest class: launches with <= 128 gradient columns (every conv outside the dense blocks) get
+  // 3-4 stages instead of 2 -- with two, the narrow classes' tensor work (1152 cycles per stage at N = 64) no longer
+  // covered the load latency and they ran at half speed.
+  a.nby_max = 1;
+  for (int c = 0; c < a.nclasses; ++c) a.nby_max = a.c_nby[c] > a.nby_max ? a.c_nby[c] : a.nby_max;
+  const size_t stage_sz = 2 * XCHUNK + (size_t)a.nby_max * YCHUNK;
+#ifdef WG_FIXED_STAGES
   a.stages = kStages;
-  const size_t smem = 1024 + (size_t)a.stages * (2 * XCHUNK + 3 * YCHUNK) + (2 * a.stages + 1) * sizeof(uint64_t) + 16;
+#else
+  a.stages = (int)((220 * 1024) / stage_sz);
+  if (a.stages > 4) a.stages = 4;
+  if (a.stages < kStages) a.stages = kStages;
+#endif
+  const size_t smem = 1024 + (size_t)a.stages * stage_sz + (2 * a.stages + 1) * sizeof(uint64_t) + 16;
   cudaError_t e = cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   wgrad_rows_kernel<<<grid, kThreads, smem, s>>>(tx, td, a);

@@ -54,7 +54,10 @@ def wgrad_case(cin, cout, k, ld_in, ld_dy):
     dw = torch.zeros((cout, cin, k, k), device=dev)
     db = torch.zeros(cout, device=dev)
     flops = 2.0 * B * H * W * cin * cout * k * k
-    ms = bench(lambda: nv.conv2d_wgrad(x[..., :cin], dy[..., :cout], dw, db, 1.0, ops.CONV_TC))
+    if k == 3:
+        ms = bench(lambda: nv.conv3x3_wgrad_grouped(x[..., :cin], dy[..., :cout], [dw], [db], [0], 1.0))
+    else:
+        ms = bench(lambda: nv.conv2d_wgrad(x[..., :cin], dy[..., :cout], dw, db, 1.0, ops.CONV_TC))
     print(f"wgrad {cin:3d}->{cout:3d} k{k}: {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF", flush=True)
 
 
@@ -130,6 +133,13 @@ if __name__ == "__main__":
         for cin in (64, 96, 128, 160, 192):
             wgrad_case(cin, 32, 3, 224, 224)
         wgrad_case(224, 64, 1, 224, 64)
+    if which == "wgrad3":
+        # 3x3 weight gradients outside the dense blocks (flow_net, attention, gff)
+        wgrad_case(96, 128, 3, 96, 128)
+        wgrad_case(128, 64, 3, 128, 64)
+        wgrad_case(192, 64, 3, 192, 64)
+        wgrad_case(64, 64, 3, 64, 64)
+        wgrad_case(64, 32, 3, 64, 32)
     if which == "wgrad1":
         # 1x1 weight gradients of the step: extractor pointwise and head conv (48 images), LFF (16 images)
         B_save = B
