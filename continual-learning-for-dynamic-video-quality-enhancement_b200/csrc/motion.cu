@@ -262,71 +262,89 @@ __device__ __forceinline__ void atomic_add8(bf16* p, float w, const f8& g) {
                : "memory");
 }
 
+// Backward warp, same two phases as the forward (the C/8 lanes of a pixel used to replay the coordinate sequence
+// each: issue-bound at 68 % with the L2 reductions idle a third of the time): phase A one pixel per LANE, phase B the
+// lanes regrouped as (pixel, 8-channel vector) with the pixel's corner weights broadcast by shuffles; the flow
+// gradient is reduced over the pixel's lanes with xor-shuffles.
 template <typename T, typename AT>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow,
                 const T* __restrict__ dout, int64_t lddo, AT* __restrict__ dfeat, int64_t lddf,
                 float* __restrict__ dflow, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode) {
-  // grid = (N*H rows, pixel groups of a row); the C/8 threads of a pixel are adjacent lanes
+  const int lane = threadIdx.x & 31;
+  const int npix = N * H * W;                                        // (< 2^31: checked by the launcher)
+  const int p = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+  // ---- phase A: lane = pixel ----
+  float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f;                 // x1f - ix, ix - x0f, y1f - iy, iy - y0f
+  int q = 0;
+  unsigned vmask = 0;                                                // bit0 nw, bit1 ne, bit2 sw, bit3 se, bit4 active
+  if (p < npix) {
+    const int x = p % W, r = p / W;
+    const int y = r % H;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+    const WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
+    const float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
+    wx0 = x1f - c.ix; wx1 = c.ix - c.x0f; wy0 = y1f - c.iy; wy1 = c.iy - c.y0f;
+    const bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
+    const bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
+    vmask = (yin0 && xin0 ? 1u : 0u) | (yin0 && xin1 ? 2u : 0u) | (yin1 && xin0 ? 4u : 0u) | (yin1 && xin1 ? 8u : 0u) | 16u;
+    q = (r - y) * W + c.y0 * W + c.x0;
+  }
+  // ---- phase B: lane = (pixel of the group, 8-channel vector) ----
   const int cg = C >> 3;
-  const int ppb = blockDim.x / cg;
-  const int x = blockIdx.y * ppb + (int)threadIdx.x / cg;
-  const int64_t rowi = blockIdx.x;                       // n*H + y
-  const int y = (int)(rowi % H);
-  {
+  const int ppi = 32 / cg;
+  const int c0 = (lane % cg) << 3;
+  const int sub = lane / cg;
+  const int pbase = p - lane;
+  // d ix / d flow_x = ((W-1)/2) * (2 * 1/(W-1)), evaluated in the reference's order
+  const float mx = ((float)(W - 1) * 0.5f) * (2.0f * inv_w);
+  const float my = ((float)(H - 1) * 0.5f) * (2.0f * inv_h);
+#pragma unroll 2
+  for (int it = 0; it < cg; ++it) {
+    const int src = it * ppi + sub;
+    const float ax0 = __shfl_sync(0xffffffffu, wx0, src), ax1 = __shfl_sync(0xffffffffu, wx1, src);
+    const float ay0 = __shfl_sync(0xffffffffu, wy0, src), ay1 = __shfl_sync(0xffffffffu, wy1, src);
+    const int qq = __shfl_sync(0xffffffffu, q, src);
+    const unsigned vm = __shfl_sync(0xffffffffu, vmask, src);
     float gix = 0.f, giy = 0.f;
-    const int64_t p = rowi * W + x;
-    const bool active = x < W;
-    if (active) {
-      const int c0 = ((int)threadIdx.x % cg) << 3;
-      const int64_t img = (rowi - y) * W;
-      float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
-      WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
-      float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
-      float wnw = (x1f - c.ix) * (y1f - c.iy);
-      float wne = (c.ix - c.x0f) * (y1f - c.iy);
-      float wsw = (x1f - c.ix) * (c.iy - c.y0f);
-      float wse = (c.ix - c.x0f) * (c.iy - c.y0f);
-      bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
-      bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
-      f8 g = ld8(dout + p * lddo + c0);
-      int64_t q = img + (int64_t)c.y0 * W + c.x0;
-      const T* fb = feat + q * ldf_ + c0;
-      AT* db = dfeat + q * lddf + c0;
-      if (yin0 && xin0) {
-        f8 v = ld8(fb);
-        atomic_add8(db, wnw, g);
+    if (vm & 16u) {
+      const f8 g = ld8(dout + (int64_t)(pbase + src) * lddo + c0);
+      const T* fb = feat + (int64_t)qq * ldf_ + c0;
+      AT* db = dfeat + (int64_t)qq * lddf + c0;
+      if (vm & 1u) {
+        const f8 v = ld8(fb);
+        atomic_add8(db, ax0 * ay0, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          gix -= v.v[k] * (y1f - c.iy) * g.v[k];
-          giy -= v.v[k] * (x1f - c.ix) * g.v[k];
+          gix -= v.v[k] * ay0 * g.v[k];
+          giy -= v.v[k] * ax0 * g.v[k];
         }
       }
-      if (yin0 && xin1) {
-        f8 v = ld8(fb + ldf_);
-        atomic_add8(db + lddf, wne, g);
+      if (vm & 2u) {
+        const f8 v = ld8(fb + ldf_);
+        atomic_add8(db + lddf, ax1 * ay0, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          gix += v.v[k] * (y1f - c.iy) * g.v[k];
-          giy -= v.v[k] * (c.ix - c.x0f) * g.v[k];
+          gix += v.v[k] * ay0 * g.v[k];
+          giy -= v.v[k] * ax1 * g.v[k];
         }
       }
-      if (yin1 && xin0) {
-        f8 v = ld8(fb + (int64_t)W * ldf_);
-        atomic_add8(db + (int64_t)W * lddf, wsw, g);
+      if (vm & 4u) {
+        const f8 v = ld8(fb + (int64_t)W * ldf_);
+        atomic_add8(db + (int64_t)W * lddf, ax0 * ay1, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          gix -= v.v[k] * (c.iy - c.y0f) * g.v[k];
-          giy += v.v[k] * (x1f - c.ix) * g.v[k];
+          gix -= v.v[k] * ay1 * g.v[k];
+          giy += v.v[k] * ax0 * g.v[k];
         }
       }
-      if (yin1 && xin1) {
-        f8 v = ld8(fb + (int64_t)(W + 1) * ldf_);
-        atomic_add8(db + (int64_t)(W + 1) * lddf, wse, g);
+      if (vm & 8u) {
+        const f8 v = ld8(fb + (int64_t)(W + 1) * ldf_);
+        atomic_add8(db + (int64_t)(W + 1) * lddf, ax1 * ay1, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          gix += v.v[k] * (c.iy - c.y0f) * g.v[k];
-          giy += v.v[k] * (c.ix - c.x0f) * g.v[k];
+          gix += v.v[k] * ay1 * g.v[k];
+          giy += v.v[k] * ax1 * g.v[k];
         }
       }
     }
@@ -334,12 +352,8 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
       gix += __shfl_xor_sync(0xffffffffu, gix, o);
       giy += __shfl_xor_sync(0xffffffffu, giy, o);
     }
-    if (active && ((int)threadIdx.x % cg) == 0) {
-      // d ix / d flow_x = ((W-1)/2) * (2 * 1/(W-1)), evaluated in the reference's order
-      float mx = ((float)(W - 1) * 0.5f) * (2.0f * inv_w);
-      float my = ((float)(H - 1) * 0.5f) * (2.0f * inv_h);
-      reinterpret_cast<float2*>(dflow)[p] = make_float2(gix * mx, giy * my);
-    }
+    if ((vm & 16u) && (lane % cg) == 0)
+      reinterpret_cast<float2*>(dflow)[pbase + src] = make_float2(gix * mx, giy * my);
   }
 }
 
@@ -418,9 +432,8 @@ static int warp_bwd_launch(const void* feat, int64_t ldf, const float* flow, con
       !aligned(dfeat, 16) || !aligned(flow, 8) || !aligned(dflow, 8))
     return NERVECL_EALIGN;
   float inv_w = 1.0f / (float)(W - 1), inv_h = 1.0f / (float)(H - 1);
-  const int ppb = 256 / (C >> 3);
-  if (cdiv(W, ppb) > 65535 || (int64_t)N * H > 0x7fffffff) return NERVECL_EUNSUPPORTED;
-  dim3 blocks((unsigned)((int64_t)N * H), (unsigned)cdiv(W, ppb));
+  if ((int64_t)N * H * W >= ((int64_t)1 << 31) - 64) return NERVECL_EUNSUPPORTED;
+  const unsigned blocks = (unsigned)cdiv((int64_t)N * H * W, 256);
   if (dfeat_dtype == NERVECL_BF16) {
     warp_bwd_kernel<bf16, bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)feat, ldf, flow, (const bf16*)dout, lddo,
                                                                        (bf16*)dfeat, lddf, dflow, N, H, W, C, inv_w, inv_h,
