@@ -227,8 +227,10 @@ int conv_tc_fwd(const nervecl_conv_params& a, cudaStream_t s) {
     cuuint64_t strides[3] = {(cuuint64_t)a.ldx * 2, (cuuint64_t)a.W * a.ldx * 2, (cuuint64_t)a.H * a.W * a.ldx * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)BW, (cuuint32_t)BH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
+    // (channel count not a multiple of the 64-channel box: promote to 64 bytes only, or the last box drags the
+    //  buffer's pad channels in from DRAM -- the 224-channel dense-block buffer was read as 256)
     if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, (a.Cin % 64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return NERVECL_EUNSUPPORTED;
   }

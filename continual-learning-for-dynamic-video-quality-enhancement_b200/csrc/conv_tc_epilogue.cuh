@@ -63,14 +63,17 @@ __device__ __forceinline__ void store16(bf16* p, const float (&f)[16], bool v256
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// 32 bytes of an epilogue operand (16 bf16 of one pixel).  L2::64B: the request fills the whole 64-byte DRAM burst into
+// L2.  The two epilogue warps that share a pixel's 32-channel slice each ask for one 32-byte sector of it; without the
+// hint DRAM was read twice per burst (ncu: 64 channel-equivalents per pixel for a 32-channel ReLU mask, 9 GB per step).
 __device__ __forceinline__ void load32B(const bf16* p, uint4& lo, uint4& hi, bool v256) {
   if (v256) {
-    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    asm volatile("ld.global.L2::64B.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
   } else {
-    lo = *reinterpret_cast<const uint4*>(p);
-    hi = *reinterpret_cast<const uint4*>(p + 8);
+    asm volatile("ld.global.L2::64B.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(p));
+    asm volatile("ld.global.L2::64B.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p + 8));
   }
 }
 __device__ __forceinline__ void store16(float* p, const float (&f)[16]) {

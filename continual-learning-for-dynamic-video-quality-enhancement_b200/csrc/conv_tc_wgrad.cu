@@ -296,7 +296,8 @@ int conv_tc_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, float
     cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            (Cin % 64) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,   // (no pad channels from DRAM)
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return NERVECL_EUNSUPPORTED;
   }

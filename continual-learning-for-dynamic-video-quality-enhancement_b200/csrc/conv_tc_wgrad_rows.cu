@@ -346,7 +346,8 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)PXB, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            (Cx % KC) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,   // (no pad channels from DRAM)
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return NERVECL_EUNSUPPORTED;
   }
@@ -356,7 +357,8 @@ int wgrad_rows(const void* x, int64_t ldx, const void* dy, int64_t ldy, int N, i
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)KPX, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (enc(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            (Cy % KC) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return NERVECL_EUNSUPPORTED;
   }
