@@ -26,6 +26,13 @@ NV_API int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t str
   int engine = p->engine;
   const bool pair_ok = engine != NERVECL_CONV_TC_ROWS1;      // (ROWS1: the 1-CTA row kernel, for A/B comparisons and tests)
   if (engine == NERVECL_CONV_TC_ROWS1) engine = NERVECL_CONV_TC;
+  if (p->sign_mode) {                            // packed ReLU signs: CTA-pair row kernel only
+    if (p->sign_mode != 1 && p->sign_mode != 2) return NERVECL_EINVAL;
+    if (!p->sign_bits || (p->Cout & 15)) return NERVECL_EINVAL;
+    if (engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) return NERVECL_EUNSUPPORTED;
+    if (!pair_ok || !conv_rows2_supported(*p)) return NERVECL_EUNSUPPORTED;
+    return conv_rows2_fwd(*p, s);
+  }
   if (p->x2) {                                   // second input: row-streaming engines only
     if (p->Cin2 <= 0 || p->ldx2 < p->Cin2) return NERVECL_EINVAL;
     if (engine != NERVECL_CONV_AUTO && engine != NERVECL_CONV_TC) return NERVECL_EUNSUPPORTED;

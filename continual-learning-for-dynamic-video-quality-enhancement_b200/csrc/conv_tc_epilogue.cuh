@@ -51,18 +51,39 @@ __device__ __forceinline__ void store16(bf16* p, const float (&f)[16]) {
 }
 // 32 bytes (16 bf16) per thread: one full 32-byte sector per instruction when the address allows it (sm_100
 // 256-bit global accesses); the two 16-byte halves of a thread otherwise go out as separate half-sector writes
-__device__ __forceinline__ void store16(bf16* p, const float (&f)[16], bool v256) {
-  if (!v256) { store16(p, f); return; }
-  uint32_t r[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    r[i] = *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ void store16(bf16* p, const uint32_t (&r)[8], bool v256) {
+  if (!v256) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<uint4*>(p + 8) = make_uint4(r[4], r[5], r[6], r[7]);
+    return;
   }
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void pack16(const float (&f)[16], uint32_t (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+__device__ __forceinline__ void store16(bf16* p, const float (&f)[16], bool v256) {
+  if (!v256) { store16(p, f); return; }
+  uint32_t r[8];
+  pack16(f, r);
+  store16(p, r, true);
+}
+// Packed ReLU signs of 16 NON-NEGATIVE bf16 (eight bf16x2 words): channel j <-> bit sign_bit_pos(j).  Adding 0x7FFF to a
+// non-negative half sets its bit 15 exactly when it is not zero (no carry into the upper half), so a word costs three
+// integer instructions instead of a compare / select / shift per channel.
+__device__ __forceinline__ uint32_t sign_word16(const uint32_t (&r)[8]) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc |= ((r[k] + 0x7FFF7FFFu) & 0x80008000u) >> k;
+  return ((acc >> 8) & 0xFFu) | ((acc >> 16) & 0xFF00u);
+}
+__device__ __forceinline__ constexpr int sign_bit_pos(int j) { return (j & 1) ? 15 - (j >> 1) : 7 - (j >> 1); }
 // 32 bytes of an epilogue operand (16 bf16 of one pixel).  L2::64B: the request fills the whole 64-byte DRAM burst into
 // L2.  The two epilogue warps that share a pixel's 32-channel slice each ask for one 32-byte sector of it; without the
 // hint DRAM was read twice per burst (ncu: 64 channel-equivalents per pixel for a 32-channel ReLU mask, 9 GB per step).

@@ -48,6 +48,9 @@ struct Pair2Args {
   bf16* out;
   int64_t ldo;
   float* colsum;
+  uint16_t* sbits;      // packed ReLU signs, [Cout / 16][pixel] (nervecl_conv_params.sign_bits)
+  int smode;            // 0 none, 1 write (kind 1), 2 read as the mask (kind 2)
+  int64_t npix;         // N * H * W (plane stride of the sign words)
   int v256_out, v256_in;
   // geometry
   int N, H, W, Cout;
@@ -321,6 +324,8 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const float alpha = a.alpha;
     const bool vo = a.v256_out != 0, vi = a.v256_in != 0;
     const bool want_cs = a.colsum != nullptr;        // (host: only with kind 2 and NOUT <= 32, i.e. one chunk per thread)
+    const int smode = a.smode;                       // (host: only with NOUT <= 32)
+    const int sgrp = c_lo / 16 + part;               // this thread's 16-channel group of the sign words
     // one register array serves both: the bias of the thread's first chunk (kind 1) or the running column sums (kind 2)
     float cs[16];
 #pragma unroll
@@ -356,6 +361,15 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         pre[i][0] = pre[i][1] = make_uint4(0, 0, 0, 0);
         if (has_e && valid && has[i]) load32B(ep + ch[i], pre[i][0], pre[i][1], vi);
       }
+      // sign words of rows oi .. oi + 3 (mode 2: 2 bytes per row instead of the 32-byte mask operand)
+      const uint16_t* sp = a.sbits + (int64_t)sgrp * a.npix + p0;       // (a warp's 32 pixels: 64 contiguous bytes)
+      const int64_t sstride = a.W;
+      uint32_t sb0 = 0, sb1 = 0, sb2 = 0;
+      if (smode == 2 && valid && has[0]) {
+        sb0 = __ldg(sp);
+        if (rows > 1) sb1 = __ldg(sp + sstride);
+        if (rows > 2) sb2 = __ldg(sp + 2 * sstride);
+      }
       uint4 q1[2], q2[2];                           // NC == 1: rows oi + 1 and oi + 2 of the operand are in flight as well
       q1[0] = q1[1] = q2[0] = q2[1] = make_uint4(0, 0, 0, 0);
       if (NC == 1 && has_e && valid && has[0]) {
@@ -379,6 +393,11 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         uint4 cur[NC][2];
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cur[i][0] = pre[i][0]; cur[i][1] = pre[i][1]; }
+        const uint32_t sbc = sb0;
+        if (smode == 2) {
+          sb0 = sb1; sb1 = sb2;
+          if (valid && has[0] && oi + 3 < rows) sb2 = __ldg(sp + (int64_t)(oi + 3) * sstride);
+        }
         if (NC == 1) {
           pre[0][0] = q1[0]; pre[0][1] = q1[1];
           q1[0] = q2[0]; q1[1] = q2[1];
@@ -445,9 +464,21 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] += e[j];
               }
+              if (smode == 1 && i == 0) {             // (relu: every value is >= 0)
+                uint32_t r8[8];
+                pack16(f, r8);
+                a.sbits[(int64_t)sgrp * a.npix + p0 + (int64_t)oi * a.W] = (uint16_t)sign_word16(r8);
+                store16(op + ch[i], r8, vo);
+                continue;
+              }
             } else if (kind == 2) {
+              if (smode == 2) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = e[j] > 0.f ? alpha * __uint_as_float(v[i][j]) : 0.f;
+                for (int j = 0; j < 16; ++j) f[j] = ((sbc >> sign_bit_pos(j)) & 1u) ? alpha * __uint_as_float(v[i][j]) : 0.f;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = e[j] > 0.f ? alpha * __uint_as_float(v[i][j]) : 0.f;
+              }
               if (want_cs && i == 0) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) cs[j] += f[j];
@@ -528,6 +559,9 @@ bool plan_rows2(const nervecl_conv_params& a, int sms, Pair2Plan& p) {
 int lean_kind(const nervecl_conv_params& a) {
   // the same three fused epilogues as the 1-CTA kernel's lean paths
   if (a.out_dtype != NERVECL_BF16 || a.mask_sub || a.relu == 2) return 0;
+  if (a.sign_mode == 2)                                        // the mask comes from packed sign bits
+    return (!a.accumulate && !a.res && !a.mask && !a.bias && !a.relu) ? 2 : 0;
+  if (a.sign_mode == 1 && (a.relu != 1 || a.accumulate || a.mask)) return 0;
   if (!a.accumulate) {
     if ((!a.res || a.res_channels >= a.Cout) && !a.mask && a.alpha == 1.0f && (a.bias || a.relu || !a.res)) return 1;
     if (!a.res && a.mask && !a.bias && !a.relu && a.mask_c0 == 0) return 2;
@@ -559,6 +593,7 @@ bool conv_rows2_supported(const nervecl_conv_params& a) {
   Pair2Plan p;
   if (!plan_rows2(a, sm_count(), p)) return false;
   if (a.colsum && !(kind == 2 && p.NOUT <= 32)) return false;
+  if (a.sign_mode && (p.NOUT > 32 || !a.sign_bits || (a.Cout & 15) || kind != a.sign_mode)) return false;
   return true;
 }
 
@@ -605,6 +640,7 @@ int conv_rows2_fwd(const nervecl_conv_params& a, cudaStream_t s) {
   else if (a.accumulate) { t.eop = (const bf16*)a.out; t.ldeop = a.ldo; }
   else if (a.res) { t.eop = (const bf16*)a.res; t.ldeop = a.ldres; }
   t.out = (bf16*)a.out; t.ldo = a.ldo; t.colsum = a.colsum;
+  t.sbits = (uint16_t*)a.sign_bits; t.smode = a.sign_mode; t.npix = (int64_t)a.N * a.H * a.W;
   t.v256_out = a.ldo % 16 == 0 && aligned(a.out, 32);
   t.v256_in = t.eop && t.ldeop % 16 == 0 && aligned(t.eop, 32);
   t.N = a.N; t.H = a.H; t.W = a.W; t.Cout = a.Cout;

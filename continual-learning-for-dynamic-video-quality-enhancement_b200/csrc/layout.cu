@@ -3,7 +3,7 @@
 
 using namespace nv;
 
-NV_API int nervecl_abi_version(void) { return 6; }
+NV_API int nervecl_abi_version(void) { return 7; }
 
 NV_API const char* nervecl_error_string(int code) {
   switch (code) {

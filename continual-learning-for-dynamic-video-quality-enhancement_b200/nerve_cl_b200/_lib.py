@@ -34,6 +34,7 @@ class ConvParams(C.Structure):
         ("out", c_vp), ("ldo", c_i64),
         ("x2", c_vp), ("ldx2", c_i64), ("Cin2", c_i32), ("x2_center", c_i32),
         ("colsum", c_vp),
+        ("sign_bits", c_vp), ("sign_mode", c_i32), ("reserved0", c_i32),
     ]
 
 

@@ -167,6 +167,10 @@ class Activations:
         self.up = act(B, 3 * s * s, f32)
         self.lr_centre: Optional[Tensor] = None   # view of the caller's frames (kept for backward)
         self.training = False
+        # packed ReLU signs of the dense-block layers (int16 per pixel and 16 channels), written by the forward convs and
+        # read back as the masks of the fused block backward; allocated on first use
+        self.rdb_bits: Optional[List[List[Tensor]]] = None
+        self.has_bits = False
 
 
 class Plan:
@@ -233,6 +237,13 @@ class Plan:
                 cmain = GROWTH * (RDB_LAYERS - s) if s > 0 else GROWTH * RDB_LAYERS
                 cols = _align(cmain, 64) + F
                 self.wslice.append(torch.zeros((9, self.NB * rows, cols), device=device, dtype=adt))
+            # The last slice's gradient is a 1x1 conv (only the LFF reaches it).  With sign-bit masks it runs as a 3x3 conv
+            # whose eight outer taps are zero, because only the CTA-pair row kernel (3x3) reads the packed masks.
+            self.wlast = torch.zeros((self.NB, 9, GROWTH, _align(F, 16)), device=device, dtype=adt)
+        # ReLU masks of the dense-block layers as packed sign bits (nervecl_conv_params.sign_bits): 4 bytes per pixel and
+        # layer instead of 64 for every mask read of the block backward.  Switched off for the plan the first time the
+        # library answers "unsupported" (shapes too small for the CTA-pair kernel).
+        self.sign_bits = self.fused_rdb_bwd
 
     # ---- activation-set pool ---------------------------------------------------------------
     def acquire(self) -> Activations:
@@ -279,6 +290,9 @@ class Plan:
                 comb[:, :, j * GROWTH:(j + 1) * GROWTH] = blk.permute(0, 2, 1, 3, 4).flip(3, 4)
             comb[:, :, _align(cmain, 64):, 1, 1] = 0.2 * Wf[:, :, c_lo:c_lo + rows].permute(0, 2, 1)    # [NB, c, d]
             nv.pack_conv_weight(comb.view(NB * rows, cols, 3, 3), self.wslice[s], False)
+        if self.sign_bits:
+            c4 = F + (RDB_LAYERS - 1) * GROWTH
+            self.wlast[:, 4].copy_(torch.stack([self.wb[f"residual_blocks.{k}.lff"][0, c4:c4 + GROWTH] for k in range(NB)]))
 
     # ---- helpers ---------------------------------------------------------------------------
     def _span(self, kind: str, x: Tensor, cin: int, cout: int, k: int):
@@ -297,12 +311,14 @@ class Plan:
         return self.timer.span(kind, flops_per_px * npix, float(npix) * channels_moved * x.element_size())
 
     def conv(self, name: str, x: Tensor, out: Tensor, P, *, relu=False, res=None, res_channels=0, alpha=1.0,
-             bias=True) -> None:
+             bias=True, sign_bits=None) -> None:
+        """``sign_bits``: int16 tensor that receives the packed signs of the (ReLU'd) output."""
         c = self.convs[name]
         b = P[name + ".bias"] if (c.has_bias and bias) else None
         with self._span("conv_fwd", x, x.shape[-1], c.cout, c.k):
             nv.conv2d_fwd(x, self.wf[name], b, res, None, None, out, c.cout, relu, False,
-                          res_channels if res is not None else 0, 0, alpha, self.engine)
+                          res_channels if res is not None else 0, 0, alpha, self.engine, None, False, None,
+                          sign_bits, 1 if sign_bits is not None else 0)
 
     def dgrad(self, name: str, dy: Tensor, out: Tensor, *, cout=None, accumulate=False, res=None, res_channels=0,
               alpha=1.0, mask=None, mask_sub=None, mask_c0=0) -> None:
@@ -420,13 +436,28 @@ class Plan:
         nv.cbam_apply_fwd(A.blend, A.gate, A.stats, P[pre + "spatial_attention.conv.weight"], A.sgate, trunk_in)
 
         # ---- residual dense blocks (super_resolution.py:245-253), concat-free ----
+        use_bits = need_bwd and self.sign_bits and self.engine != CONV_SIMT
+        if use_bits and A.rdb_bits is None:
+            A.rdb_bits = [[torch.empty((GROWTH // 16, B, H, W), device=self.device, dtype=torch.int16)
+                           for _ in range(RDB_LAYERS)] for _ in range(self.NB)]
         for k in range(self.NB):
             buf = A.rdb[k]
             for i in range(RDB_LAYERS):
                 c0 = F + i * GROWTH
-                self.conv(f"residual_blocks.{k}.layers.{i}.0", buf[..., :c0], buf[..., c0:c0 + GROWTH], P, relu=True)
+                name = f"residual_blocks.{k}.layers.{i}.0"
+                if use_bits:
+                    try:
+                        self.conv(name, buf[..., :c0], buf[..., c0:c0 + GROWTH], P, relu=True, sign_bits=A.rdb_bits[k][i])
+                        continue
+                    except RuntimeError as e:
+                        if "not supported" not in str(e) or (k, i) != (0, 0):
+                            raise
+                        self.sign_bits = use_bits = False          # too small for the CTA-pair kernel: bf16 masks
+                self.conv(name, buf[..., :c0], buf[..., c0:c0 + GROWTH], P, relu=True)
             nxt = A.rdb[k + 1][..., :F] if k + 1 < self.NB else A.trunk
             self.conv(f"residual_blocks.{k}.lff", buf, nxt, P, alpha=0.2, res=buf[..., :F], res_channels=F)
+
+        A.has_bits = bool(use_bits)
 
         # ---- global fusion, upsampler, bicubic skip, clamp (super_resolution.py:372-382) ----
         self.conv("gff.0", A.trunk, A.fused, P, relu=True, res=centre, res_channels=F)
@@ -499,7 +530,22 @@ class Plan:
             else:
                 self.dgrad(name, dy, g[..., :c0], cout=c0, accumulate=True)
 
-    def _rdb_backward_fused(self, k: int, buf: Tensor, g: Tensor, dblock: Tensor, G: Dict[str, Tensor]) -> None:
+    def _masked_conv(self, x, w, mask, bits, out, rows, alpha, x2, colsum) -> None:
+        """Mask-gated data-gradient conv of the fused block backward: the mask from the packed sign bits where the
+        library takes them, from the forward activation otherwise."""
+        if bits is not None:
+            try:
+                nv.conv2d_fwd(x, w, None, None, None, None, out, rows, False, False, 0, 0, alpha, self.engine, x2,
+                              x2 is not None, colsum, bits, 2)
+                return
+            except RuntimeError as e:
+                if "not supported" not in str(e):
+                    raise
+        nv.conv2d_fwd(x, w, None, None, mask, None, out, rows, False, False, 0, 0, alpha, self.engine, x2,
+                      x2 is not None, colsum)
+
+    def _rdb_backward_fused(self, k: int, buf: Tensor, g: Tensor, dblock: Tensor, G: Dict[str, Tensor],
+                            bits: Optional[List[Tensor]] = None) -> None:
         """Dense-block backward as 1 + 5 convolutions that each WRITE one slice of the gradient buffer once
         (no read-modify-write accumulation) followed by one grouped weight-gradient GEMM.
 
@@ -522,8 +568,13 @@ class Plan:
         names = [f"residual_blocks.{k}.layers.{i}.0" for i in range(RDB_LAYERS)]
         g4 = gpos(RDB_LAYERS - 1)
         with self._span("conv_dgrad", dblock, F, GROWTH, 1):
-            nv.conv2d_fwd(dblock, self.wb[lff][:, c4:CT, :], None, None, buf[..., c4:CT], None, g[..., g4:g4 + GROWTH],
-                          GROWTH, False, False, 0, 0, 0.2, self.engine, None, False, G[names[RDB_LAYERS - 1] + ".bias"])
+            if bits is not None:
+                self._masked_conv(dblock, self.wlast[k], buf[..., c4:CT], bits[RDB_LAYERS - 1], g[..., g4:g4 + GROWTH],
+                                  GROWTH, 0.2, None, G[names[RDB_LAYERS - 1] + ".bias"])
+            else:
+                nv.conv2d_fwd(dblock, self.wb[lff][:, c4:CT, :], None, None, buf[..., c4:CT], None,
+                              g[..., g4:g4 + GROWTH], GROWTH, False, False, 0, 0, 0.2, self.engine, None, False,
+                              G[names[RDB_LAYERS - 1] + ".bias"])
         for s in range(RDB_LAYERS - 1, -1, -1):              # slices F+(s-1)G .. (s >= 1), then the x slice (s = 0)
             rows = F if s == 0 else GROWTH
             c_lo = 0 if s == 0 else F + (s - 1) * GROWTH      # the slice in the FORWARD buffer (its ReLU mask)
@@ -536,10 +587,13 @@ class Plan:
             # the slice's ReLU mask in (s > 0), the slice out
             moved = n_later + F + (F if s == 0 else rows) + rows
             with self._span_flops(f"conv_dgrad|slice{s}", buf, 2.0 * rows * (9 * n_later + F), moved):
-                # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
-                nv.conv2d_fwd(g[..., F:F + n_later], w, None, dblock if s == 0 else None, mask, None,
-                              g[..., o_lo:o_lo + rows], rows, False, False, F if s == 0 else 0, 0, 1.0, self.engine,
-                              dblock, True, G[names[s - 1] + ".bias"] if s > 0 else None)
+                if s > 0:
+                    self._masked_conv(g[..., F:F + n_later], w, mask, bits[s - 1] if bits is not None else None,
+                                      g[..., o_lo:o_lo + rows], rows, 1.0, dblock, G[names[s - 1] + ".bias"])
+                else:
+                    # the x slice also receives the block's own skip connection (+ dblock) as the epilogue residual
+                    nv.conv2d_fwd(g[..., F:F + n_later], w, None, dblock, None, None, g[..., :rows], rows, False, False,
+                                  F, 0, 1.0, self.engine, dblock, True, None)
         cx = F + (RDB_LAYERS - 1) * GROWTH
         with self._span_flops("conv_wgrad|rdb_grouped", buf, sum(2.0 * 9 * (F + i * GROWTH) * GROWTH
                                                                 for i in range(RDB_LAYERS)), cx + RDB_LAYERS * GROWTH):
@@ -585,7 +639,7 @@ class Plan:
             name = f"residual_blocks.{k}.lff"
             self.wgrad(name, buf, dblock, G, scale=0.2)
             if fused:
-                self._rdb_backward_fused(k, buf, g, dblock, G)
+                self._rdb_backward_fused(k, buf, g, dblock, G, A.rdb_bits[k] if A.has_bits else None)
             else:
                 self._rdb_backward_layers(k, buf, g, dblock, G)
             ready(f"residual_blocks.{k}.")

@@ -192,9 +192,10 @@ def _pack_conv_weights_batched(w, dst, transpose_flip) -> None:
 # --------------------------------------------------------------------------------------------
 @_op("conv2d_fwd(Tensor x, Tensor w, Tensor? bias, Tensor? res, Tensor? mask, Tensor? mask_sub, "
      "Tensor(a!) out, int cout, int relu, bool accumulate, int res_channels, int mask_c0, float alpha, "
-     "int engine, Tensor? x2=None, bool x2_center=False, Tensor(b!)? colsum=None) -> ()")
+     "int engine, Tensor? x2=None, bool x2_center=False, Tensor(b!)? colsum=None, Tensor(c!)? sign_bits=None, "
+     "int sign_mode=0) -> ()")
 def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, res_channels, mask_c0, alpha,
-                engine, x2=None, x2_center=False, colsum=None) -> None:
+                engine, x2=None, x2_center=False, colsum=None, sign_bits=None, sign_mode=0) -> None:
     """Fused conv (see ``nervecl_conv2d_fwd``).  ``w`` is a packed [K*K, rows, cols] tensor; ``cout`` is the
     number of output channels actually computed (<= rows)."""
     xp, ldx, n, h, wd, cin = _nhwc(x, "x")
@@ -236,6 +237,11 @@ def _conv2d_fwd(x, w, bias, res, mask, mask_sub, out, cout, relu, accumulate, re
         if colsum.numel() < cout:
             raise RuntimeError("nervecl.conv2d_fwd: colsum must have at least cout elements")
         p.colsum = _flat(colsum, "colsum")
+    if sign_mode:                                # packed ReLU signs: int16 [cout / 16, N, H, W], written (1) or read as mask (2)
+        if (sign_bits is None or sign_bits.dtype != torch.int16 or not sign_bits.is_contiguous()
+                or sign_bits.numel() != n * h * wd * (cout // 16) or cout % 16):
+            raise RuntimeError("nervecl.conv2d_fwd: sign_bits must be a contiguous int16 [cout / 16, N, H, W] tensor")
+        p.sign_bits, p.sign_mode = sign_bits.data_ptr(), int(sign_mode)
     _lib.check(_lib.load().nervecl_conv2d_fwd(C.byref(p), _stream()), "conv2d_fwd")
 
 

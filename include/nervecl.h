@@ -157,6 +157,15 @@ typedef struct nervecl_conv_params {
    * the gradient is needed.  Row-streaming engine, mask-gated bf16 outputs with <= 32 channels per CTA only
    * (NERVECL_EUNSUPPORTED otherwise). */
   float* colsum;
+  /* ABI v7: packed ReLU sign bits, one uint16 per (16-channel group, pixel), group-major: bit j of
+   * sign_bits[g * N*H*W + p] <-> channel 16 g + c with j = (c odd ? 15 - c/2 : 7 - c/2) (a warp's 32 pixels are 64
+   * contiguous bytes; the bit order is what eight packed bf16x2 words give in three instructions each).  sign_mode 1: WRITE the signs of the written outputs (out > 0;
+   * a forward conv with relu == 1).  sign_mode 2: READ them as the ReLU mask (v = 0 where the bit is clear; `mask` must
+   * be NULL) -- the mask of relu'(y) of super_resolution.py:237 costs 2 bytes per pixel and 16 channels instead of 32.
+   * CTA-pair row kernel (3x3, bf16, Cout % 16 == 0, <= 32 output channels per CTA); NERVECL_EUNSUPPORTED otherwise. */
+  void* sign_bits;
+  int32_t sign_mode;
+  int32_t reserved0;
 } nervecl_conv_params;
 
 int nervecl_conv2d_fwd(const nervecl_conv_params* p, nervecl_stream_t stream);

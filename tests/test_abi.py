@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert name in _lib._SIGNATURES, f"{name} has no ctypes signature"
         assert len(_lib._SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, binding {len(_lib._SIGNATURES[name])}"
     assert set(_lib._SIGNATURES) == set(decls)
-    assert lib.nervecl_abi_version() == 6
+    assert lib.nervecl_abi_version() == 7
     assert lib.nervecl_error_string(-2).decode().startswith("misaligned")
 
 
@@ -40,7 +40,7 @@ def test_conv_params_struct_layout():
     from nerve_cl_b200._lib import ConvParams
     # 16 x 4-byte scalars then 8-byte aligned pointer/pitch pairs (matches the C struct on LP64)
     assert ConvParams.x.offset == 64
-    assert ctypes.sizeof(ConvParams) == 64 + 8 * 12 + 24 + 8      # ABI v2: + x2, ldx2, Cin2, x2_center; v3: + colsum
+    assert ctypes.sizeof(ConvParams) == 64 + 8 * 12 + 24 + 8 + 16  # ABI v2: + x2, ldx2, Cin2, x2_center; v3: + colsum; v7: + sign_bits, sign_mode
     assert ConvParams.x2.offset == 160 and ConvParams.Cin2.offset == 176 and ConvParams.colsum.offset == 184
 
 

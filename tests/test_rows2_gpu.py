@@ -93,3 +93,45 @@ def test_pair_kernel_second_input(shape, center):
                     nhwc(x2, torch.bfloat16), center)
     assert relerr(nchw(out[..., :cout]), ref) <= BF16_TOL
     assert float((out[..., cout:].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(2, 160, 640, 64, 32), (1, 360, 640, 160, 32), (3, 140, 320, 32, 16), (2, 123, 650, 96, 32)])
+def test_pair_kernel_sign_bits(shape):
+    """ABI v7 packed ReLU signs: a forward conv (bias + ReLU) writes one bit per channel of word (group, pixel) <-> out[pixel, channel] > 0;
+    a data-gradient conv that reads them as its mask == the same conv gated by the bf16 activation (bit-identical), with
+    and without the centre-tap second input and the fused column sums."""
+    n, h, w, cin, cout = shape
+    tc, _ = engines()
+    g = torch.Generator().manual_seed(sum(shape) + 5)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    xo, wp = nhwc(x, torch.bfloat16, pad_to=(cin + 63) // 64 * 64), pack(wt, torch.bfloat16)
+    act = torch.empty((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+    bits = torch.zeros((cout // 16, n, h, w), device="cuda", dtype=torch.int16)
+    nv().conv2d_fwd(xo, wp, b.cuda(), None, None, None, act, cout, True, False, 0, 0, 1.0, tc, None, False, None, bits, 1)
+    ref = F.relu(F.conv2d(x, wt, b, 1, 1))
+    assert relerr(nchw(act), ref) <= BF16_TOL
+    want = (act.view(n, h, w, cout // 16, 16) > 0).to(torch.int32)
+    pos = torch.tensor([15 - c // 2 if c & 1 else 7 - c // 2 for c in range(16)], device="cuda", dtype=torch.int32)
+    want = (want << pos).sum(-1).permute(3, 0, 1, 2)
+    assert torch.equal(bits.to(torch.int32) & 0xFFFF, want)
+    # mode 2: gradient conv gated by the bits vs gated by the activation itself
+    dy = bf(torch.randn(n, cin, h, w, generator=g))
+    x2 = bf(torch.randn(n, 64, h, w, generator=g))
+    cpad = (cin + 63) // 64 * 64
+    comb = torch.zeros(cout, cpad + 64, 3, 3)
+    comb[:, :cin] = bf(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    comb[:, cpad:, 1, 1] = bf(torch.randn(cout, 64, generator=g) / 8)
+    wc = pack(comb, torch.bfloat16)
+    dyo, x2o = nhwc(dy, torch.bfloat16, pad_to=cpad), nhwc(x2, torch.bfloat16)
+    for second in (False, True):
+        a_out = torch.empty((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+        b_out = torch.empty_like(a_out)
+        cs_a, cs_b = torch.zeros(cout, device="cuda"), torch.zeros(cout, device="cuda")
+        nv().conv2d_fwd(dyo, wc, None, None, act, None, a_out, cout, False, False, 0, 0, 0.5, tc,
+                        x2o if second else None, second, cs_a)
+        nv().conv2d_fwd(dyo, wc, None, None, None, None, b_out, cout, False, False, 0, 0, 0.5, tc,
+                        x2o if second else None, second, cs_b, bits, 2)
+        assert torch.equal(a_out, b_out)
+        assert relerr(cs_b, cs_a) <= 1e-5
