@@ -9,7 +9,8 @@ namespace nv {   // fe_fast.cu
 bool fe_fast_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b);
 bool dw_tiled_supported(int C, int64_t lda, int64_t ldb, const void* a, const void* b);
 int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int dtype, int N, int H, int W, int C,
-                 int flip, int accumulate, cudaStream_t s);
+                 int flip, int accumulate, cudaStream_t s, const void* add = nullptr, int64_t ldadd = 0,
+                 const void* mask = nullptr, int64_t ldmask = 0);
 int dwconv_wgrad_slide(const void* x, int64_t ldx, const void* dy, int64_t lddy, int dtype, float* dw, int N, int H, int W,
                        int C, cudaStream_t s);
 bool bn_sums_fast_supported(int C, int64_t lda, int64_t ldb);
@@ -353,6 +354,18 @@ NV_API int nervecl_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, voi
   NV_DISPATCH_DTYPE(dtype, E, (dwconv_kernel<E><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
                                   (const E*)x, ldx, w, (E*)y, ldy, N, H, W, C, flip, accumulate)));
   return launch_status();
+}
+
+NV_API int nervecl_dwconv3x3_fwd_masked(const void* x, int64_t ldx, const float* w, const void* add, int64_t ldadd,
+                                        const void* mask, int64_t ldmask, void* y, int64_t ldy, int dtype, int N, int H,
+                                        int W, int C, int flip, nervecl_stream_t stream) {
+  if (!x || !w || !y || !add || !mask || N <= 0 || H <= 0 || W <= 0 || C <= 0) return NERVECL_EINVAL;
+  if ((C & 7) || (ldx & 7) || (ldy & 7) || (ldadd & 7) || (ldmask & 7) || !aligned(x, 16) || !aligned(y, 16) ||
+      !aligned(add, 16) || !aligned(mask, 16))
+    return NERVECL_EALIGN;
+  if (dtype != NERVECL_BF16) return NERVECL_EDTYPE;
+  if (!dw_tiled_supported(C, ldx, ldy, x, y)) return NERVECL_EUNSUPPORTED;
+  return dwconv_slide(x, ldx, w, y, ldy, dtype, N, H, W, C, flip, 0, as_stream(stream), add, ldadd, mask, ldmask);
 }
 
 NV_API int nervecl_dwconv3x3_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype,

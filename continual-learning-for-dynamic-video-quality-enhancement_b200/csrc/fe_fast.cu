@@ -13,7 +13,14 @@ using namespace nv;
 namespace {
 
 constexpr int kThreadsFe = 256;
-constexpr int DW_TH = 8;         // output rows per tile
+#ifndef DW_TH_ROWS
+#define DW_TH_ROWS 8
+#endif
+#ifndef DW_NBUF
+#define DW_NBUF 2
+#endif
+constexpr int DW_TH = DW_TH_ROWS;         // output rows per tile
+constexpr int kDwBufs = DW_NBUF;           // tile buffers per CTA (TMA loads in flight: kDwBufs - 1)
 
 // Depthwise tiles are brought in by TMA: one 4-D box {C, TWp + 2, TH + 2, 1} per tile with out-of-image pixels
 // zero-filled (= the conv padding), landing in shared memory as [(TH+2)][(TWp+2)][C].  The per-thread cp.async
@@ -28,9 +35,22 @@ __device__ __forceinline__ TileXY tile_xy(int64_t tile, int tiles_x, int tiles_y
 
 // One output column of DW_TH rows: each input row's three neighbour vectors are loaded / converted once and feed
 // the three output rows they belong to (rolling accumulators).  FULL: all DW_TH rows are inside the image.
-template <typename T, bool ACC, bool FULL>
+// MODE 0: y = conv;  1: y += conv;  2: y = (conv + add) where mask > 0, else 0 (`pre`: the thread's add / mask vectors
+// of all DW_TH rows, requested before the tile's barrier wait so that their latency hides behind it).
+template <typename T> struct DwPre { uint4 add[DW_TH], mask[DW_TH]; };
+__device__ __forceinline__ f8 unpack8(const uint4& t) {
+  f8 r;
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return r;
+}
+template <typename T, int MODE, bool FULL>
 __device__ __forceinline__ void dw_column(const T* __restrict__ col, int rstride, int C, const float (&wt)[3][3][8],
-                                          T* __restrict__ yp, int64_t ystride, int nrows) {
+                                          T* __restrict__ yp, int64_t ystride, int nrows, const DwPre<T>* pre = nullptr) {
   float acc[3][8];
 #pragma unroll
   for (int ri = 0; ri < DW_TH + 2; ++ri) {
@@ -55,10 +75,14 @@ __device__ __forceinline__ void dw_column(const T* __restrict__ col, int rstride
     if (od >= 0 && (FULL || od < nrows)) {
       const float* a = acc[od % 3];
       f8 o;
-      if (ACC) {
+      if (MODE == 1) {
         o = ld8(yp);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] += a[k];
+      } else if (MODE == 2) {
+        const f8 ad = unpack8(pre->add[od]), mk = unpack8(pre->mask[od]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = mk.v[k] > 0.f ? a[k] + ad.v[k] : 0.f;
       } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] = a[k];
@@ -72,12 +96,13 @@ __device__ __forceinline__ void dw_column(const T* __restrict__ col, int rstride
 // y[p,c] (+)= sum_taps x[p+tap,c] * w[c][tap]   (flip: 180-degree rotated filter = data gradient)
 // block = 256 threads = (C/8 channel groups) x TWp pixel columns; tile = DW_TH rows x TWp columns; two tile
 // buffers so the next tile's TMA load is in flight while this one is computed.
-template <typename T, bool ACC>
-__global__ void __launch_bounds__(kThreadsFe, 2)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreadsFe, MODE == 2 ? 1 : 2)
 dwconv_tile_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ w, T* __restrict__ y, int64_t ldy,
-                   int N, int H, int W, int C, int flip, int tiles_x, int tiles_y) {
+                   int N, int H, int W, int C, int flip, int tiles_x, int tiles_y, const T* __restrict__ add = nullptr,
+                   int64_t ldadd = 0, const T* __restrict__ mask = nullptr, int64_t ldmask = 0) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[kDwBufs];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int cg = C >> 3;
   const int TWp = kThreadsFe / cg;
@@ -98,38 +123,50 @@ dwconv_tile_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restr
   const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(T));
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmx);
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
+    for (int b = 0; b < kDwBufs; ++b) tc::mbar_init(&bars[b], 1);
     tc::fence_barrier_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) {
-    const TileXY t0 = tile_xy(blockIdx.x, tiles_x, tiles_y, TWp, DW_TH);
-    tc::mbar_expect_tx(&bars[0], tile_bytes);
-    tc::tma_load_4d(sm, &tmx, &bars[0], 0, t0.x0 - 1, t0.y0 - 1, t0.n);
-  }
+  auto load = [&](int b, int64_t tile) {
+    const TileXY t0 = tile_xy(tile, tiles_x, tiles_y, TWp, DW_TH);
+    tc::mbar_expect_tx(&bars[b], tile_bytes);
+    tc::tma_load_4d(sm + b * tile_elems, &tmx, &bars[b], 0, t0.x0 - 1, t0.y0 - 1, t0.n);
+  };
+  if (threadIdx.x == 0)
+    for (int b = 0; b < kDwBufs - 1; ++b)
+      if ((int64_t)blockIdx.x + (int64_t)b * gridDim.x < ntiles) load(b, blockIdx.x + (int64_t)b * gridDim.x);
   int buf = 0;
   uint32_t par = 0;                        // phase parity bit of each buffer's barrier
   const int rstride = PWs * C;
   const int64_t ystride = (int64_t)W * ldy;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const TileXY t = tile_xy(tile, tiles_x, tiles_y, TWp, DW_TH);
-    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) {   // (every read of that buffer ended before the last barrier)
-      const TileXY tn = tile_xy(tile + gridDim.x, tiles_x, tiles_y, TWp, DW_TH);
-      tc::mbar_expect_tx(&bars[buf ^ 1], tile_bytes);
-      tc::tma_load_4d(sm + (buf ^ 1) * tile_elems, &tmx, &bars[buf ^ 1], 0, tn.x0 - 1, tn.y0 - 1, tn.n);
+    // refill the buffer that was read in the previous round (every read of it ended before the last barrier)
+    const int nb = buf == 0 ? kDwBufs - 1 : buf - 1;
+    const int64_t nt = tile + (int64_t)(kDwBufs - 1) * gridDim.x;
+    if (threadIdx.x == 0 && nt < ntiles) load(nb, nt);
+    const int xx = t.x0 + tx;
+    DwPre<T> pre;
+    if (MODE == 2 && sizeof(T) == 2 && xx < W) {
+      const int64_t p0 = ((int64_t)t.n * H + t.y0) * W + xx;
+#pragma unroll
+      for (int r = 0; r < DW_TH; ++r) {
+        const bool ok = t.y0 + r < H;
+        pre.add[r] = ok ? *reinterpret_cast<const uint4*>(add + (p0 + (int64_t)r * W) * ldadd + c0) : make_uint4(0, 0, 0, 0);
+        pre.mask[r] = ok ? *reinterpret_cast<const uint4*>(mask + (p0 + (int64_t)r * W) * ldmask + c0) : make_uint4(0, 0, 0, 0);
+      }
     }
     tc::mbar_wait(&bars[buf], (par >> buf) & 1u);
     par ^= 1u << buf;
-    const int xx = t.x0 + tx;
     if (xx < W) {
       const T* col = sm + buf * tile_elems + tx * C + c0;                // this thread's column of the tile
       T* yp = y + (((int64_t)t.n * H + t.y0) * W + xx) * ldy + c0;
       const int nrows = H - t.y0;
-      if (nrows >= DW_TH) dw_column<T, ACC, true>(col, rstride, C, wt, yp, ystride, DW_TH);
-      else dw_column<T, ACC, false>(col, rstride, C, wt, yp, ystride, nrows);
+      if (nrows >= DW_TH) dw_column<T, MODE, true>(col, rstride, C, wt, yp, ystride, DW_TH, &pre);
+      else dw_column<T, MODE, false>(col, rstride, C, wt, yp, ystride, nrows, &pre);
     }
     __syncthreads();                       // every read of this buffer is done before the next round refills it
+    if (++buf == kDwBufs) buf = 0;
   }
 }
 
@@ -446,24 +483,27 @@ static bool encode_tile_map(CUtensorMap* m, const void* base, int64_t ld, int dt
 }
 
 int dwconv_slide(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int dtype, int N, int H, int W, int C,
-                 int flip, int accumulate, cudaStream_t s) {
+                 int flip, int accumulate, cudaStream_t s, const void* add, int64_t ldadd, const void* mask, int64_t ldmask) {
   const int TWp = kThreadsFe / (C >> 3);
   const int tiles_x = (W + TWp - 1) / TWp, tiles_y = (H + DW_TH - 1) / DW_TH;
   const int64_t ntiles = (int64_t)N * tiles_x * tiles_y;
-  const int blocks = (int)imax(1, imin(ntiles, kSMs * 2));
+  const bool masked = add != nullptr;                                          // (bf16 only: checked by the caller)
+  const int blocks = (int)imax(1, imin(ntiles, kSMs * (masked ? 1 : 2)));
   const size_t esz = dtype == NERVECL_F32 ? 4 : 2;
-  const size_t smem = 2 * (size_t)(DW_TH + 2) * (TWp + 2) * C * esz;          // two tile buffers
+  const size_t smem = kDwBufs * (size_t)(DW_TH + 2) * (TWp + 2) * C * esz;          // the tile buffers
   CUtensorMap tmx;
   if (!encode_tile_map(&tmx, x, ldx, dtype, N, H, W, C, TWp + 2, DW_TH + 2)) return NERVECL_EUNSUPPORTED;
   cudaError_t e;
-#define NV_DW_LAUNCH(E, A)                                                                                           \
+#define NV_DW_LAUNCH(E, A, ...)                                                                                      \
   e = cudaFuncSetAttribute(dwconv_tile_kernel<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
   if (e != cudaSuccess) return (int)e;                                                                              \
-  dwconv_tile_kernel<E, A><<<blocks, kThreadsFe, smem, s>>>(tmx, w, (E*)y, ldy, N, H, W, C, flip, tiles_x, tiles_y)
-  if (dtype == NERVECL_F32) {
-    if (accumulate) { NV_DW_LAUNCH(float, true); } else { NV_DW_LAUNCH(float, false); }
+  dwconv_tile_kernel<E, A><<<blocks, kThreadsFe, smem, s>>>(tmx, w, (E*)y, ldy, N, H, W, C, flip, tiles_x, tiles_y, ##__VA_ARGS__)
+  if (masked) {
+    NV_DW_LAUNCH(bf16, 2, (const bf16*)add, ldadd, (const bf16*)mask, ldmask);
+  } else if (dtype == NERVECL_F32) {
+    if (accumulate) { NV_DW_LAUNCH(float, 1); } else { NV_DW_LAUNCH(float, 0); }
   } else {
-    if (accumulate) { NV_DW_LAUNCH(bf16, true); } else { NV_DW_LAUNCH(bf16, false); }
+    if (accumulate) { NV_DW_LAUNCH(bf16, 1); } else { NV_DW_LAUNCH(bf16, 0); }
   }
 #undef NV_DW_LAUNCH
   return launch_status();

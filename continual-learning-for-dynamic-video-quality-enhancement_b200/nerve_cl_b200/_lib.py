@@ -61,6 +61,8 @@ _SIGNATURES = {
                                       C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_vp),
                                       C.POINTER(c_vp), c_f32, c_vp],
     "nervecl_dwconv3x3_fwd": [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "nervecl_dwconv3x3_fwd_masked": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32,
+                                     c_i32, c_i32, c_vp],
     "nervecl_dwconv3x3_wgrad": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "nervecl_bn_stats": [c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp],
     "nervecl_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_f32, c_f32, c_i32, c_vp],

@@ -716,10 +716,13 @@ class Plan:
             if j > 0:
                 nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], s2, True, False)
                 dy = s2
+            elif self.adt == torch.bfloat16 and self.engine != CONV_SIMT:
+                # extractor skip (feat = body(head) + head): d(head) = d(feat) + depthwise data gradient, gated by the
+                # head conv's ReLU -- one pass (s0 is free again: the pointwise gradients above consumed it)
+                nv.dwconv3x3_fwd_masked(s1, P[pre + "depthwise.weight"], ws["dfeat"], A.head, s0, True)
             else:
-                # extractor skip (feat = body(head) + head): d(head) = d(feat) + depthwise data gradient
                 nv.dwconv3x3_fwd(s1, P[pre + "depthwise.weight"], ws["dfeat"], True, True)
-        nv.relu_bwd(ws["dfeat"], A.head, None, ws["t"][0])
+                nv.relu_bwd(ws["dfeat"], A.head, None, s0)
         gw = G["feature_extractor.head.0.weight"]
         with self._span("conv_wgrad", A.x_in, 27, F, 1):
             nv.conv2d_wgrad(A.x_in[..., :27], ws["t"][0], gw.view(gw.shape[0], -1, 1, 1),

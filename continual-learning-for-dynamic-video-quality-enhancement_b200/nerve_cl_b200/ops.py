@@ -297,6 +297,17 @@ def _dwconv3x3_fwd(x, w, y, flip, accumulate) -> None:
                                                 int(accumulate), _stream()), "dwconv3x3_fwd")
 
 
+@_op("dwconv3x3_fwd_masked(Tensor x, Tensor w, Tensor add, Tensor mask, Tensor(a!) y, bool flip) -> ()")
+def _dwconv3x3_fwd_masked(x, w, add, mask, y, flip) -> None:
+    """y = (dwconv3x3(x) + add) where mask > 0, else 0 (``nervecl_dwconv3x3_fwd_masked``; bf16)."""
+    xp, ldx, n, h, wd, c = _nhwc(x, "x")
+    ap, lda, *_ = _nhwc(add, "add")
+    mp, ldm, *_ = _nhwc(mask, "mask")
+    yp, ldy, *_ = _nhwc(y, "y")
+    _lib.check(_lib.load().nervecl_dwconv3x3_fwd_masked(xp, ldx, _flat(w, "w"), ap, lda, mp, ldm, yp, ldy, _dt(x), n, h, wd,
+                                                       c, int(flip), _stream()), "dwconv3x3_fwd_masked")
+
+
 @_op("dwconv3x3_wgrad(Tensor x, Tensor dy, Tensor(a!) dw) -> ()")
 def _dwconv3x3_wgrad(x, dy, dw) -> None:
     xp, ldx, n, h, wd, c = _nhwc(x, "x")

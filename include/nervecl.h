@@ -201,6 +201,12 @@ int nervecl_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, void* y, i
                           nervecl_stream_t stream);
 int nervecl_dwconv3x3_wgrad(const void* x, int64_t ldx, const void* dy, int64_t ldy, int dtype,
                             float* dw, int N, int H, int W, int C, nervecl_stream_t stream);
+/* ABI v7: y = (dwconv3x3(x) + add) where mask > 0, else 0 -- the depthwise data gradient of the extractor's first body
+ * layer, the skip gradient of super_resolution.py:53 (feat = body(head) + head) and the ReLU of the head conv (:40-43)
+ * in one pass (bf16, TMA-tiled kernel only; y may not alias add or mask). */
+int nervecl_dwconv3x3_fwd_masked(const void* x, int64_t ldx, const float* w, const void* add, int64_t ldadd,
+                                 const void* mask, int64_t ldmask, void* y, int64_t ldy, int dtype,
+                                 int N, int H, int W, int C, int flip, nervecl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm2d + ReLU over `groups` consecutive image groups that each have their own batch

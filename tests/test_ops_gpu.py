@@ -97,6 +97,23 @@ def test_conv_wgrad_simt(shape):
     assert relerr(db, 0.5 * b.grad) <= TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 13, 40), (3, 64, 50, 70), (1, 32, 9, 130)])
+def test_depthwise_masked(shape):
+    """y = (dwconv3x3(x, flipped filter) + add) * (mask > 0): the extractor's first-layer data gradient + skip gradient +
+    head ReLU in one pass == the three separate ATen ops (ragged tiles in both directions)."""
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x, add, mask = (bf(torch.randn(n, c, h, w, generator=g)) for _ in range(3))
+    wt = torch.randn(c, 1, 3, 3, generator=g)
+    for flip in (False, True):
+        ref = (F.conv2d(x, wt.flip(2, 3) if flip else wt, None, 1, 1, 1, c) + add) * (mask > 0)
+        y = torch.full((n, h, w, c + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+        nv().dwconv3x3_fwd_masked(nhwc(x, torch.bfloat16), wt.cuda(), nhwc(add, torch.bfloat16, pad_to=c + 8),
+                                  nhwc(mask, torch.bfloat16), y[..., :c], flip)
+        assert relerr(nchw(y[..., :c]), ref) <= 2e-2
+        assert float((y[..., c:].float() - 7).abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_depthwise(dtype):
     g = torch.Generator().manual_seed(3)
