@@ -324,8 +324,8 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const float alpha = a.alpha;
     const bool vo = a.v256_out != 0, vi = a.v256_in != 0;
     const bool want_cs = a.colsum != nullptr;        // (host: only with kind 2 and NOUT <= 32, i.e. one chunk per thread)
-    const int smode = a.smode;                       // (host: only with NOUT <= 32)
-    const int sgrp = c_lo / 16 + part;               // this thread's 16-channel group of the sign words
+    const int smode = NC <= 2 ? a.smode : 0;       // (host: sign bits only with <= 64 output channels per CTA pair)
+    const int sgrp = c_lo / 16 + part;               // 16-channel group of the thread's first chunk (chunk i: sgrp + 2 i)
     // one register array serves both: the bias of the thread's first chunk (kind 1) or the running column sums (kind 2)
     float cs[16];
 #pragma unroll
@@ -363,12 +363,16 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       // sign words of rows oi .. oi + 3 (mode 2: 2 bytes per row instead of the 32-byte mask operand)
       const uint16_t* sp = a.sbits + (int64_t)sgrp * a.npix + p0;       // (a warp's 32 pixels: 64 contiguous bytes)
-      const int64_t sstride = a.W;
-      uint32_t sb0 = 0, sb1 = 0, sb2 = 0;
-      if (smode == 2 && valid && has[0]) {
-        sb0 = __ldg(sp);
-        if (rows > 1) sb1 = __ldg(sp + sstride);
-        if (rows > 2) sb2 = __ldg(sp + 2 * sstride);
+      const int64_t sstride = a.W, splane = 2 * a.npix;                 // next row / next chunk of this thread
+      uint32_t sb0[NC], sb1[NC], sb2[NC];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        sb0[i] = sb1[i] = sb2[i] = 0;
+        if (smode == 2 && valid && has[i]) {
+          sb0[i] = __ldg(sp + i * splane);
+          if (rows > 1) sb1[i] = __ldg(sp + i * splane + sstride);
+          if (rows > 2) sb2[i] = __ldg(sp + i * splane + 2 * sstride);
+        }
       }
       uint4 q1[2], q2[2];                           // NC == 1: rows oi + 1 and oi + 2 of the operand are in flight as well
       q1[0] = q1[1] = q2[0] = q2[1] = make_uint4(0, 0, 0, 0);
@@ -393,10 +397,14 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         uint4 cur[NC][2];
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cur[i][0] = pre[i][0]; cur[i][1] = pre[i][1]; }
-        const uint32_t sbc = sb0;
-        if (smode == 2) {
-          sb0 = sb1; sb1 = sb2;
-          if (valid && has[0] && oi + 3 < rows) sb2 = __ldg(sp + (int64_t)(oi + 3) * sstride);
+        uint32_t sbc[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          sbc[i] = sb0[i];
+          if (smode == 2) {
+            sb0[i] = sb1[i]; sb1[i] = sb2[i];
+            if (valid && has[i] && oi + 3 < rows) sb2[i] = __ldg(sp + i * splane + (int64_t)(oi + 3) * sstride);
+          }
         }
         if (NC == 1) {
           pre[0][0] = q1[0]; pre[0][1] = q1[1];
@@ -464,17 +472,17 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] += e[j];
               }
-              if (smode == 1 && i == 0) {             // (relu: every value is >= 0)
+              if (smode == 1) {                       // (relu: every value is >= 0)
                 uint32_t r8[8];
                 pack16(f, r8);
-                a.sbits[(int64_t)sgrp * a.npix + p0 + (int64_t)oi * a.W] = (uint16_t)sign_word16(r8);
+                a.sbits[(int64_t)(sgrp + 2 * i) * a.npix + p0 + (int64_t)oi * a.W] = (uint16_t)sign_word16(r8);
                 store16(op + ch[i], r8, vo);
                 continue;
               }
             } else if (kind == 2) {
               if (smode == 2) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = ((sbc >> sign_bit_pos(j)) & 1u) ? alpha * __uint_as_float(v[i][j]) : 0.f;
+                for (int j = 0; j < 16; ++j) f[j] = ((sbc[i] >> sign_bit_pos(j)) & 1u) ? alpha * __uint_as_float(v[i][j]) : 0.f;
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = e[j] > 0.f ? alpha * __uint_as_float(v[i][j]) : 0.f;
@@ -593,7 +601,7 @@ bool conv_rows2_supported(const nervecl_conv_params& a) {
   Pair2Plan p;
   if (!plan_rows2(a, sm_count(), p)) return false;
   if (a.colsum && !(kind == 2 && p.NOUT <= 32)) return false;
-  if (a.sign_mode && (p.NOUT > 32 || !a.sign_bits || (a.Cout & 15) || kind != a.sign_mode)) return false;
+  if (a.sign_mode && (p.NOUT > 64 || !a.sign_bits || (a.Cout & 15) || kind != a.sign_mode)) return false;
   return true;
 }
 

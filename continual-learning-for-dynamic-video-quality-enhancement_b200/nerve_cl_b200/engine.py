@@ -171,6 +171,8 @@ class Activations:
         # read back as the masks of the fused block backward; allocated on first use
         self.rdb_bits: Optional[List[List[Tensor]]] = None
         self.has_bits = False
+        self.sbits: Dict[object, Tensor] = {}     # the same for flow_net / attention activations, by (name, frame)
+        self.use_bits = False
 
 
 class Plan:
@@ -244,6 +246,7 @@ class Plan:
         # layer instead of 64 for every mask read of the block backward.  Switched off for the plan the first time the
         # library answers "unsupported" (shapes too small for the CTA-pair kernel).
         self.sign_bits = self.fused_rdb_bwd
+        self._bits_off = set()            # activations whose conv shape the sign-bit path does not take
 
     # ---- activation-set pool ---------------------------------------------------------------
     def acquire(self) -> Activations:
@@ -320,10 +323,37 @@ class Plan:
                           res_channels if res is not None else 0, 0, alpha, self.engine, None, False, None,
                           sign_bits, 1 if sign_bits is not None else 0)
 
+    def conv_signed(self, A: Activations, key, name: str, x: Tensor, out: Tensor, P, **kw) -> None:
+        """Forward conv + ReLU that also leaves the packed signs of its output in ``A.sbits[key]`` (for the data
+        gradient that will be gated by this activation) when the library takes the shape."""
+        if A.use_bits and key not in self._bits_off:
+            b = A.sbits.get(key)
+            if b is None:
+                b = torch.empty((self.convs[name].cout // 16,) + tuple(out.shape[:3]), device=self.device, dtype=torch.int16)
+            try:
+                self.conv(name, x, out, P, sign_bits=b, **kw)
+                A.sbits[key] = b
+                return
+            except RuntimeError as e:
+                if "not supported" not in str(e):
+                    raise
+                self._bits_off.add(key)
+                A.sbits.pop(key, None)
+        self.conv(name, x, out, P, **kw)
+
     def dgrad(self, name: str, dy: Tensor, out: Tensor, *, cout=None, accumulate=False, res=None, res_channels=0,
-              alpha=1.0, mask=None, mask_sub=None, mask_c0=0) -> None:
+              alpha=1.0, mask=None, mask_sub=None, mask_c0=0, bits=None) -> None:
+        """``bits``: packed signs of ``mask`` (written by ``conv_signed``); used instead of it where supported."""
         c = self.convs[name]
         with self._span("conv_dgrad", dy, dy.shape[-1], cout or c.cin_pad, c.k):
+            if bits is not None and mask is not None and not accumulate and res is None and mask_sub is None:
+                try:
+                    nv.conv2d_fwd(dy, self.wb[name], None, None, None, None, out, cout or c.cin_pad, False, False, 0, 0,
+                                  alpha, self.engine, None, False, None, bits, 2)
+                    return
+                except RuntimeError as e:
+                    if "not supported" not in str(e):
+                        raise
             nv.conv2d_fwd(dy, self.wb[name], None, res, mask, mask_sub, out, cout or c.cin_pad, False, accumulate,
                           res_channels if res is not None else 0, mask_c0, alpha, self.engine)
 
@@ -368,6 +398,9 @@ class Plan:
         B, T, H, W, F, s = self.B, self.T, self.H, self.W, self.F, self.scale
         A = self.acquire()
         A.training = training
+        A.use_bits = bool(need_bwd and self.sign_bits and self.engine != CONV_SIMT and self.adt == torch.bfloat16)
+        if not A.use_bits:
+            A.sbits.clear()                  # (a pooled activation set may hold another forward's signs)
         # Pure inference (eval mode, no backward) on the tcgen05 path: BatchNorm's running statistics are folded into
         # the pointwise conv -- W' = W * gamma / sqrt(var + eps) per output channel, b' = beta - mean * that -- so
         # conv + BN + ReLU (+ the extractor skip) is ONE conv launch with a bias / ReLU / residual epilogue and the
@@ -415,15 +448,15 @@ class Plan:
         nv.axpy(centre, A.cat[..., self.mid * F:(self.mid + 1) * F], 1.0, False)
         for t in self.others:
             nv.corr_fwd(feat[t], centre, A.corr[t])
-            self.conv("motion_estimator.flow_net.0", A.corr[t], A.fn1[t], P, relu=True)
-            self.conv("motion_estimator.flow_net.2", A.fn1[t], A.fn2[t], P, relu=True)
-            self.conv("motion_estimator.flow_net.4", A.fn2[t], A.fn3[t], P, relu=True)
+            self.conv_signed(A, ("fn1", t), "motion_estimator.flow_net.0", A.corr[t], A.fn1[t], P, relu=True)
+            self.conv_signed(A, ("fn2", t), "motion_estimator.flow_net.2", A.fn1[t], A.fn2[t], P, relu=True)
+            self.conv_signed(A, ("fn3", t), "motion_estimator.flow_net.4", A.fn2[t], A.fn3[t], P, relu=True)
             self.conv("motion_estimator.flow_net.6", A.fn3[t], A.flow[t], P)
             nv.warp_fwd(feat[t], A.flow[t], A.cat[..., t * F:(t + 1) * F], self.div_mode, None)
 
         # ---- temporal aggregation (super_resolution.py:194-209) ----
-        self.conv("temporal_aggregator.attention.0", A.cat, A.a1, P, relu=True)
-        self.conv("temporal_aggregator.attention.2", A.a1, A.a2, P, relu=True)
+        self.conv_signed(A, "a1", "temporal_aggregator.attention.0", A.cat, A.a1, P, relu=True)
+        self.conv_signed(A, "a2", "temporal_aggregator.attention.2", A.a1, A.a2, P, relu=True)
         self.conv("temporal_aggregator.attention.4", A.a2, A.logits, P)
         nv.tfuse_fwd(A.cat, A.logits, A.attn, A.blend)
         pre = "temporal_aggregator.refine."
@@ -436,7 +469,7 @@ class Plan:
         nv.cbam_apply_fwd(A.blend, A.gate, A.stats, P[pre + "spatial_attention.conv.weight"], A.sgate, trunk_in)
 
         # ---- residual dense blocks (super_resolution.py:245-253), concat-free ----
-        use_bits = need_bwd and self.sign_bits and self.engine != CONV_SIMT
+        use_bits = A.use_bits
         if use_bits and A.rdb_bits is None:
             A.rdb_bits = [[torch.empty((GROWTH // 16, B, H, W), device=self.device, dtype=torch.int16)
                            for _ in range(RDB_LAYERS)] for _ in range(self.NB)]
@@ -663,9 +696,9 @@ class Plan:
         dlog = ws["dlogits_a"][..., :T]
         nv.axpy(ws["dlogits"], dlog, 1.0, False)
         self.wgrad("temporal_aggregator.attention.4", A.a2, dlog, G, dy_padded=ws["dlogits_a"])
-        self.dgrad("temporal_aggregator.attention.4", ws["dlogits_a"], ws["da2"], mask=A.a2)
+        self.dgrad("temporal_aggregator.attention.4", ws["dlogits_a"], ws["da2"], mask=A.a2, bits=A.sbits.get("a2"))
         self.wgrad("temporal_aggregator.attention.2", A.a1, ws["da2"], G)
-        self.dgrad("temporal_aggregator.attention.2", ws["da2"], ws["da1"], mask=A.a1)
+        self.dgrad("temporal_aggregator.attention.2", ws["da2"], ws["da1"], mask=A.a1, bits=A.sbits.get("a1"))
         self.wgrad("temporal_aggregator.attention.0", A.cat, ws["da1"], G)
         self.dgrad("temporal_aggregator.attention.0", ws["da1"], ws["dcat"], accumulate=True)
         ready("temporal_aggregator.")
@@ -687,11 +720,11 @@ class Plan:
             dflow = ws["dflow_a"][..., :2]
             nv.axpy(ws["dflow"], dflow, 1.0, False)
             self.wgrad("motion_estimator.flow_net.6", A.fn3[t], dflow, G, dy_padded=ws["dflow_a"])
-            self.dgrad("motion_estimator.flow_net.6", ws["dflow_a"], ws["dfn3"], mask=A.fn3[t])
+            self.dgrad("motion_estimator.flow_net.6", ws["dflow_a"], ws["dfn3"], mask=A.fn3[t], bits=A.sbits.get(("fn3", t)))
             self.wgrad("motion_estimator.flow_net.4", A.fn2[t], ws["dfn3"], G)
-            self.dgrad("motion_estimator.flow_net.4", ws["dfn3"], ws["dfn2"], mask=A.fn2[t])
+            self.dgrad("motion_estimator.flow_net.4", ws["dfn3"], ws["dfn2"], mask=A.fn2[t], bits=A.sbits.get(("fn2", t)))
             self.wgrad("motion_estimator.flow_net.2", A.fn1[t], ws["dfn2"], G)
-            self.dgrad("motion_estimator.flow_net.2", ws["dfn2"], ws["dfn1"], mask=A.fn1[t])
+            self.dgrad("motion_estimator.flow_net.2", ws["dfn2"], ws["dfn1"], mask=A.fn1[t], bits=A.sbits.get(("fn1", t)))
             self.wgrad("motion_estimator.flow_net.0", A.corr[t][..., :CORR_CH], ws["dfn1"], G)
             self.dgrad("motion_estimator.flow_net.0", ws["dfn1"], ws["dcorr"])
             nv.corr_bwd(feat[t], centre, ws["dcorr"], dfeat[t], True, dfeat[self.mid], True, ws["dcorr_t"])

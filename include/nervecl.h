@@ -162,7 +162,7 @@ typedef struct nervecl_conv_params {
    * contiguous bytes; the bit order is what eight packed bf16x2 words give in three instructions each).  sign_mode 1: WRITE the signs of the written outputs (out > 0;
    * a forward conv with relu == 1).  sign_mode 2: READ them as the ReLU mask (v = 0 where the bit is clear; `mask` must
    * be NULL) -- the mask of relu'(y) of super_resolution.py:237 costs 2 bytes per pixel and 16 channels instead of 32.
-   * CTA-pair row kernel (3x3, bf16, Cout % 16 == 0, <= 32 output channels per CTA); NERVECL_EUNSUPPORTED otherwise. */
+   * CTA-pair row kernel (3x3, bf16, Cout % 16 == 0); NERVECL_EUNSUPPORTED otherwise. */
   void* sign_bits;
   int32_t sign_mode;
   int32_t reserved0;
