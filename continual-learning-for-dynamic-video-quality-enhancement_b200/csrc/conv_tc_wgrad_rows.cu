@@ -27,7 +27,7 @@ constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA, w
 constexpr int KC = 64;
 constexpr uint32_t ROWB = 128;
 // One pipeline stage = KPX pixels of a row (the GEMM's K extent per stage).  Measured at the cfg-2 dense block
-// (profiles/r02h_wgrad.md): 128 px x 2 stages 1.65 ms, 64 x 5 1.99 ms, 32 x 10 3.17 ms -- smaller stages spread the
+// (profiles/r02h_experiments.md): 128 px x 2 stages 1.65 ms, 64 x 5 1.99 ms, 32 x 10 3.17 ms -- smaller stages spread the
 // classes over more rows at a time and the L2 hit rate drops (40 % -> 26 %), so the deeper pipeline loses.
 #ifndef WG_KPX
 #define WG_KPX 128
