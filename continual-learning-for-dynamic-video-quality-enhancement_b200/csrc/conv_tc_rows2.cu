@@ -29,6 +29,9 @@ using namespace nv::tc;
 
 namespace {
 
+#ifndef R2_SKIP
+#define R2_SKIP 0
+#endif
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);     // warp 0 = TMA, warp 1 = MMA issuer (leader CTA), warps 2..9 = epilogue
 constexpr int KC = 64;
@@ -364,14 +367,14 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // sign words of rows oi .. oi + 3 (mode 2: 2 bytes per row instead of the 32-byte mask operand)
       const uint16_t* sp = a.sbits + (int64_t)sgrp * a.npix + p0;       // (a warp's 32 pixels: 64 contiguous bytes)
       const int64_t sstride = a.W, splane = 2 * a.npix;                 // next row / next chunk of this thread
-      uint32_t sb0[NC], sb1[NC], sb2[NC];
+      constexpr int SBQ = 8;                          // sign words in flight per chunk (2 bytes each: a deep queue is free)
+      uint32_t sbq[NC][SBQ];
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
-        sb0[i] = sb1[i] = sb2[i] = 0;
-        if (smode == 2 && valid && has[i]) {
-          sb0[i] = __ldg(sp + i * splane);
-          if (rows > 1) sb1[i] = __ldg(sp + i * splane + sstride);
-          if (rows > 2) sb2[i] = __ldg(sp + i * splane + 2 * sstride);
+#pragma unroll
+        for (int d = 0; d < SBQ; ++d) {
+          sbq[i][d] = 0;
+          if (smode == 2 && valid && has[i] && d < rows) sbq[i][d] = __ldg(sp + i * splane + (int64_t)d * sstride);
         }
       }
       uint4 q1[2], q2[2];                           // NC == 1: rows oi + 1 and oi + 2 of the operand are in flight as well
@@ -400,21 +403,12 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         uint32_t sbc[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-          sbc[i] = sb0[i];
+          sbc[i] = sbq[i][0];
           if (smode == 2) {
-            sb0[i] = sb1[i]; sb1[i] = sb2[i];
-            if (valid && has[i] && oi + 3 < rows) sb2[i] = __ldg(sp + i * splane + (int64_t)(oi + 3) * sstride);
-          }
-        }
-        if (NC == 1) {
-          pre[0][0] = q1[0]; pre[0][1] = q1[1];
-          q1[0] = q2[0]; q1[1] = q2[1];
-          if (has_e && valid && has[0] && oi + 3 < rows) load32B(ep + (int64_t)(oi + 3) * estride + ch[0], q2[0], q2[1], vi);
-        } else if (has_e && valid && oi + 1 < rows) {
-          const bf16* en = ep + (int64_t)(oi + 1) * estride;
 #pragma unroll
-          for (int i = 0; i < NC; ++i)
-            if (has[i]) load32B(en + ch[i], pre[i][0], pre[i][1], vi);
+            for (int d = 0; d + 1 < SBQ; ++d) sbq[i][d] = sbq[i][d + 1];
+            if (valid && has[i] && oi + SBQ < rows) sbq[i][SBQ - 1] = __ldg(sp + i * splane + (int64_t)(oi + SBQ) * sstride);
+          }
         }
         mbar_wait(&acc_full[slot], par);
         tc_fence_after();
@@ -444,7 +438,7 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
         for (int i = 0; i < NC; ++i)
           if (has[i]) tmem_st16_zero(tcol + (uint32_t)((part + 2 * i) * 16));
-        if (valid) {
+        if (valid && !R2_SKIP) {
 #pragma unroll
           for (int i = 0; i < NC; ++i) {
             if (!has[i]) continue;

@@ -71,6 +71,29 @@ def grouped_case():
     print(f"wgrad grouped dense block: {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF", flush=True)
 
 
+def slice_case(cin, with_x2, bits):
+    """A slice gradient of the fused dense-block backward: 3x3 over `cin` later-layer gradient channels (+ the block
+    gradient through the centre tap) -> 32 channels, gated by a ReLU mask (bf16 activation or packed sign bits)."""
+    g = torch.randn((B, H, W, 256), device=dev, dtype=torch.bfloat16)
+    db = torch.randn((B, H, W, 64), device=dev, dtype=torch.bfloat16)
+    act = torch.randn((B, H, W, 256), device=dev, dtype=torch.bfloat16)
+    out = torch.zeros((B, H, W, 256), device=dev, dtype=torch.bfloat16)
+    cpad = (cin + 63) // 64 * 64
+    w = torch.randn((9, 32, cpad + 64), device=dev, dtype=torch.bfloat16) * 0.05
+    cs = torch.zeros(32, device=dev)
+    sb = (torch.randint(0, 65536, (2, B, H, W), device=dev, dtype=torch.int32) - 32768).to(torch.int16)
+    x2 = db if with_x2 else None
+    if bits:
+        fn = lambda: nv.conv2d_fwd(g[..., 64:64 + cin], w, None, None, None, None, out[..., 192:224], 32, False, False, 0, 0,
+                                   1.0, ops.CONV_TC, x2, with_x2, cs, sb, 2)
+    else:
+        fn = lambda: nv.conv2d_fwd(g[..., 64:64 + cin], w, None, None, act[..., 96:128], None, out[..., 192:224], 32, False,
+                                   False, 0, 0, 1.0, ops.CONV_TC, x2, with_x2, cs)
+    ms = bench(fn)
+    nbytes = (cin + (64 if with_x2 else 0) + 32 + (0 if bits else 32)) * 2.0 * B * H * W
+    print(f"slice {cin:3d}{'+64c' if with_x2 else '    '} -> 32 {'bits' if bits else 'mask'}: {ms:7.3f} ms  {nbytes / ms / 1e6:6.0f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
     engines = [ops.CONV_TC, ops.CONV_TC_TAPS]
@@ -96,6 +119,11 @@ if __name__ == "__main__":
         fwd_case(128, 64, 3, 128, 64, eng2)
         fwd_case(192, 64, 3, 192, 64, eng2)
         fwd_case(64, 64, 3, 64, 64, eng2)
+    if which == "slices":
+        for bits in (False, True):
+            slice_case(64, False, bits)
+            for cin in (32, 64, 96, 128):
+                slice_case(cin, True, bits)
     if which == "align":
         # input channel slice starting on / off a 128-byte line of the 256-channel-pitch buffer (slice gradients)
         for cin, c0 in ((64, 128), (64, 160), (64, 96), (128, 64), (128, 96), (128, 32)):
