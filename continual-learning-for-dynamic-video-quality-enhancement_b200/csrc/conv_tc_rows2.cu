@@ -29,9 +29,6 @@ using namespace nv::tc;
 
 namespace {
 
-#ifndef R2_SKIP
-#define R2_SKIP 0
-#endif
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);     // warp 0 = TMA, warp 1 = MMA issuer (leader CTA), warps 2..9 = epilogue
 constexpr int KC = 64;
@@ -230,14 +227,28 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     PieceIter it(a, pair);
     int n_, strip_, y0_, rows;
     bool live_;
+    // (-DR2_PROF: clock64 breakdown of the issuer's and the epilogue's row loop, printed by pair 5; profiles/r02h_experiments.md)
+#ifdef R2_PROF
+    long long t_acc = 0, t_full = 0, t_mma = 0, t_rest = 0, tp0 = clock64(), tp1;
+    int nrows_p = 0;
+#define R2T(x) tp1 = clock64(); x += tp1 - tp0; tp0 = tp1;
+#else
+#define R2T(x)
+#endif
     while (it.next(0, n_, strip_, y0_, rows, live_)) {
       for (int ri = 0; ri < rows + 2; ++ri) {
+        R2T(t_rest)
         if (!acc_ready) mbar_wait(&acc_empty[s2], k2 & 1u);  // both CTAs drained + re-zeroed that slot
         acc_ready = false;
+        R2T(t_acc)
+#ifdef R2_PROF
+        ++nrows_p;
+#endif
         const uint32_t d = tmem_base + (uint32_t)(p * a.NOUT);
         for (int gi = 0; gi < ngrp; ++gi) {
           if (!ready) mbar_wait(&ch_full[stage], phase);
           tc_fence_after();
+          R2T(t_full)
           int nstage = stage + 1;
           uint32_t nphase = phase;
           if (nstage == a.stages) { nstage = 0; nphase ^= 1; }
@@ -275,6 +286,7 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (second_left) umma_commit_pair(&ch_empty[pend_stage]);
             if (!defer_stage) umma_commit_pair(&ch_empty[stage]);      // stage consumed when these MMAs retire
           }
+          R2T(t_mma)
           pend_stage = defer_stage ? stage : -1;
           if (gi == 0) pend = -1;
           ready = mbar_try_wait(&ch_full[nstage], nphase);
@@ -296,6 +308,11 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (pend >= 0) umma_commit_pair(&acc_full[pend]);
     }
     __syncwarp();
+#ifdef R2_PROF
+    if (pair == 5 && lane == 0 && blockIdx.y == 0)
+      printf("MMA issuer: rows %d  per row: wait acc_empty %lld  wait ch_full %lld  issue %lld  rest %lld\n", nrows_p,
+             t_acc / nrows_p, t_full / nrows_p, t_mma / nrows_p, t_rest / nrows_p);
+#endif
   } else if (warp >= 2) {
     // ================= epilogue (warps 2..9 of both CTAs) =================
     const int q = warp & 3;
@@ -334,6 +351,13 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
     for (int j = 0; j < 16; ++j) cs[j] = (kind == 1 && a.bias && has[0]) ? __ldg(a.bias + ch[0] + j) : 0.f;
 
+#ifdef R2_PROF
+    long long e_wait = 0, e_ld = 0, e_comp = 0, e_rel = 0, ep0 = clock64(), ep1;
+    int erows = 0;
+#define R2E(x) ep1 = clock64(); x += ep1 - ep0; ep0 = ep1;
+#else
+#define R2E(x)
+#endif
     int slot = 0;
     uint32_t par = 0;
     auto release = [&]() {
@@ -410,8 +434,13 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (valid && has[i] && oi + SBQ < rows) sbq[i][SBQ - 1] = __ldg(sp + i * splane + (int64_t)(oi + SBQ) * sstride);
           }
         }
+        R2E(e_comp)
         mbar_wait(&acc_full[slot], par);
         tc_fence_after();
+        R2E(e_wait)
+#ifdef R2_PROF
+        ++erows;
+#endif
         const uint32_t tcol = lane_addr + (uint32_t)(slot * a.NOUT);
         uint32_t v[NC][16];
 #pragma unroll
@@ -438,7 +467,8 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
         for (int i = 0; i < NC; ++i)
           if (has[i]) tmem_st16_zero(tcol + (uint32_t)((part + 2 * i) * 16));
-        if (valid && !R2_SKIP) {
+        R2E(e_ld)
+        if (valid) {
 #pragma unroll
           for (int i = 0; i < NC; ++i) {
             if (!has[i]) continue;
@@ -493,9 +523,16 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
         op += ostride;
+        R2E(e_comp)
         release();
+        R2E(e_rel)
       }
     }
+#ifdef R2_PROF
+    if (pair == 5 && lane == 0 && blockIdx.y == 0 && rank == 0 && (warp == 2 || warp == 7))
+      printf("epilogue warp %d: rows %d  per row: wait acc_full %lld  tmem ld/zero %lld  compute+store %lld  release %lld\n", warp,
+             erows, e_wait / erows, e_ld / erows, e_comp / erows, e_rel / erows);
+#endif
     if (want_cs && has[0]) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
