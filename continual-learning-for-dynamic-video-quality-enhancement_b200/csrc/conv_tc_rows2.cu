@@ -434,6 +434,17 @@ conv_rows2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (valid && has[i] && oi + SBQ < rows) sbq[i][SBQ - 1] = __ldg(sp + i * splane + (int64_t)(oi + SBQ) * sstride);
           }
         }
+        // the operand rows behind the current one: NC == 1 keeps rows oi + 1 .. oi + 3 in flight, wider threads row oi + 1
+        if (NC == 1) {
+          pre[0][0] = q1[0]; pre[0][1] = q1[1];
+          q1[0] = q2[0]; q1[1] = q2[1];
+          if (has_e && valid && has[0] && oi + 3 < rows) load32B(ep + (int64_t)(oi + 3) * estride + ch[0], q2[0], q2[1], vi);
+        } else if (has_e && valid && oi + 1 < rows) {
+          const bf16* en = ep + (int64_t)(oi + 1) * estride;
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+            if (has[i]) load32B(en + ch[i], pre[i][0], pre[i][1], vi);
+        }
         R2E(e_comp)
         mbar_wait(&acc_full[slot], par);
         tc_fence_after();
