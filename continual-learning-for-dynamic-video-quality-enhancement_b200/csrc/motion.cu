@@ -262,6 +262,53 @@ __device__ __forceinline__ void atomic_add8(bf16* p, float w, const f8& g) {
                : "memory");
 }
 
+// eight elements as loaded (bf16: one 16-byte register quad; converted to fp32 where they are used, so that a
+// prefetched pixel costs 4 registers per vector instead of 8)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ static Raw8 zero() { Raw8 r; r.u = make_uint4(0, 0, 0, 0); return r; }
+  __device__ __forceinline__ f8 f() const {
+    f8 r;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+    return r;
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ static Raw8 zero() { Raw8 r; r.a = r.b = make_float4(0.f, 0.f, 0.f, 0.f); return r; }
+  __device__ __forceinline__ f8 f() const { return f8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}}; }
+};
+__device__ __forceinline__ Raw8<bf16> ldraw(const bf16* p) { Raw8<bf16> r; r.u = *reinterpret_cast<const uint4*>(p); return r; }
+__device__ __forceinline__ Raw8<float> ldraw(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+
+// the same reductions for an already-weighted contribution vector
+__device__ __forceinline__ void red_add8(float* p, const f8& c) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(c.v[0], c.v[1], c.v[2], c.v[3]));
+  atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(c.v[4], c.v[5], c.v[6], c.v[7]));
+}
+__device__ __forceinline__ void red_add8(bf16* p, const f8& c) {
+  uint32_t r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(c.v[2 * i], c.v[2 * i + 1]);
+    r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  // (no "memory" clobber: the reductions go to a buffer nothing in the kernel reads, and the clobber would pin every later
+  //  load behind them -- one exposed DRAM latency per pixel of the run)
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]));
+}
+
 // Backward warp, same two phases as the forward (the C/8 lanes of a pixel used to replay the coordinate sequence
 // each: issue-bound at 68 % with the L2 reductions idle a third of the time): phase A one pixel per LANE, phase B the
 // lanes regrouped as (pixel, 8-channel vector) with the pixel's corner weights broadcast by shuffles; the flow
@@ -290,71 +337,124 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
     vmask = (yin0 && xin0 ? 1u : 0u) | (yin0 && xin1 ? 2u : 0u) | (yin1 && xin0 ? 4u : 0u) | (yin1 && xin1 ? 8u : 0u) | 16u;
     q = (r - y) * W + c.y0 * W + c.x0;
   }
-  // ---- phase B: lane = (pixel of the group, 8-channel vector) ----
+  // ---- phase B: lane = (run of consecutive pixels, 8-channel vector) ----
+  // A lane group walks cg CONSECUTIVE pixels.  With a smooth flow the north-east / south-east targets of one pixel are the
+  // north-west / south-west targets of the next, so those contributions are carried in registers and leave as ONE
+  // reduction per target and source row (2 per pixel and vector instead of 4: the scatter is bound by L2 reduction
+  // operations, profiles/r01z_summary.md).  Carries that do not meet their successor are flushed on their own.
   const int cg = C >> 3;
-  const int ppi = 32 / cg;
   const int c0 = (lane % cg) << 3;
   const int sub = lane / cg;
   const int pbase = p - lane;
   // d ix / d flow_x = ((W-1)/2) * (2 * 1/(W-1)), evaluated in the reference's order
   const float mx = ((float)(W - 1) * 0.5f) * (2.0f * inv_w);
   const float my = ((float)(H - 1) * 0.5f) * (2.0f * inv_h);
-#pragma unroll 2
+  f8 ct, cb;                                                         // carried north-east / south-east contributions
+  int qt = -1, qb = -1;                                              // their target pixels (-1: none)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ct.v[k] = cb.v[k] = 0.f;
+  // One pixel's operands, requested one iteration ahead of their use (the reductions of pixel i are issued while the loads
+  // of pixel i + 1 are in flight; a straight loop exposes one DRAM latency per pixel of the run).
+  struct Item {
+    Raw8<T> g, v0, v1, v2, v3;
+    float ax0, ax1, ay0, ay1;
+    int qq;
+    unsigned vm;
+  };
+  auto fetch = [&](int it, Item& I) {
+    const int src = sub * cg + it;
+    I.ax0 = __shfl_sync(0xffffffffu, wx0, src); I.ax1 = __shfl_sync(0xffffffffu, wx1, src);
+    I.ay0 = __shfl_sync(0xffffffffu, wy0, src); I.ay1 = __shfl_sync(0xffffffffu, wy1, src);
+    I.qq = __shfl_sync(0xffffffffu, q, src);
+    I.vm = __shfl_sync(0xffffffffu, vmask, src);
+    const T* fb = feat + (int64_t)I.qq * ldf_ + c0;
+    I.g = (I.vm & 16u) ? ldraw(dout + (int64_t)(pbase + src) * lddo + c0) : Raw8<T>::zero();
+    I.v0 = (I.vm & 1u) ? ldraw(fb) : Raw8<T>::zero();
+    I.v1 = (I.vm & 2u) ? ldraw(fb + ldf_) : Raw8<T>::zero();
+    I.v2 = (I.vm & 4u) ? ldraw(fb + (int64_t)W * ldf_) : Raw8<T>::zero();
+    I.v3 = (I.vm & 8u) ? ldraw(fb + (int64_t)(W + 1) * ldf_) : Raw8<T>::zero();
+  };
+  Item cur;
+  fetch(0, cur);
   for (int it = 0; it < cg; ++it) {
-    const int src = it * ppi + sub;
-    const float ax0 = __shfl_sync(0xffffffffu, wx0, src), ax1 = __shfl_sync(0xffffffffu, wx1, src);
-    const float ay0 = __shfl_sync(0xffffffffu, wy0, src), ay1 = __shfl_sync(0xffffffffu, wy1, src);
-    const int qq = __shfl_sync(0xffffffffu, q, src);
-    const unsigned vm = __shfl_sync(0xffffffffu, vmask, src);
+    Item nxt = cur;
+    if (it + 1 < cg) fetch(it + 1, nxt);                             // (warp-uniform: the shuffles inside are full-warp)
+    const int src = sub * cg + it;
+    const float ax0 = cur.ax0, ax1 = cur.ax1, ay0 = cur.ay0, ay1 = cur.ay1;
+    const int qq = cur.qq;
+    const unsigned vm = cur.vm;
     float gix = 0.f, giy = 0.f;
+    f8 nt, nb;
+    int nqt = -1, nqb = -1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nt.v[k] = nb.v[k] = 0.f;
     if (vm & 16u) {
-      const f8 g = ld8(dout + (int64_t)(pbase + src) * lddo + c0);
-      const T* fb = feat + (int64_t)qq * ldf_ + c0;
-      AT* db = dfeat + (int64_t)qq * lddf + c0;
+      const f8 g = cur.g.f();
       if (vm & 1u) {
-        const f8 v = ld8(fb);
-        atomic_add8(db, ax0 * ay0, g);
+        const f8 v = cur.v0.f();
+        const float w = ax0 * ay0;
+        const bool merge = qt == qq;
+        f8 c;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          c.v[k] = w * g.v[k] + (merge ? ct.v[k] : 0.f);
           gix -= v.v[k] * ay0 * g.v[k];
           giy -= v.v[k] * ax0 * g.v[k];
         }
+        if (merge) qt = -1;
+        red_add8(dfeat + (int64_t)qq * lddf + c0, c);
       }
       if (vm & 2u) {
-        const f8 v = ld8(fb + ldf_);
-        atomic_add8(db + lddf, ax1 * ay0, g);
+        const f8 v = cur.v1.f();
+        const float w = ax1 * ay0;
+        nqt = qq + 1;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          nt.v[k] = w * g.v[k];
           gix += v.v[k] * ay0 * g.v[k];
           giy -= v.v[k] * ax1 * g.v[k];
         }
       }
       if (vm & 4u) {
-        const f8 v = ld8(fb + (int64_t)W * ldf_);
-        atomic_add8(db + (int64_t)W * lddf, ax0 * ay1, g);
+        const f8 v = cur.v2.f();
+        const float w = ax0 * ay1;
+        const bool merge = qb == qq + W;
+        f8 c;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          c.v[k] = w * g.v[k] + (merge ? cb.v[k] : 0.f);
           gix -= v.v[k] * ay1 * g.v[k];
           giy += v.v[k] * ax0 * g.v[k];
         }
+        if (merge) qb = -1;
+        red_add8(dfeat + (int64_t)(qq + W) * lddf + c0, c);
       }
       if (vm & 8u) {
-        const f8 v = ld8(fb + (int64_t)(W + 1) * ldf_);
-        atomic_add8(db + (int64_t)(W + 1) * lddf, ax1 * ay1, g);
+        const f8 v = cur.v3.f();
+        const float w = ax1 * ay1;
+        nqb = qq + W + 1;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          nb.v[k] = w * g.v[k];
           gix += v.v[k] * ay1 * g.v[k];
           giy += v.v[k] * ax1 * g.v[k];
         }
       }
     }
+    // carries that did not meet this pixel's north-west / south-west targets
+    if (qt >= 0) red_add8(dfeat + (int64_t)qt * lddf + c0, ct);
+    if (qb >= 0) red_add8(dfeat + (int64_t)qb * lddf + c0, cb);
+    ct = nt; cb = nb; qt = nqt; qb = nqb;
     for (int o = cg >> 1; o > 0; o >>= 1) {
       gix += __shfl_xor_sync(0xffffffffu, gix, o);
       giy += __shfl_xor_sync(0xffffffffu, giy, o);
     }
     if ((vm & 16u) && (lane % cg) == 0)
       reinterpret_cast<float2*>(dflow)[pbase + src] = make_float2(gix * mx, giy * my);
+    cur = nxt;
   }
+  if (qt >= 0) red_add8(dfeat + (int64_t)qt * lddf + c0, ct);
+  if (qb >= 0) red_add8(dfeat + (int64_t)qb * lddf + c0, cb);
 }
 
 }  // namespace

@@ -39,6 +39,7 @@ corr = torch.empty(N, H, W, 96, device=dev, dtype=bf)
 g = torch.randn(N, H, W, 96, device=dev).to(bf)
 d1, d2 = torch.empty_like(x1), torch.empty_like(x2)
 flow = (torch.rand(N, H, W, 2, device=dev) - 0.5) * 6
+flow_smooth = 0.3 + 0.05 * torch.randn(N, H, W, 2, device=dev)       # what flow_net produces: neighbours share their corners
 out = torch.empty_like(x1)
 dfeat = torch.zeros_like(x1)
 dflow = torch.empty_like(flow)
@@ -51,6 +52,8 @@ rows = {
     "corr_bwd_mma": ((96 * e + 4 * C * e) * px, lambda: nv.corr_bwd(x1, x2, g, d1, False, d2, False)),
     "warp_fwd": ((2 * C * e + 8) * px, lambda: nv.warp_fwd(x1, flow, out, 0, None)),
     "warp_bwd_lp": ((3 * C * e + 16) * px, lambda: nv.warp_bwd_lp(x1, flow, g[..., :C], dfeat, dflow, 0)),
+    "warp_fwd_smooth": ((2 * C * e + 8) * px, lambda: nv.warp_fwd(x1, flow_smooth, out, 0, None)),
+    "warp_bwd_lp_smooth": ((3 * C * e + 16) * px, lambda: nv.warp_bwd_lp(x1, flow_smooth, g[..., :C], dfeat, dflow, 0)),
 }
 only = sys.argv[1:] or list(rows)
 for k in only:

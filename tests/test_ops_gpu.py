@@ -333,8 +333,9 @@ def test_warp_backward_bf16_packed_reductions():
     assert torch.equal(dfl16, dfl32)
 
 
-def test_temporal_fusion():
-    T, B, C, H, W = 3, 2, 16, 7, 9
+@pytest.mark.parametrize("shape", [(3, 2, 16, 7, 9), (5, 1, 64, 21, 37), (1, 2, 8, 3, 5), (8, 1, 32, 9, 11)])
+def test_temporal_fusion(shape):
+    T, B, C, H, W = shape
     g = torch.Generator().manual_seed(10)
     feats = torch.randn(B, T, C, H, W, generator=g, requires_grad=True)
     logits = torch.randn(B, T, H, W, generator=g, requires_grad=True)
@@ -355,9 +356,10 @@ def test_temporal_fusion():
     assert relerr(dlg.permute(0, 3, 1, 2), logits.grad) <= TOL
 
 
-def test_cbam_forward_backward():
+@pytest.mark.parametrize("shape", [(2, 32, 11, 13), (1, 64, 19, 45), (2, 8, 33, 70)])
+def test_cbam_forward_backward(shape):
     from oracle import sr_oracle
-    B, C, H, W = 2, 32, 11, 13
+    B, C, H, W = shape
     g = torch.Generator().manual_seed(11)
     x = torch.randn(B, C, H, W, generator=g, requires_grad=True)
     sd = {"temporal_aggregator.refine.channel_attention.fc.0.weight": torch.randn(2, C, generator=g).requires_grad_(True),
@@ -393,9 +395,10 @@ def test_cbam_forward_backward():
     assert relerr(dw1, w1.grad) <= TOL and relerr(dw2, w2.grad) <= TOL and relerr(dw7, w7.grad) <= TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 9, 12), (1, 37, 70), (3, 5, 131)])
 @pytest.mark.parametrize("s", [2, 3, 4])
-def test_output_stage(s):
-    B, H, W = 2, 9, 12
+def test_output_stage(s, shape):
+    B, H, W = shape
     g = torch.Generator().manual_seed(12 + s)
     conv = (0.3 * torch.randn(B, 3 * s * s, H, W, generator=g)).requires_grad_(True)
     lr = torch.rand(B, 5, 3, H, W, generator=g)[:, 2]            # strided view like lr_frames[:, mid]
@@ -425,6 +428,19 @@ def test_elementwise_helpers():
     x3 = torch.randn(2, 3, 5, 7, generator=g)
     nv().axpy(nhwc(x3), o3[..., :3], 1.0, False)                 # scalar path (C % 4 != 0)
     assert relerr(nchw(o3[..., :3]), x3) <= 1e-2
+    # 8-wide path: C % 8 == 0, strided source and destination rows, copy and accumulate, bf16 and fp32
+    x8, y8 = torch.randn(3, 64, 9, 21, generator=g), torch.randn(3, 64, 9, 21, generator=g)
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        sbuf = torch.zeros((3, 9, 21, 192), device="cuda", dtype=dt)
+        dbuf = torch.zeros((3, 9, 21, 80), device="cuda", dtype=dt)
+        sbuf[..., 64:128] = x8.permute(0, 2, 3, 1).to("cuda", dt)
+        dbuf[..., :64] = y8.permute(0, 2, 3, 1).to("cuda", dt)
+        src, dst = sbuf[..., 64:128], dbuf[..., :64]
+        ref_y = nchw(dst).clone()
+        nv().axpy(src, dst, -1.5, True)
+        assert relerr(nchw(dst), ref_y - 1.5 * nchw(src)) <= tol
+        nv().axpy(src, dst, 1.0, False)
+        assert torch.equal(dst, src) and float(dbuf[..., 64:].abs().max()) == 0.0
     out = torch.empty(2, 5, 7, 16, device="cuda")
     nv().relu_bwd(nhwc(x), nhwc(y), None, out)
     assert torch.equal(nchw(out).cpu(), x * (y > 0))
