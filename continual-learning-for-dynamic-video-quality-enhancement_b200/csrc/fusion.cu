@@ -265,7 +265,7 @@ cbam_stats_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
     float s = 0.f, m = -INFINITY;
     if (active) {
       f8 v = ld8(x + p * ldx + c0);
-      const float* g = gate + (p / pix) * C + c0;
+      const float* g = gate + (small ? (int64_t)((uint32_t)p / (uint32_t)pix) : p / pix) * C + c0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float xs = v.v[k] * __ldg(g + k);
@@ -362,7 +362,7 @@ cbam_bwd_dz_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
     if (active) {
       f8 v = ld8(x + p * ldx + c0);
       f8 d = ld8(dy + p * lddy + c0);
-      const float* g = gate + (p / pix) * C + c0;
+      const float* g = gate + (small ? (int64_t)((uint32_t)p / (uint32_t)pix) : p / pix) * C + c0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) s = fmaf(d.v[k], v.v[k] * __ldg(g + k), s);
     }
