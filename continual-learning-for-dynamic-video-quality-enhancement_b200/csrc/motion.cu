@@ -171,97 +171,6 @@ __device__ __forceinline__ WarpCoord warp_coord(int x, int y, float fx, float fy
   return c;
 }
 
-// Forward warp.  The first version gave each pixel C/8 adjacent lanes that ALL replayed the ~70-instruction
-// coordinate sequence: 69 warp instructions per pixel, instruction-issue bound at 0.40 of the HBM roofline
-// (profiles/r01z_summary.md).  Here a warp owns 32 consecutive pixels: phase A computes one pixel per LANE
-// (coalesced flow load, coordinates, corner weights, validity), phase B walks the 32 pixels 32/cg at a time with
-// the lanes regrouped as (pixel, 8-channel vector) and the pixel's parameters broadcast by shuffles.
-template <typename T>
-__global__ void __launch_bounds__(256)
-warp_fwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow, T* __restrict__ out,
-                int64_t ldo, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode,
-                int32_t* __restrict__ idx_out) {
-  const int lane = threadIdx.x & 31;
-  const int npix = N * H * W;                                        // (< 2^31: checked by the launcher)
-  const int p = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
-  // ---- phase A: lane = pixel ----
-  float wnw = 0.f, wne = 0.f, wsw = 0.f, wse = 0.f;
-  int q = 0;                                                         // pixel index of the north-west corner
-  unsigned vmask = 0;                                                // bit0 nw, bit1 ne, bit2 sw, bit3 se, bit4 active
-  if (p < npix) {
-    const int x = p % W, r = p / W;
-    const int y = r % H;
-    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
-    const WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
-    if (idx_out) {
-      idx_out[(int64_t)p * 2] = (int)c.x0f;
-      idx_out[(int64_t)p * 2 + 1] = (int)c.y0f;
-    }
-    const float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
-    wnw = (x1f - c.ix) * (y1f - c.iy);
-    wne = (c.ix - c.x0f) * (y1f - c.iy);
-    wsw = (x1f - c.ix) * (c.iy - c.y0f);
-    wse = (c.ix - c.x0f) * (c.iy - c.y0f);
-    const bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
-    const bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
-    vmask = (yin0 && xin0 ? 1u : 0u) | (yin0 && xin1 ? 2u : 0u) | (yin1 && xin0 ? 4u : 0u) | (yin1 && xin1 ? 8u : 0u) | 16u;
-    q = (r - y) * W + c.y0 * W + c.x0;                               // n*H*W + y0*W + x0 (only used where valid)
-  }
-  // ---- phase B: lane = (pixel of the group, 8-channel vector) ----
-  const int cg = C >> 3;                                             // lanes per pixel (power of two <= 32)
-  const int ppi = 32 / cg;                                           // pixels per iteration
-  const int c0 = (lane % cg) << 3;
-  const int sub = lane / cg;
-  const int pbase = p - lane;
-#pragma unroll 2
-  for (int it = 0; it < cg; ++it) {
-    const int src = it * ppi + sub;
-    const float a = __shfl_sync(0xffffffffu, wnw, src), b = __shfl_sync(0xffffffffu, wne, src);
-    const float c = __shfl_sync(0xffffffffu, wsw, src), d = __shfl_sync(0xffffffffu, wse, src);
-    const int qq = __shfl_sync(0xffffffffu, q, src);
-    const unsigned vm = __shfl_sync(0xffffffffu, vmask, src);
-    if (vm & 16u) {
-      const T* base = feat + (int64_t)qq * ldf_ + c0;
-      const f8 z = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
-      const f8 v0 = (vm & 1u) ? ld8(base) : z;
-      const f8 v1 = (vm & 2u) ? ld8(base + ldf_) : z;
-      const f8 v2 = (vm & 4u) ? ld8(base + (int64_t)W * ldf_) : z;
-      const f8 v3 = (vm & 8u) ? ld8(base + (int64_t)(W + 1) * ldf_) : z;
-      f8 o;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {                                  // (nw, ne, sw, se; fused multiply-adds from zero)
-        float acc = fmaf(v0.v[k], a, 0.f);
-        acc = fmaf(v1.v[k], b, acc);
-        acc = fmaf(v2.v[k], c, acc);
-        acc = fmaf(v3.v[k], d, acc);
-        o.v[k] = acc;
-      }
-      st8(out + (int64_t)(pbase + src) * ldo + c0, o);
-    }
-  }
-}
-
-// blockDim multiple of 32; the cg (= C/8, power of two <= 32) threads of one pixel are adjacent
-// lanes, so the flow gradient is reduced with xor-shuffles.
-// 8 consecutive fp32 accumulations as two 128-bit vector reductions (red.global.add.v4.f32, sm_90+)
-__device__ __forceinline__ void atomic_add8(float* p, float w, const f8& g) {
-  atomicAdd(reinterpret_cast<float4*>(p), make_float4(w * g.v[0], w * g.v[1], w * g.v[2], w * g.v[3]));
-  atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(w * g.v[4], w * g.v[5], w * g.v[6], w * g.v[7]));
-}
-
-// 8 consecutive bf16 accumulations as ONE 128-bit packed reduction (red.global.add.noftz.v4.bf16x2): half the
-// L2 reduction operations of the fp32 form, which is what bounds the scatter (one 16-byte RED per L2 slice clock)
-__device__ __forceinline__ void atomic_add8(bf16* p, float w, const f8& g) {
-  uint32_t r[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(w * g.v[2 * i], w * g.v[2 * i + 1]);
-    r[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
-               : "memory");
-}
-
 // eight elements as loaded (bf16: one 16-byte register quad; converted to fp32 where they are used, so that a
 // prefetched pixel costs 4 registers per vector instead of 8)
 template <typename T> struct Raw8;
@@ -292,6 +201,120 @@ __device__ __forceinline__ Raw8<float> ldraw(const float* p) {
   return r;
 }
 
+constexpr int WP_W = 8, WP_H = 4;                  // pixel patch of a warp (WP_W * WP_H == 32)
+
+// Forward warp.  The first version gave each pixel C/8 adjacent lanes that ALL replayed the ~70-instruction
+// coordinate sequence: 69 warp instructions per pixel, instruction-issue bound at 0.40 of the HBM roofline
+// (profiles/r01z_summary.md).  Here a warp owns 32 consecutive pixels: phase A computes one pixel per LANE
+// (coalesced flow load, coordinates, corner weights, validity), phase B walks the 32 pixels 32/cg at a time with
+// the lanes regrouped as (pixel, 8-channel vector) and the pixel's parameters broadcast by shuffles.
+template <typename T, int CGT>                     // CGT: C / 8 at compile time (the pixel loop unrolls fully), 0 = run time
+__global__ void __launch_bounds__(256)
+warp_fwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow, T* __restrict__ out,
+                int64_t ldo, int N, int H, int W, int C, float inv_w, float inv_h, int div_mode,
+                int32_t* __restrict__ idx_out) {
+  const int lane = threadIdx.x & 31;
+  // a warp owns a WP_H x WP_W pixel patch (not 32 pixels of one row): the south corners of one patch row are the north
+  // corners of the next, so they hit in L1 instead of travelling from L2 once per row
+  const int ppx = (W + WP_W - 1) / WP_W, ppy = (H + WP_H - 1) / WP_H;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int patch_x = wid % ppx, pr = wid / ppx;
+  const int n_img = pr / ppy;
+  if (n_img >= N) return;                                            // (whole warps)
+  const int x = patch_x * WP_W + lane % WP_W, y = (pr - n_img * ppy) * WP_H + lane / WP_W;
+  const int p = (n_img * H + y) * W + x;                             // (< 2^31: checked by the launcher)
+  // ---- phase A: lane = pixel ----
+  float wnw = 0.f, wne = 0.f, wsw = 0.f, wse = 0.f;
+  int q = 0;                                                         // pixel index of the north-west corner
+  unsigned vmask = 0;                                                // bit0 nw, bit1 ne, bit2 sw, bit3 se, bit4 active
+  if (x < W && y < H) {
+    const int r = n_img * H + y;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+    const WarpCoord c = warp_coord(x, y, f.x, f.y, W, H, inv_w, inv_h, div_mode);
+    if (idx_out) {
+      idx_out[(int64_t)p * 2] = (int)c.x0f;
+      idx_out[(int64_t)p * 2 + 1] = (int)c.y0f;
+    }
+    const float x1f = c.x0f + 1.f, y1f = c.y0f + 1.f;
+    wnw = (x1f - c.ix) * (y1f - c.iy);
+    wne = (c.ix - c.x0f) * (y1f - c.iy);
+    wsw = (x1f - c.ix) * (c.iy - c.y0f);
+    wse = (c.ix - c.x0f) * (c.iy - c.y0f);
+    const bool xin0 = c.x0 >= 0 && c.x0 < W, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < W;
+    const bool yin0 = c.y0 >= 0 && c.y0 < H, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < H;
+    vmask = (yin0 && xin0 ? 1u : 0u) | (yin0 && xin1 ? 2u : 0u) | (yin1 && xin0 ? 4u : 0u) | (yin1 && xin1 ? 8u : 0u) | 16u;
+    q = (r - y) * W + c.y0 * W + c.x0;                               // n*H*W + y0*W + x0 (only used where valid)
+  }
+  // ---- phase B: lane = (pixel of the group, 8-channel vector) ----
+  // The four corner vectors of the NEXT group of pixels are requested (as raw 16-byte registers) before the current
+  // group is blended and stored: two groups of loads in flight per lane instead of one.
+  const int cg = CGT ? CGT : (C >> 3);                               // lanes per pixel (power of two <= 32)
+  const int ppi = 32 / cg;                                           // pixels per iteration
+  const int c0 = (lane % cg) << 3;
+  const int sub = lane / cg;
+  struct Item {
+    Raw8<T> v0, v1, v2, v3;
+    float a, b, c, d;
+    unsigned vm;
+    int pp;                                                          // the pixel's linear index
+  };
+  auto fetch = [&](int it, Item& I) {
+    const int src = it * ppi + sub;
+    I.a = __shfl_sync(0xffffffffu, wnw, src); I.b = __shfl_sync(0xffffffffu, wne, src);
+    I.c = __shfl_sync(0xffffffffu, wsw, src); I.d = __shfl_sync(0xffffffffu, wse, src);
+    const int qq = __shfl_sync(0xffffffffu, q, src);
+    I.vm = __shfl_sync(0xffffffffu, vmask, src);
+    I.pp = __shfl_sync(0xffffffffu, p, src);
+    const T* base = feat + (int64_t)qq * ldf_ + c0;
+    I.v0 = (I.vm & 1u) ? ldraw(base) : Raw8<T>::zero();
+    I.v1 = (I.vm & 2u) ? ldraw(base + ldf_) : Raw8<T>::zero();
+    I.v2 = (I.vm & 4u) ? ldraw(base + (int64_t)W * ldf_) : Raw8<T>::zero();
+    I.v3 = (I.vm & 8u) ? ldraw(base + (int64_t)(W + 1) * ldf_) : Raw8<T>::zero();
+  };
+  Item cur;
+  fetch(0, cur);
+#pragma unroll
+  for (int it = 0; it < cg; ++it) {
+    Item nxt = cur;
+    if (it + 1 < cg) fetch(it + 1, nxt);                             // (warp-uniform: the shuffles inside are full-warp)
+    if (cur.vm & 16u) {
+      const f8 v0 = cur.v0.f(), v1 = cur.v1.f(), v2 = cur.v2.f(), v3 = cur.v3.f();
+      f8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {                                  // (nw, ne, sw, se; fused multiply-adds from zero)
+        float acc = fmaf(v0.v[k], cur.a, 0.f);
+        acc = fmaf(v1.v[k], cur.b, acc);
+        acc = fmaf(v2.v[k], cur.c, acc);
+        acc = fmaf(v3.v[k], cur.d, acc);
+        o.v[k] = acc;
+      }
+      st8(out + (int64_t)cur.pp * ldo + c0, o);
+    }
+    cur = nxt;
+  }
+}
+
+// blockDim multiple of 32; the cg (= C/8, power of two <= 32) threads of one pixel are adjacent
+// lanes, so the flow gradient is reduced with xor-shuffles.
+// 8 consecutive fp32 accumulations as two 128-bit vector reductions (red.global.add.v4.f32, sm_90+)
+__device__ __forceinline__ void atomic_add8(float* p, float w, const f8& g) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(w * g.v[0], w * g.v[1], w * g.v[2], w * g.v[3]));
+  atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(w * g.v[4], w * g.v[5], w * g.v[6], w * g.v[7]));
+}
+
+// 8 consecutive bf16 accumulations as ONE 128-bit packed reduction (red.global.add.noftz.v4.bf16x2): half the
+// L2 reduction operations of the fp32 form, which is what bounds the scatter (one 16-byte RED per L2 slice clock)
+__device__ __forceinline__ void atomic_add8(bf16* p, float w, const f8& g) {
+  uint32_t r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(w * g.v[2 * i], w * g.v[2 * i + 1]);
+    r[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
 // the same reductions for an already-weighted contribution vector
 __device__ __forceinline__ void red_add8(float* p, const f8& c) {
   atomicAdd(reinterpret_cast<float4*>(p), make_float4(c.v[0], c.v[1], c.v[2], c.v[3]));
@@ -313,7 +336,7 @@ __device__ __forceinline__ void red_add8(bf16* p, const f8& c) {
 // each: issue-bound at 68 % with the L2 reductions idle a third of the time): phase A one pixel per LANE, phase B the
 // lanes regrouped as (pixel, 8-channel vector) with the pixel's corner weights broadcast by shuffles; the flow
 // gradient is reduced over the pixel's lanes with xor-shuffles.
-template <typename T, typename AT>
+template <typename T, typename AT, int CGT>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restrict__ flow,
                 const T* __restrict__ dout, int64_t lddo, AT* __restrict__ dfeat, int64_t lddf,
@@ -342,7 +365,7 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
   // north-west / south-west targets of the next, so those contributions are carried in registers and leave as ONE
   // reduction per target and source row (2 per pixel and vector instead of 4: the scatter is bound by L2 reduction
   // operations, profiles/r01z_summary.md).  Carries that do not meet their successor are flushed on their own.
-  const int cg = C >> 3;
+  const int cg = CGT ? CGT : (C >> 3);
   const int c0 = (lane % cg) << 3;
   const int sub = lane / cg;
   const int pbase = p - lane;
@@ -376,6 +399,7 @@ warp_bwd_kernel(const T* __restrict__ feat, int64_t ldf_, const float* __restric
   };
   Item cur;
   fetch(0, cur);
+#pragma unroll
   for (int it = 0; it < cg; ++it) {
     Item nxt = cur;
     if (it + 1 < cg) fetch(it + 1, nxt);                             // (warp-uniform: the shuffles inside are full-warp)
@@ -515,9 +539,14 @@ NV_API int nervecl_warp_fwd(const void* feat, int64_t ldf, const float* flow, vo
   const int ppb = 256 / (C >> 3);
   if (cdiv(W, ppb) > 65535 || (int64_t)N * H > 0x7fffffff) return NERVECL_EUNSUPPORTED;
   if ((int64_t)N * H * W >= ((int64_t)1 << 31) - 64) return NERVECL_EUNSUPPORTED;
-  const unsigned blocks = (unsigned)cdiv((int64_t)N * H * W, 256);
-  NV_DISPATCH_DTYPE(dtype, E, (warp_fwd_kernel<E><<<blocks, 256, 0, as_stream(stream)>>>(
-                                  (const E*)feat, ldf, flow, (E*)out, ldo, N, H, W, C, inv_w, inv_h, div_mode, idx_out)));
+  const unsigned blocks = (unsigned)cdiv((int64_t)N * cdiv(H, WP_H) * cdiv(W, WP_W), 8);     // one warp per pixel patch
+  if (C == 64) {
+    NV_DISPATCH_DTYPE(dtype, E, (warp_fwd_kernel<E, 8><<<blocks, 256, 0, as_stream(stream)>>>(
+                                    (const E*)feat, ldf, flow, (E*)out, ldo, N, H, W, C, inv_w, inv_h, div_mode, idx_out)));
+  } else {
+    NV_DISPATCH_DTYPE(dtype, E, (warp_fwd_kernel<E, 0><<<blocks, 256, 0, as_stream(stream)>>>(
+                                    (const E*)feat, ldf, flow, (E*)out, ldo, N, H, W, C, inv_w, inv_h, div_mode, idx_out)));
+  }
   return launch_status();
 }
 
@@ -535,12 +564,17 @@ static int warp_bwd_launch(const void* feat, int64_t ldf, const float* flow, con
   if ((int64_t)N * H * W >= ((int64_t)1 << 31) - 64) return NERVECL_EUNSUPPORTED;
   const unsigned blocks = (unsigned)cdiv((int64_t)N * H * W, 256);
   if (dfeat_dtype == NERVECL_BF16) {
-    warp_bwd_kernel<bf16, bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)feat, ldf, flow, (const bf16*)dout, lddo,
-                                                                       (bf16*)dfeat, lddf, dflow, N, H, W, C, inv_w, inv_h,
-                                                                       div_mode);
+    if (C == 64)
+      warp_bwd_kernel<bf16, bf16, 8><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)feat, ldf, flow, (const bf16*)dout, lddo,
+                                                                            (bf16*)dfeat, lddf, dflow, N, H, W, C, inv_w, inv_h,
+                                                                            div_mode);
+    else
+      warp_bwd_kernel<bf16, bf16, 0><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)feat, ldf, flow, (const bf16*)dout, lddo,
+                                                                            (bf16*)dfeat, lddf, dflow, N, H, W, C, inv_w, inv_h,
+                                                                            div_mode);
     return launch_status();
   }
-  NV_DISPATCH_DTYPE(dtype, E, (warp_bwd_kernel<E, float><<<blocks, 256, 0, as_stream(stream)>>>(
+  NV_DISPATCH_DTYPE(dtype, E, (warp_bwd_kernel<E, float, 0><<<blocks, 256, 0, as_stream(stream)>>>(
                                   (const E*)feat, ldf, flow, (const E*)dout, lddo, (float*)dfeat, lddf, dflow, N, H, W, C,
                                   inv_w, inv_h, div_mode)));
   return launch_status();

@@ -131,31 +131,38 @@ corr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_wait(acc_full, accp);
       tc_fence_after();
       float res[NDISP];
-      // region row qy = 2q + s goes through slab (s & 1); step i reads slabs i (lanes 0-15) and i + 1 (lanes 16-31)
-      auto stage_row = [&](int s) {
+      // Region row 2q + s (24 accumulator columns, the same for every lane) is displacement row i = s of the lanes in tile
+      // row 2q and i = s - 1 of the lanes in tile row 2q + 1.  A lane needs its columns px .. px + 8: the 24 registers are
+      // shifted down by px with four select stages (8, 4, 2, 1) -- a lane-dependent register index without the
+      // shared-memory bounce of the first version, whose 1300 cycles per tile shared the shared-memory pipe with the
+      // tile's 64 KB of TMA writes and the MMAs' operand reads.
+      const bool s8 = px & 8, s4 = px & 4, s2 = px & 2, s1 = px & 1, row0 = pyl == 0;
+#pragma unroll
+      for (int s = 0; s <= ND; ++s) {
         const uint32_t col = (uint32_t)((2 * q + s) * RX);
-        uint32_t v[16], w[8];
-        tmem_ld16(lane_addr + col, v);
+        uint32_t lo[16], v[24];
+        tmem_ld16(lane_addr + col, lo);
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
                      : "r"(lane_addr + col + 16u)
                      : "memory");
         tmem_ld_wait();
-        float* dst = slab + (s & 1) * (RX * 32) + lane;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dst[c * 32] = __uint_as_float(v[c]);
+        for (int c = 0; c < 16; ++c) v[c] = lo[c];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[(16 + c) * 32] = __uint_as_float(w[c]);
-      };
-      stage_row(0);
+        for (int c = 0; c < 16; ++c) v[c] = s8 ? v[c + 8] : v[c];
 #pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        __syncwarp();                                  // readers of the slab about to be overwritten are done
-        stage_row(i + 1);
-        __syncwarp();
-        const float* src = slab + ((i + pyl) & 1) * (RX * 32) + px * 32 + lane;
+        for (int c = 0; c < 12; ++c) v[c] = s4 ? v[c + 4] : v[c];
 #pragma unroll
-        for (int j = 0; j < ND; ++j) res[i * ND + j] = src[j * 32] * inv_c;
+        for (int c = 0; c < 10; ++c) v[c] = s2 ? v[c + 2] : v[c];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) v[c] = s1 ? v[c + 1] : v[c];
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          const float r = __uint_as_float(v[j]) * inv_c;
+          if (s < ND) res[s * ND + j] = row0 ? r : res[s * ND + j];
+          if (s > 0) res[(s - 1) * ND + j] = row0 ? res[(s - 1) * ND + j] : r;
+        }
       }
       tc_fence_before();
       __syncwarp();
