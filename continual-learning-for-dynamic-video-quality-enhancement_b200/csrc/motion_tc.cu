@@ -17,6 +17,8 @@
 // register index i*9+j stays compile-time.  A thread then writes its pixel's 96 channels (81 + zero pad) as six 32-byte
 // stores.  Shared-memory bandwidth bounds the epilogue at ~1300 cycles per tile, the same order as the 64 KB of TMA
 // loads per tile, i.e. the kernel sits near the HBM roofline of its algorithmic bytes instead of 3-4x above it.
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -497,12 +499,13 @@ corr_transpose_kernel(const bf16* __restrict__ g, int64_t ldg, bf16* __restrict_
   // 384 pixels x 12 chunks = 4608 chunks = 18 per thread, requested six at a time before anything is stored (a plain
   // load-store loop pays one global-memory latency per chunk)
   constexpr int PER = RY * RX * 12 / GT_THREADS;       // 18
-  static_assert(PER * GT_THREADS == RY * RX * 12 && PER % 6 == 0, "chunk split");
+  constexpr int GB = 9;                                // chunks requested per round trip (two round trips per tile)
+  static_assert(PER * GT_THREADS == RY * RX * 12 && PER % GB == 0, "chunk split");
 #pragma unroll 1
-  for (int b = 0; b < PER; b += 6) {
-    uint4 u[6];
+  for (int b = 0; b < PER; b += GB) {
+    uint4 u[GB];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < GB; ++k) {
       const int e = threadIdx.x + (b + k) * GT_THREADS;
       const int rp = e / 12, c = e - rp * 12;
       const int ry = rp / RX, rx = rp - ry * RX;
@@ -511,7 +514,7 @@ corr_transpose_kernel(const bf16* __restrict__ g, int64_t ldg, bf16* __restrict_
       if (y >= 0 && y < H && x >= 0 && x < W) u[k] = __ldg(reinterpret_cast<const uint4*>(g + (((int64_t)n * H + y) * W + x) * ldg) + c);
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < GB; ++k) {
       const int e = threadIdx.x + (b + k) * GT_THREADS;
       const int rp = e / 12, c = e - rp * 12;
       uint32_t* dst = st + rp * GT_PITCH + c * 4;
@@ -524,21 +527,28 @@ corr_transpose_kernel(const bf16* __restrict__ g, int64_t ldg, bf16* __restrict_
   const int y = ty * TY + py, x = tx * TX + px;
   const uint16_t* sh = reinterpret_cast<const uint16_t*>(st);
   uint32_t o[24];
+  // (the two halves are whole warps: with `half` resolved per branch every displacement index below is a compile-time
+  //  constant -- the run-time form divided d by 9 for each of the 48 gathers)
+  const uint16_t* pix = sh + (py * RX + px) * (GT_PITCH * 2);
+  auto gather = [&](auto HALF) {
+    constexpr int hbase = decltype(HALF)::value * 48;
 #pragma unroll
-  for (int k = 0; k < 24; ++k) {
-    uint32_t word = 0;
+    for (int k = 0; k < 24; ++k) {
+      uint32_t word = 0;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int d = half * 48 + 2 * k + hf;                          // output channel i*9+j (d >= 81: zero padding)
-      uint16_t v = 0;
-      if (d < NDISP) {
-        const int i = d / ND, j = d - i * ND;
-        v = sh[((py + i) * RX + px + j) * (GT_PITCH * 2) + (NDISP - 1 - d)];
+      for (int hf = 0; hf < 2; ++hf) {
+        const int d = hbase + 2 * k + hf;                            // output channel i*9+j (d >= 81: zero padding)
+        uint16_t v = 0;
+        if (d < NDISP) {
+          const int i = d / ND, j = d - i * ND;
+          v = pix[(i * RX + j) * (GT_PITCH * 2) + (NDISP - 1 - d)];
+        }
+        word |= (uint32_t)v << (16 * hf);
       }
-      word |= (uint32_t)v << (16 * hf);
+      o[k] = word;
     }
-    o[k] = word;
-  }
+  };
+  if (half == 0) gather(std::integral_constant<int, 0>{}); else gather(std::integral_constant<int, 1>{});
   if (y < H && x < W) {
     uint4* dst = reinterpret_cast<uint4*>(gt + (((int64_t)n * H + y) * W + x) * ldt + half * 48);
 #pragma unroll
