@@ -184,6 +184,8 @@ class EnhancementEngine(nn.Module):
         B, T, C, H, W = video.shape
         per_call = max(1, batch_size)
         out: Optional[Tensor] = None
+        if self.super_resolution is not None and (self.frame_recovery is None or corruption_masks is None):
+            return self._enhance_video_sr_only(video, per_call, squeeze)
         for c, idx, frames_t in self._video_plan(T, per_call, video.device):
             n, length = idx.shape
             win = video[:, idx]                                           # (B, n, L, C, H, W): one device gather
@@ -196,6 +198,44 @@ class EnhancementEngine(nn.Module):
             if out is None:
                 out = torch.empty((B, T) + tuple(enh.shape[1:]), device=enh.device, dtype=enh.dtype)
             out[:, frames_t] = enh.view(n, B, *enh.shape[1:]).transpose(0, 1)
+        return out.squeeze(0) if squeeze else out
+
+    def _enhance_video_sr_only(self, video: Tensor, per_call: int, squeeze: bool) -> Tensor:
+        """``enhance_video`` when no recovery runs (no recovery network, or no masks): every frame's result is the SR
+        network on its SR window, and all those windows have the SAME shape -- the clipped ones are padded to
+        ``2 * sr_temporal_window + 1`` frames (:152-158) -- so the windows of ALL frames, edge frames included, go through
+        the network ``per_call`` at a time.  (Grouping by (window length, centre) as the general path must for the
+        recovery network gives every edge frame a network call of its own: 4 extra batch-1 calls per clip at T = 5.)
+        The window -> source-frame table is ``inference.sr_window_indices`` (pinned to the reference loop by
+        ``tests/golden/enhance_windows.npz``)."""
+        from ..inference import sr_window_indices
+        B, T, C, H, W = video.shape
+        light = isinstance(self.super_resolution, LightweightSuperResolution)
+        key = ("sr_only", T, str(video.device), self.config.recovery_temporal_window, self.config.sr_temporal_window)
+        cache = self.__dict__.setdefault("_video_plans", {})
+        if key not in cache:
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = sr_window_indices(T, self.config.sr_temporal_window,
+                                           self.config.recovery_temporal_window).to(video.device)
+        idx = cache[key]
+        strength = self._strength()
+        s = self.config.scale_factor
+        out: Optional[Tensor] = None
+        for t0 in range(0, T, per_call):
+            n = min(per_call, T - t0)
+            centre = video[:, t0:t0 + n].transpose(0, 1).reshape(n * B, C, H, W)      # the frames themselves (blend, lightweight)
+            if light:
+                sr = self.super_resolution(centre)
+            else:
+                win = video[:, idx[t0:t0 + n]]                                         # (B, n, L, C, H, W): one device gather
+                sr = self.super_resolution(win.transpose(0, 1).reshape(n * B, idx.shape[1], C, H, W))
+            if strength < 1.0:
+                sr = sr.clone()
+                _ops.nv.bicubic_blend(sr, centre.detach().float().contiguous(), s, float(strength))
+            if out is None:
+                out = torch.empty((B, T) + tuple(sr.shape[1:]), device=sr.device, dtype=sr.dtype)
+            out[:, t0:t0 + n] = sr.view(n, B, *sr.shape[1:]).transpose(0, 1)
         return out.squeeze(0) if squeeze else out
 
     # ------------------------------------------------------------------------------------------------------------

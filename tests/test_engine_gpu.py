@@ -148,6 +148,26 @@ def test_enhance_video_matches_reference_engine(batch_size):
     assert relerr(o3[..., ::2, ::2], torch.from_numpy(g["sronly/video_out"])) <= TOL
 
 
+def test_enhance_video_sr_only_path_equals_the_window_loop():
+    """The SR-only fast path (all frames' windows batched uniformly) == the reference's loop structure (one forward per
+    frame on its clipped window, `enhancement_engine.py:214-240`), including the strength blend and the lightweight net."""
+    from nerve_cl_b200.models import EnhancementConfig, EnhancementEngine
+    torch.manual_seed(5)
+    video = torch.rand(9, 3, 24, 40, device="cuda")
+    for light in (False, True):
+        eng = EnhancementEngine(EnhancementConfig(frame_recovery_enabled=False, sr_num_features=16, sr_num_residual_blocks=1,
+                                                  use_lightweight_sr=light)).cuda().eval()
+        eng.super_resolution.compute_dtype = torch.float32
+        for strength in (1.0, 0.6):
+            with torch.no_grad():
+                eng.enhancement_strength.fill_(strength)
+                fast = eng.enhance_video(video, batch_size=4)
+                loop = torch.stack([eng(video[a:b].unsqueeze(0), center_idx=c)["enhanced"][0]
+                                    for a, b, c in eng.window_table(video.shape[0])])
+            assert fast.shape == loop.shape
+            assert relerr(fast, loop) <= 1e-6, (light, strength)
+
+
 def test_engine_trains_through_the_sr_path():
     """train_continual.py's configuration: SR-only engine, loss on results['enhanced'], gradients reach the SR
     parameters (and only them), with and without the strength blend."""
