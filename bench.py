@@ -566,15 +566,30 @@ def run_native(args):
         mask5 = torch.zeros(n5, 1, 540, 960)
         mask5[::2, :, 100:300, 200:600] = 1
         mask5 = mask5.pin_memory()
-        out5 = torch.empty(n5, 3, 1080, 1920).pin_memory()
+        out5 = [torch.empty(n5, 3, 1080, 1920).pin_memory() for _ in range(2)]
+        d2h5 = {"k": 0}
 
         def pipe_step():
+            # the same user loop as cfg 3: clip k + 1 is enhanced while clip k's 398 MB of HR frames travel back
             v, m = clip5.to(dev, non_blocking=True), mask5.to(dev, non_blocking=True)
-            out5.copy_(eng5.enhance_video(v, m, batch_size=8), non_blocking=True)
+            hr = eng5.enhance_video(v, m, batch_size=8)
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                out5[d2h5["k"] & 1].copy_(hr, non_blocking=True)
+                hr.record_stream(d2h_stream)
+            d2h5["k"] += 1
+
+        def run_pipe():
+            for _ in range(max(args.steps // 2, 1)):
+                pipe_step()
+            torch.cuda.current_stream().wait_stream(d2h_stream)      # the last clip's frames are back before the clock stops
 
         for _ in range(max(args.warmup, 3)):
             pipe_step()
-        ms_c5 = timed(pipe_step, max(args.steps // 2, 1))
+        torch.cuda.synchronize()
+        ms_c5 = timed(run_pipe, 1)
         cfg5 = {"metric": "enhance_pipeline_frames_per_sec", "value": n5 * world * max(args.steps // 2, 1) / (ms_c5 / 1e3),
                 "unit": UNIT, "ms_per_clip": ms_c5 / max(args.steps // 2, 1), "frames_per_clip": n5,
                 "note": "EnhancementEngine.enhance_video: FrameRecoveryNet (4 reference frames, mask on every 2nd frame) + "
