@@ -19,6 +19,27 @@ def test_sr_window_indices_match_reference_enhance_video():
         assert np.array_equal(got, g[key]), key
 
 
+def test_sr_window_indices_equal_the_engine_forward_selection():
+    """The SR-only path of EnhancementEngine.enhance_video batches every frame through `sr_window_indices`; the general
+    path cuts the engine window (`window_table`) and lets `forward` slice / pad the SR frames out of it.  Same frames,
+    for every clip length and window configuration (host logic only: no GPU)."""
+    from nerve_cl_b200.inference import sr_window_indices
+    from nerve_cl_b200.models import EnhancementConfig, EnhancementEngine
+    for sr_w in (1, 2, 3):
+        for rec_w in (1, 2, 3):
+            eng = EnhancementEngine.__new__(EnhancementEngine)          # window_table only reads the config
+            eng.config = EnhancementConfig(sr_temporal_window=sr_w, recovery_temporal_window=rec_w)
+            for T in (1, 2, 3, 5, 8, 13):
+                idx = sr_window_indices(T, sr_w, rec_w)
+                want = 2 * sr_w + 1
+                assert idx.shape == (T, want)
+                for t, (start, end, c) in enumerate(eng.window_table(T)):
+                    s0, e0 = max(0, c - sr_w), min(end - start, c + sr_w + 1)      # EnhancementEngine.forward
+                    sel = list(range(start + s0, start + e0))
+                    sel += [sel[-1]] * (want - len(sel))
+                    assert idx[t].tolist() == sel, (sr_w, rec_w, T, t)
+
+
 @pytest.mark.gpu
 def test_enhance_video_batched_equals_per_frame_loop():
     from nerve_cl_b200.inference import enhance_video, sr_window_indices
